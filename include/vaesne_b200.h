@@ -1,0 +1,135 @@
+/* vaesne_b200.h — C ABI of the B200-native VAESNe hot path.
+ *
+ * The reference (YunyiShen/VAESNe-dev) is pure PyTorch and has no FFI; this header is the
+ * lower surface defined in SURVEY.md §8(b).  Each entry point names the reference code whose
+ * arithmetic it replaces (paths relative to /root/reference/package/VAESNe).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller unless the comment says "host";
+ *     kernels never allocate, free or synchronise; they enqueue on `stream` (a cudaStream_t
+ *     passed as void*), so the whole step can be captured into a CUDA graph;
+ *   - all float tensors are fp32, row-major; `ld*` are row strides in elements;
+ *   - return value 0 = ok, negative = error (see VAESNE_E*), message in vaesne_last_error();
+ *   - functions are re-entrant; the only global state is the thread-local error string;
+ *   - gradient outputs named d<W>, d<b>, dgamma, dbeta, dtable ACCUMULATE (atomicAdd) into
+ *     caller-zeroed buffers; dX / dR style outputs overwrite unless their *_acc flag is set;
+ *   - dropout: `seed` points to one uint64 on the device (so a captured graph can advance it),
+ *     `stream_id` separates the independent masks of one step; p_drop == 0 disables it.
+ *   - model_dim 32 / 4 heads / head_dim 8 (what every reference script uses) is the supported
+ *     geometry of the fused kernels; anything else returns VAESNE_EUNSUPPORTED.
+ */
+#ifndef VAESNE_B200_H
+#define VAESNE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VAESNE_B200_ABI_VERSION 1
+#define VAESNE_OK 0
+#define VAESNE_EBADSHAPE (-1)
+#define VAESNE_EUNSUPPORTED (-2)
+#define VAESNE_EALIGN (-3)
+#define VAESNE_ECUDA (-4)
+#define VAESNE_ENULL (-5)
+
+const char* vaesne_last_error(void);
+int vaesne_abi_version(void);
+int vaesne_is_emulated(void);   /* 1 only for the CPU test build under tests/emu */
+
+/* ---- token-wise linear (+activation | +dropout+residual+LayerNorm) --------------------------
+ * Y[T,N] = act((X [+ Xadd]) W^T + b)                      nn.Linear / MLPs  util_layers.py:9-34
+ * Y      = LayerNorm(R + dropout(X W^T + b))  when R != NULL (N must be 32)
+ *                                              TransformerBlock.forward util_layers.py:292,303,307
+ * act: 0 none, 1 ReLU, 2 GELU(erf) (nn.GELU, util_layers.py:277).  H (optional) receives the
+ * pre-activation, S (optional, [T,32]) the pre-LayerNorm sum; both are what the backward needs. */
+int vaesne_lin_fwd(const float* X, long long ldx, const float* Xadd, long long ldxa,
+                   int T, int K, int N, const float* W, const float* b, int act,
+                   float* H, long long ldh,
+                   const float* R, long long ldr, const float* gamma, const float* beta, float eps,
+                   float* S, float p_drop, const uint64_t* seed, uint32_t stream_id,
+                   float* Y, long long ldy, void* stream);
+
+/* Backward of the above.  S != NULL selects the LayerNorm path (dgamma/dbeta accumulate, dR gets
+ * the residual gradient).  A is the saved pre-activation (GELU) or output (ReLU).  dW/db accumulate. */
+int vaesne_lin_bwd(const float* dY, long long lddy, int T, int K, int N,
+                   const float* S, const float* gamma, float eps, float* dgamma, float* dbeta,
+                   float* dR, long long lddr, int dR_acc,
+                   float p_drop, const uint64_t* seed, uint32_t stream_id,
+                   int act, const float* A, long long lda,
+                   const float* X, long long ldx, const float* Xadd, long long ldxa,
+                   const float* W, float* dW, float* db,
+                   float* dX, long long lddx, int dX_acc, void* stream);
+
+/* ---- masked multi-head attention, 4 heads x head_dim 8 -------------------------------------
+ * nn.MultiheadAttention core (q*sqrt(1/8), QK^T, key-padding mask as -inf, softmax, dropout(P), PV)
+ * util_layers.py:289,297,301.  q/k/v/O are [N, L, ld] with head h at columns h*8..h*8+7 of the
+ * pointer passed.  mask is torch.bool storage [mask_rows, mask_len]; batch row n uses row
+ * n % mask_rows (K-sample / source replication, PhotometricVAE.py:191-197), key j >= mask_len is
+ * never masked (the appended phase token, SpectraLayers.py:129-131).  LSE is [N,4,Lq]. */
+int vaesne_attn_fwd(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
+                    int N, int Lq, int Lk, const unsigned char* mask, int mask_rows, int mask_len,
+                    float p_drop, const uint64_t* seed, uint32_t stream_id,
+                    float* O, long long ldo, float* LSE, void* stream);
+int vaesne_attn_bwd(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
+                    int N, int Lq, int Lk, const unsigned char* mask, int mask_rows, int mask_len,
+                    float p_drop, const uint64_t* seed, uint32_t stream_id,
+                    const float* O, long long ldo, const float* LSE, const float* dO, long long lddo,
+                    float* delta_ws /* [N,4,Lq] scratch */, float* dq, long long lddq, float* dk, long long lddk,
+                    float* dv, long long lddv, void* stream);
+
+/* ---- embeddings and data movement -----------------------------------------------------------
+ * sincos_feat: out[t, 0:nf] = sin(x[t]*div), out[t, nf:2nf] = cos(x[t]*div)   util_layers.py:125-129,142-146
+ * gather/scatter_rows: nn.Embedding(num_bands, 32) forward / weight gradient   PhotometricLayers.py:61,129
+ * expand_rows(_bwd): x.unsqueeze(0).expand(copies, ...) and its sum-backward   PhotometricVAE.py:191-197
+ * copy3d: strided block copy used for torch.cat along tokens                   SpectraLayers.py:59,128 */
+int vaesne_sincos_feat(const float* x, long long T, const float* div, int nf, float* out, long long ld, void* stream);
+int vaesne_gather_rows(const long long* idx, long long T, const float* table, int nrows, float* out, long long ld, int accumulate, void* stream);
+int vaesne_scatter_rows(const long long* idx, long long T, const float* dout, long long ld, float* dtable, int nrows, void* stream);
+int vaesne_expand_rows(const float* src, long long row_elems, long long Bs, int copies, float* dst, void* stream);
+int vaesne_expand_rows_bwd(const float* ddst, long long row_elems, long long Bs, int copies, float* dsrc, int accumulate, void* stream);
+int vaesne_copy3d(const float* src, long long sgs, long long srs, float* dst, long long dgs, long long drs,
+                  long long G, long long R, long long C, int accumulate, void* stream);
+
+/* ---- posterior heads, sampling, mixture-of-experts latent terms ------------------------------
+ * bott/noise/mu/s/dbott are HOST arrays of M device pointers.
+ * fwd: mu = bott[:, :T], s = softplus(bott[:, T:])   PhotometricVAE.py:53-54 / SpectraVAE.py:48-49
+ *      z[m,k,b] = rsample(mu_m, s_m; noise_m[k,b])   PhotometricVAE.py:162-163
+ *      lat[r,k,b] = sum log p(z_r) - (logsumexp_m sum log q_m(z_r) - log M)   losses.py:53-54
+ *      pi[r,k,b,m] = softmax_m of the expert log-densities (saved for the backward)
+ * bwd: gradients of everything above wrt the bottleneck tokens, plus an optional closed-form
+ *      KL(q||p) term with coefficient kl_coef (losses.py:21, torch/distributions/kl.py). */
+int vaesne_latent_fwd(int M, int K, int B, int T, int Z, const float* const* bott, const float* const* noise,
+                      const int* fam_post /* host */, int fam_prior, const float* pz_mu, const float* pz_s,
+                      float* z, float* const* mu, float* const* s, float* lat, float* pi, void* stream);
+int vaesne_latent_bwd(int M, int K, int B, int T, int Z, const float* const* bott, const float* const* noise,
+                      const int* fam_post /* host */, int fam_prior, const float* pz_mu, const float* pz_s,
+                      const float* dz, const float* dlat, const float* pi,
+                      const float* const* dmu_ext, const float* const* ds_ext, float kl_coef,
+                      float* const* dbott, void* stream);
+int vaesne_kl_fwd(const float* mu, const float* s, int fam, const float* pz_mu, const float* pz_s, int B, int TZ, float* kld, void* stream);
+
+/* ---- likelihood + objective reductions --------------------------------------------------------
+ * loglik: lpx[r,b] (+)= scaling * sum_l log p(x[b,l] | loc[r,b,l], 1 or scale_masked)   losses.py:20,55-57
+ * iwae_combine: lw = lat + lpx, obj = sum_b(logsumexp_r lw - log R), w = softmax_r lw    losses.py:60-62,93
+ * elbo_combine: obj = mean_{k,b} lpx - mean_b kld                                        losses.py:24 */
+int vaesne_loglik_fwd(const float* loc, const float* x, const unsigned char* mask, int R, int B, int L, int fam,
+                      float scale_masked, float scaling, float* lpx, int accumulate, void* stream);
+int vaesne_loglik_bwd(const float* loc, const float* x, const unsigned char* mask, int R, int B, int L, int fam,
+                      float scale_masked, float scaling, const float* coef, float gscale, float* dloc, void* stream);
+int vaesne_iwae_combine(const float* lat, const float* lpx, int R, int B, float* w, float* lw, float* obj, void* stream);
+int vaesne_elbo_combine(const float* lpx, const float* kld, int K, int B, float* obj, void* stream);
+
+/* ---- optimiser -----------------------------------------------------------------------------------
+ * torch.optim.AdamW over one flat buffer (cannon/test_photospectra.py:135); `step` is a device int
+ * advanced by vaesne_step_advance so the update is CUDA-graph replayable; grad_scale multiplies g
+ * first (1/world_size for mean-type objectives under data parallelism). */
+int vaesne_adamw_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, const int* step, float grad_scale, void* stream);
+int vaesne_step_advance(int* step, unsigned long long* seed, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAESNE_B200_H */

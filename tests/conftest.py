@@ -24,3 +24,16 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    """Route the product's native binding to the CPU emulator build of the same kernel sources."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    from VAESNe import _native
+    path = build_emu.build()
+    prev = (_native._lib, _native._emulated)
+    _native.use_library(path)
+    yield _native
+    _native._lib, _native._emulated = prev

@@ -1,0 +1,380 @@
+"""Op-level parity cases shared by the CPU-emulator tests and the GPU tests (test infrastructure).
+
+Each runner builds seeded inputs, calls the product's op wrapper (VAESNe._ops -> C ABI) on
+`device`, and compares with a plain torch reference of the same arithmetic evaluated in fp64.
+Tolerances: fp32 kernels vs fp64 truth, 1e-5 relative to the tensor scale unless stated."""
+import math
+import zlib
+
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_err
+from oracle import vaesne_oracle as O
+
+TOL = 2e-5
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _dev(t, device):
+    return t.to(device) if t is not None else None
+
+
+# ------------------------------------------------------------------------------------------------
+LIN_CASES = [
+    dict(id="32x32_none", T=200, K=32, N=32, act=0),
+    dict(id="32x96_none", T=130, K=32, N=96, act=0),
+    dict(id="96x32_relu", T=77, K=96, N=32, act=1),
+    dict(id="64x32_relu", T=129, K=64, N=32, act=1),
+    dict(id="32x32_gelu_H", T=150, K=32, N=32, act=2, H=True),
+    dict(id="1x32_none", T=140, K=1, N=32, act=0),
+    dict(id="4x32_relu", T=33, K=4, N=32, act=1),
+    dict(id="2x32_relu", T=33, K=2, N=32, act=1),
+    dict(id="32x1_none", T=260, K=32, N=1, act=0),
+    dict(id="32x4_none_xadd", T=50, K=32, N=4, act=0, xadd=True),
+    dict(id="32x2_none", T=50, K=32, N=2, act=0),
+    dict(id="16x8_none", T=20, K=16, N=8, act=0),
+    dict(id="16x128_relu", T=40, K=16, N=128, act=1),
+    dict(id="128x128_relu", T=70, K=128, N=128, act=1),
+    dict(id="128x5_none", T=70, K=128, N=5, act=0),
+    dict(id="32x32_ln", T=300, K=32, N=32, act=0, ln=True),
+    dict(id="32x32_ln_strided", T=65, K=32, N=32, act=0, ln=True, strided=True),
+    dict(id="32x64_strided_out", T=65, K=32, N=64, act=0, strided=True),
+]
+
+
+def run_lin_case(c, device):
+    from VAESNe import _ops as P
+    T, K, Nn, act = c["T"], c["K"], c["N"], c["act"]
+    g = _g(zlib.crc32(c["id"].encode()) % 10000)
+    X = torch.randn(T, K, generator=g)
+    Xadd = torch.randn(T, K, generator=g) if c.get("xadd") else None
+    W = torch.randn(Nn, K, generator=g) / math.sqrt(K)
+    b = torch.randn(Nn, generator=g) * 0.1
+    dY = torch.randn(T, Nn, generator=g)
+    ln = c.get("ln", False)
+    R = torch.randn(T, Nn, generator=g) if ln else None
+    gamma = (1 + 0.1 * torch.randn(Nn, generator=g)) if ln else None
+    beta = (0.1 * torch.randn(Nn, generator=g)) if ln else None
+
+    # fp64 reference
+    Xd, Wd, bd = X.double().requires_grad_(), W.double().requires_grad_(), b.double().requires_grad_()
+    Xa = Xadd.double() if Xadd is not None else None
+    lin = (Xd + Xa if Xa is not None else Xd) @ Wd.T + bd
+    if act == 1:
+        out = F.relu(lin)
+    elif act == 2:
+        out = F.gelu(lin)
+    else:
+        out = lin
+    refs = {}
+    if ln:
+        Rd, gd, bed = R.double().requires_grad_(), gamma.double().requires_grad_(), beta.double().requires_grad_()
+        S = Rd + out
+        out = F.layer_norm(S, (Nn,), gd, bed, 1e-5)
+        out.backward(dY.double())
+        refs.update(dR=Rd.grad, dgamma=gd.grad, dbeta=bed.grad, S=S.detach())
+    else:
+        out.backward(dY.double())
+    refs.update(Y=out.detach(), dX=Xd.grad, dW=Wd.grad, db=bd.grad, H=lin.detach())
+
+    # product
+    def strided(t, width):
+        buf = torch.zeros(t.shape[0], width, device=device)
+        view = buf[:, 5 - 1:4 + t.shape[1]] if False else buf[:, 4:4 + t.shape[1]]
+        view.copy_(t)
+        return view
+    st = c.get("strided", False)
+    Xc = strided(X.to(device), K + 8) if st else X.to(device)
+    Y = torch.zeros(T, Nn + 12, device=device)[:, 4:4 + Nn] if st else None
+    H = torch.empty(T, Nn, device=device) if c.get("H") else None
+    Sbuf = torch.empty(T, Nn, device=device) if ln else None
+    Y = P.lin_fwd(Xc, W.to(device), b.to(device), Xadd=_dev(Xadd, device), act=act, H=H, R=_dev(R, device), gamma=_dev(gamma, device),
+                  beta=_dev(beta, device), S=Sbuf, Y=Y)
+    assert rel_err(Y.cpu(), refs["Y"]) < TOL, ("Y", rel_err(Y.cpu(), refs["Y"]))
+    if H is not None:
+        assert rel_err(H.cpu(), refs["H"]) < TOL
+    if ln:
+        assert rel_err(Sbuf.cpu(), refs["S"]) < TOL
+
+    dW = torch.zeros(Nn, K, device=device); db = torch.zeros(Nn, device=device)
+    dX = torch.full((T, K), 0.5, device=device)       # accumulate mode on top of 0.5
+    kw = {}
+    if ln:
+        kw = dict(S=Sbuf, gamma=gamma.to(device), dgamma=torch.zeros(Nn, device=device), dbeta=torch.zeros(Nn, device=device),
+                  dR=torch.empty(T, Nn, device=device))
+    A = None
+    if act == 1:
+        A = Y
+    elif act == 2:
+        A = H
+    dYc = strided(dY.to(device), Nn + 8) if st else dY.to(device)
+    P.lin_bwd(dYc, Xc, W.to(device), Xadd=_dev(Xadd, device), act=act, A=A, dW=dW, db=db, dX=dX, dX_acc=True, **kw)
+    assert rel_err(dX.cpu() - 0.5, refs["dX"]) < TOL, ("dX", rel_err(dX.cpu() - 0.5, refs["dX"]))
+    assert rel_err(dW.cpu(), refs["dW"]) < TOL, ("dW", rel_err(dW.cpu(), refs["dW"]))
+    assert rel_err(db.cpu(), refs["db"]) < TOL
+    if ln:
+        assert rel_err(kw["dR"].cpu(), refs["dR"]) < TOL
+        assert rel_err(kw["dgamma"].cpu(), refs["dgamma"]) < TOL
+        assert rel_err(kw["dbeta"].cpu(), refs["dbeta"]) < TOL
+    # dX only (frozen weights) and overwrite mode
+    dX2 = torch.full((T, K), 7.0, device=device)
+    P.lin_bwd(dYc, None, W.to(device), act=act, A=A, dX=dX2, **({k: v for k, v in kw.items() if k in ("S", "gamma")}))
+    assert rel_err(dX2.cpu(), refs["dX"]) < TOL
+
+
+# ------------------------------------------------------------------------------------------------
+ATTN_CASES_SMALL = [
+    dict(id="self_8x8", N=3, Lq=8, Lk=8, mask=False, packed="qkv"),
+    dict(id="cross_8x61_mask", N=2, Lq=8, Lk=61, mask=True, mask_len=60, packed="q+kv"),
+    dict(id="self_60x60_mask_rowmod", N=4, Lq=60, Lk=60, mask=True, mask_rows=2, packed="qkv"),
+    dict(id="cross_60x4", N=2, Lq=60, Lk=4, mask=False, packed="q+kv"),
+    dict(id="cross_150x5", N=2, Lq=150, Lk=5, mask=False, packed="q+kv"),
+    dict(id="self_150x150_mask", N=2, Lq=150, Lk=150, mask=True, packed="qkv"),
+    dict(id="cross_8x200_mask", N=2, Lq=8, Lk=200, mask=True, mask_len=199, packed="q+kv"),
+]
+ATTN_CASES_FULL = ATTN_CASES_SMALL + [
+    dict(id="self_982_mask_rowmod", N=4, Lq=982, Lk=982, mask=True, mask_rows=2, packed="qkv"),
+    dict(id="self_983_masklen", N=2, Lq=983, Lk=983, mask=True, mask_len=982, packed="qkv"),
+    dict(id="cross_8x983", N=3, Lq=8, Lk=983, mask=True, mask_len=982, packed="q+kv"),
+    dict(id="cross_982x5", N=3, Lq=982, Lk=5, mask=False, packed="q+kv"),
+]
+
+
+def attn_reference(q, k, v, mask_full, dO):
+    """fp64 torch reference; q,k,v [N,L,32] (4 heads x 8); mask_full bool [N,Lk] or None."""
+    q = q.double().requires_grad_(); k = k.double().requires_grad_(); v = v.double().requires_grad_()
+    N, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+    qh = q.view(N, Lq, 4, 8).transpose(1, 2) * math.sqrt(1 / 8)
+    kh = k.view(N, Lk, 4, 8).transpose(1, 2)
+    vh = v.view(N, Lk, 4, 8).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2)
+    if mask_full is not None:
+        s = s.masked_fill(mask_full[:, None, None, :], float("-inf"))
+    lse = torch.logsumexp(s, -1)
+    o = (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(N, Lq, 32)
+    o.backward(dO.double())
+    return o.detach(), lse.detach(), q.grad, k.grad, v.grad
+
+
+def make_attn_inputs(c, device, scale=1.0):
+    g = _g(zlib.crc32(c["id"].encode()) % 10000)
+    N, Lq, Lk = c["N"], c["Lq"], c["Lk"]
+    if c["packed"] == "qkv":
+        qkv = torch.randn(N, Lq, 96, generator=g) * scale
+        q, k, v = qkv[..., :32], qkv[..., 32:64], qkv[..., 64:]
+        bufs = (qkv.to(device),)
+        qd, kd, vd = bufs[0][..., :32], bufs[0][..., 32:64], bufs[0][..., 64:]
+    else:
+        qb = torch.randn(N, Lq, 32, generator=g) * scale
+        kv = torch.randn(N, Lk, 64, generator=g) * scale
+        q, k, v = qb, kv[..., :32], kv[..., 32:]
+        bufs = (qb.to(device), kv.to(device))
+        qd, kd, vd = bufs[0], bufs[1][..., :32], bufs[1][..., 32:]
+    mask = mask_full = None
+    if c.get("mask"):
+        rows = c.get("mask_rows", N)
+        mlen = c.get("mask_len", Lk)
+        mask = torch.rand(rows, mlen, generator=g) < 0.3
+        mask[:, 0] = False
+        mask_full = torch.zeros(N, Lk, dtype=torch.bool)
+        mask_full[:, :mlen] = mask[torch.arange(N) % rows]
+    dO = torch.randn(N, Lq, 32, generator=g)
+    return (q, k, v, mask, mask_full, dO), (qd, kd, vd)
+
+
+def run_attn_case(c, device, fwd=None, bwd=None, tol=TOL, scale=1.0):
+    from VAESNe import _ops as P
+    fwd = fwd or P.attn_fwd
+    bwd = bwd or P.attn_bwd
+    (q, k, v, mask, mask_full, dO), (qd, kd, vd) = make_attn_inputs(c, device, scale)
+    o_ref, lse_ref, dq_ref, dk_ref, dv_ref = attn_reference(q, k, v, mask_full, dO)
+    md = mask.to(device) if mask is not None else None
+    Oo, LSE = fwd(qd, kd, vd, md)
+    assert rel_err(Oo.cpu(), o_ref) < tol, ("O", rel_err(Oo.cpu(), o_ref))
+    assert rel_err(LSE.cpu(), lse_ref) < tol, ("LSE", rel_err(LSE.cpu(), lse_ref))
+    if c["packed"] == "qkv":
+        dqkv = torch.zeros(c["N"], c["Lq"], 96, device=device)
+        dq, dk, dv = dqkv[..., :32], dqkv[..., 32:64], dqkv[..., 64:]
+    else:
+        dq = torch.zeros(c["N"], c["Lq"], 32, device=device)
+        dkv = torch.zeros(c["N"], c["Lk"], 64, device=device)
+        dk, dv = dkv[..., :32], dkv[..., 32:]
+    bwd(qd, kd, vd, md, Oo, LSE, dO.to(device), dq, dk, dv)
+    assert rel_err(dq.cpu(), dq_ref) < tol, ("dq", rel_err(dq.cpu(), dq_ref))
+    assert rel_err(dk.cpu(), dk_ref) < tol, ("dk", rel_err(dk.cpu(), dk_ref))
+    assert rel_err(dv.cpu(), dv_ref) < tol, ("dv", rel_err(dv.cpu(), dv_ref))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_misc_cases(device):
+    from VAESNe import _ops as P
+    g = _g(5)
+    # sincos features: same fp32 frequency table as the reference (util_layers.py:122,138)
+    x = torch.randn(37, generator=g) * 2
+    for step, nf in ((1, 32), (2, 16)):
+        div = O.div_term(32, step, torch.float32)
+        out = torch.zeros(37, 2 * nf + 8, device=device)
+        P.sincos_feat(x.to(device), div.to(device), out[:, 4:4 + 2 * nf])
+        a = x[:, None] * div
+        ref = torch.cat([torch.sin(a), torch.cos(a)], -1)
+        assert rel_err(out[:, 4:4 + 2 * nf].cpu(), ref) < 1e-6
+        assert out[:, :4].abs().sum() == 0 and out[:, 4 + 2 * nf:].abs().sum() == 0
+    # gather / scatter (bit-exact gather)
+    idx = torch.randint(0, 6, (5, 11), generator=g)
+    table = torch.randn(6, 32, generator=g)
+    out = torch.ones(55, 32, device=device)
+    P.gather_rows(idx.to(device), table.to(device), out, accumulate=True)
+    assert torch.equal(out.cpu(), 1 + table[idx.reshape(-1)])
+    P.gather_rows(idx.to(device), table.to(device), out, accumulate=False)
+    assert torch.equal(out.cpu(), table[idx.reshape(-1)])
+    dout = torch.randn(55, 32, generator=g)
+    dt = torch.zeros(6, 32, device=device)
+    P.scatter_rows(idx.to(device), dout.to(device), dt)
+    ref = torch.zeros(6, 32).index_add_(0, idx.reshape(-1), dout)
+    assert rel_err(dt.cpu(), ref) < 1e-6
+    # expand rows: r -> r % Bs  (K-sample replication, bit-exact) and its sum-backward
+    src = torch.randn(3, 7, 32, generator=g)
+    e = P.expand_rows(src.to(device), 4)
+    assert torch.equal(e.cpu(), src.unsqueeze(0).expand(4, 3, 7, 32).reshape(12, 7, 32))
+    de = torch.randn(12, 7, 32, generator=g)
+    ds = P.expand_rows_bwd(de.to(device), 3, 4)
+    assert rel_err(ds.cpu(), de.view(4, 3, 7, 32).sum(0)) < 1e-6
+    # token concat through copy3d: cat([a[G,4,32], b[G,1,32]], dim=1)
+    a = torch.randn(5, 4, 32, generator=g); b = torch.randn(5, 1, 32, generator=g)
+    dst = torch.zeros(5, 5, 32, device=device)
+    P.copy3d(a.to(device), 4 * 32, 32, dst, 5 * 32, 32, 5, 4, 32)
+    P.copy3d(b.to(device), 32, 32, dst, 5 * 32, 32, 5, 1, 32, dst_off=4 * 32)
+    assert torch.equal(dst.cpu(), torch.cat([a, b], 1))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_latent_case(fam, device):
+    from VAESNe import _ops as P
+    g = _g(9)
+    M, K, B, T, Z = 2, 3, 5, 4, 4
+    f = P.FAMILY[fam]
+    botts = [torch.randn(B, 2 * T, Z, generator=g) for _ in range(M)]
+    botts[0][0, T, 0] = 25.0     # softplus threshold branch
+    noises = [O.draw_noise(fam, (K, B, T, Z), generator=g) for _ in range(M)]
+    pz_mu = torch.randn(T, Z, generator=g) * 0.1
+    pz_s = 1 + 0.2 * torch.rand(T, Z, generator=g)
+    dz_ext = torch.randn(M, K, B, T, Z, generator=g)
+    dlat = torch.randn(M, K, B, generator=g)
+
+    bd = [b.double().requires_grad_() for b in botts]
+    mus = [b[:, :T] for b in bd]
+    ss = [F.softplus(b[:, T:]) for b in bd]
+    zs = [O.rsample(fam, mus[m][None], ss[m][None], noises[m].double()) for m in range(M)]
+    lat = []
+    for r in range(M):
+        lpz = O.log_prob(fam, zs[r], pz_mu.double(), pz_s.double()).sum((-1, -2))
+        lq = O.log_mean_exp(torch.stack([O.log_prob(fam, zs[r], mus[m], ss[m]).sum((-1, -2)) for m in range(M)]))
+        lat.append(lpz - lq)
+    lat = torch.stack(lat)
+    zall = torch.stack(zs)
+    kl = sum(O.kl(fam, mus[m], ss[m], fam, pz_mu.double(), pz_s.double()).sum() for m in range(M))
+    total = (zall * dz_ext.double()).sum() + (lat * dlat.double()).sum() + 0.37 * kl
+    total.backward()
+
+    bt = [b.to(device) for b in botts]; nt = [n.to(device) for n in noises]
+    z, mu_o, s_o, lat_o, pi = P.latent_fwd(bt, nt, [f] * M, T, f, pz_mu.to(device), pz_s.to(device), want_lat=True)
+    assert rel_err(z.cpu(), zall.detach()) < TOL
+    assert rel_err(lat_o.cpu(), lat.detach()) < TOL
+    for m in range(M):
+        assert rel_err(mu_o[m].cpu(), mus[m].detach()) < TOL and rel_err(s_o[m].cpu(), ss[m].detach()) < TOL
+    db = P.latent_bwd(bt, nt, [f] * M, T, f, pz_mu.to(device), pz_s.to(device), dz_ext.to(device), dlat.to(device), pi, kl_coef=0.37)
+    for m in range(M):
+        assert rel_err(db[m].cpu(), bd[m].grad) < 5e-5, rel_err(db[m].cpu(), bd[m].grad)
+    kld = P.kl_fwd(mu_o[0], s_o[0], f, pz_mu.to(device), pz_s.to(device))
+    assert rel_err(kld.cpu(), O.kl(fam, mus[0], ss[0], fam, pz_mu.double(), pz_s.double()).sum((-1, -2)).detach()) < TOL
+
+
+def run_loglik_case(fam, device):
+    from VAESNe import _ops as P
+    g = _g(10)
+    R, B, L = 4, 3, 75
+    f = P.FAMILY[fam]
+    loc = torch.randn(R, B, L, generator=g)
+    x = torch.randn(B, L, generator=g)
+    mask = torch.rand(B, L, generator=g) < 0.3
+    big = P.masked_scale(1e10)
+    lat = torch.randn(R, B, generator=g)
+    ld = loc.double().requires_grad_()
+    scale = torch.where(mask, torch.tensor(big, dtype=torch.float64), torch.tensor(1.0, dtype=torch.float64))
+    lpx = (O.log_prob(fam, x.double()[None], ld, scale[None]) * 1.7).sum(-1)
+    lw = lat.double() + lpx
+    obj = O.log_mean_exp(lw).sum()
+    obj.backward()
+    lpx_o = torch.zeros(R, B, device=device)
+    P.loglik_fwd(loc.to(device), x.to(device), mask.to(device), f, big, 1.7, lpx_o, False)
+    assert rel_err(lpx_o.cpu(), lpx.detach()) < TOL
+    o, w, lw_o = P.iwae_combine(lat.to(device), lpx_o, want_lw=True)
+    assert abs(o.item() - obj.item()) < 1e-5 * abs(obj.item())
+    assert rel_err(lw_o.cpu(), lw.detach()) < TOL
+    dloc = P.loglik_bwd(loc.to(device), x.to(device), mask.to(device), f, big, 1.7, w, 1.0)
+    # the softmax weights inherit fp32 round-off of lpx (~|lpx|*6e-8 absolute in the exponent)
+    assert rel_err(dloc.cpu(), ld.grad) < 5e-4, rel_err(dloc.cpu(), ld.grad)
+    # masked-point constants
+    if fam == "laplace":
+        one = torch.zeros(1, 1, 4, device=device)
+        xm = torch.zeros(1, 4, device=device)
+        mk = torch.tensor([[True, True, False, False]], device=device)
+        out = torch.zeros(1, 1, device=device)
+        P.loglik_fwd(one, xm, mk, 0, P.masked_scale(1e8), 1.0, out, False)
+        assert abs(out.item() - (2 * -19.113827924512312 + 2 * -math.log(2))) < 1e-4
+    # elbo combine
+    kld = torch.rand(B, generator=g)
+    e = P.elbo_combine(lpx_o, kld.to(device))
+    assert abs(e.item() - (lpx.detach().mean() - kld.double().mean()).item()) < 1e-5 * abs(lpx.mean().item())
+
+
+def run_dropout_case(device):
+    """p = 0.1 masks: keep-rate, unbiasedness, fwd/bwd mask consistency, stream independence."""
+    from VAESNe import _ops as P
+    T = 4096
+    seed = torch.tensor([123456789], dtype=torch.int64, device=device)
+    X = torch.ones(T, 32, device=device)
+    W = torch.eye(32, device=device); b = torch.zeros(32, device=device)
+    R = torch.zeros(T, 32, device=device)
+    g1 = torch.ones(32, device=device); b0 = torch.zeros(32, device=device)
+    S = torch.empty(T, 32, device=device)
+    P.lin_fwd(X, W, b, R=R, gamma=g1, beta=b0, S=S, drop=P.Drop(0.1, seed, 3))
+    keep = (S != 0).float().mean().item()
+    assert abs(keep - 0.9) < 0.005, keep
+    assert abs(S.mean().item() - 1.0) < 0.01
+    vals = torch.unique(S)
+    assert len(vals) == 2 and abs(vals.max().item() - 1 / 0.9) < 1e-3
+    S2 = torch.empty(T, 32, device=device)
+    P.lin_fwd(X, W, b, R=R, gamma=g1, beta=b0, S=S2, drop=P.Drop(0.1, seed, 4))
+    assert ((S != 0) != (S2 != 0)).float().mean().item() > 0.1       # different stream -> different mask
+    S3 = torch.empty(T, 32, device=device)
+    P.lin_fwd(X, W, b, R=R, gamma=g1, beta=b0, S=S3, drop=P.Drop(0.1, seed, 3))
+    assert torch.equal(S, S3)                                           # deterministic given (seed, stream)
+    # attention: rows of P still sum to 1 before dropout; output mean preserved
+    g = _g(3)
+    qkv = torch.randn(2, 200, 96, generator=g).to(device)
+    v1 = torch.ones(2, 200, 32, device=device)
+    Oo, _ = P.attn_fwd(qkv[..., :32], qkv[..., 32:64], v1, None, P.Drop(0.1, seed, 9))
+    assert abs(Oo.mean().item() - 1.0) < 0.01
+    assert Oo.std().item() > 1e-3
+
+
+def run_adamw_case(device):
+    from VAESNe import _ops as P
+    g = _g(4)
+    n = 1000
+    p0 = torch.randn(n, generator=g); grads = [torch.randn(n, generator=g) for _ in range(3)]
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-2, weight_decay=0.01)
+    for gr in grads:
+        ref.grad = gr.clone(); opt.step()
+    p = p0.clone().to(device); m = torch.zeros(n, device=device); v = torch.zeros(n, device=device)
+    step = torch.zeros(1, dtype=torch.int32, device=device)
+    for gr in grads:
+        P.step_advance(step, None)
+        P.adamw_flat(p, gr.to(device), m, v, 1e-2, 0.9, 0.999, 1e-8, 0.01, step)
+    assert rel_err(p.cpu(), ref.detach()) < 1e-5

@@ -1,0 +1,253 @@
+"""Tensor-level wrappers over the C ABI: argument checking, output allocation, pointer plumbing.
+
+No arithmetic happens here; every function enqueues one (or two) kernels of the native library on
+torch's current stream.  2-D operands may be row-strided views (``stride(1) == 1``), which is how
+column slices of concatenated feature buffers and packed q|k|v projections are addressed.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _native as N
+
+LN_EPS = 1e-5
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+FAMILY = {"laplace": 0, "normal": 1}
+
+
+class Drop:
+    """One dropout mask of the step: probability, device seed cell, and a stream id."""
+    __slots__ = ("p", "seed", "sid")
+
+    def __init__(self, p: float, seed: Optional[torch.Tensor], sid: int):
+        self.p = float(p) if seed is not None else 0.0
+        self.seed = seed
+        self.sid = int(sid) & 0xFFFFFFFF
+
+
+NO_DROP = Drop(0.0, None, 0)
+
+
+def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    return t
+
+
+def _rows(t: Optional[torch.Tensor], name: str):
+    """(ptr, ld) of a row-strided 2-D view."""
+    if t is None:
+        return 0, 0
+    _f32(t, name)
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError(f"{name}: need a 2-D tensor with unit inner stride, got shape {tuple(t.shape)} strides {t.stride()}")
+    return t.data_ptr(), (t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]))
+
+
+def _c(t: Optional[torch.Tensor], name: str):
+    if t is None:
+        return 0
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: must be contiguous")
+    return t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+def lin_fwd(X, W, b, *, Xadd=None, act=ACT_NONE, H=None, R=None, gamma=None, beta=None, S=None,
+            drop: Drop = NO_DROP, Y=None):
+    T, K = X.shape
+    Nn = W.shape[0]
+    if W.shape[1] != K:
+        raise ValueError(f"lin_fwd: X is [*, {K}] but W is {tuple(W.shape)}")
+    if Y is None:
+        Y = torch.empty(T, Nn, device=X.device, dtype=torch.float32)
+    xp, ldx = _rows(X, "X"); ap, lda = _rows(Xadd, "Xadd"); hp, ldh = _rows(H, "H"); rp, ldr = _rows(R, "R"); yp, ldy = _rows(Y, "Y")
+    N.check(N.lib().vaesne_lin_fwd(xp, ldx, ap, lda, T, K, Nn, _c(W, "W"), _c(b, "b"), act, hp, ldh, rp, ldr,
+                                   _c(gamma, "gamma"), _c(beta, "beta"), LN_EPS, _c(S, "S"),
+                                   drop.p, N.ptr(drop.seed), drop.sid, yp, ldy, N.stream_of(X)))
+    return Y
+
+
+def lin_bwd(dY, X, W, *, Xadd=None, S=None, gamma=None, dgamma=None, dbeta=None, dR=None, dR_acc=False,
+            drop: Drop = NO_DROP, act=ACT_NONE, A=None, dW=None, db=None, dX=None, dX_acc=False):
+    T, Nn = dY.shape
+    K = W.shape[1]
+    dyp, lddy = _rows(dY, "dY"); xp, ldx = _rows(X, "X"); xap, ldxa = _rows(Xadd, "Xadd")
+    ap, lda = _rows(A, "A"); drp, lddr = _rows(dR, "dR"); dxp, lddx = _rows(dX, "dX")
+    N.check(N.lib().vaesne_lin_bwd(dyp, lddy, T, K, Nn, _c(S, "S"), _c(gamma, "gamma"), LN_EPS, _c(dgamma, "dgamma"), _c(dbeta, "dbeta"),
+                                   drp, lddr, int(dR_acc), drop.p, N.ptr(drop.seed), drop.sid, act, ap, lda,
+                                   xp, ldx, xap, ldxa, _c(W, "W"), _c(dW, "dW"), _c(db, "db"), dxp, lddx, int(dX_acc), N.stream_of(dY)))
+
+
+# ------------------------------------------------------------------------------------------------
+def _attn_operand(t: torch.Tensor, name: str):
+    """[N, L, C] view with unit inner stride and token stride ld; batch stride must be L*ld."""
+    _f32(t, name)
+    if t.dim() != 3 or t.stride(2) != 1:
+        raise ValueError(f"{name}: need [N, L, C] with unit inner stride")
+    ld = t.stride(1)
+    if t.shape[0] > 1 and t.stride(0) != t.shape[1] * ld:
+        raise ValueError(f"{name}: batch stride {t.stride(0)} != L*ld {t.shape[1] * ld}")
+    return t.data_ptr(), ld
+
+
+def _mask_args(mask: Optional[torch.Tensor]):
+    if mask is None:
+        return 0, 1, 0
+    if mask.dtype != torch.bool or mask.dim() != 2 or not mask.is_contiguous():
+        raise ValueError("key_padding_mask must be a contiguous 2-D torch.bool tensor")
+    return mask.data_ptr(), mask.shape[0], mask.shape[1]
+
+
+def attn_fwd(q, k, v, mask, drop: Drop = NO_DROP):
+    """q [N,Lq,32] view, k/v [N,Lk,32] views -> O [N,Lq,32], LSE [N,4,Lq]."""
+    Nb, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+    O = torch.empty(Nb, Lq, 32, device=q.device, dtype=torch.float32)
+    LSE = torch.empty(Nb, 4, Lq, device=q.device, dtype=torch.float32)
+    qp, ldq = _attn_operand(q, "q"); kp, ldk = _attn_operand(k, "k"); vp, ldv = _attn_operand(v, "v")
+    mp, mrows, mlen = _mask_args(mask)
+    N.check(N.lib().vaesne_attn_fwd(qp, ldq, kp, ldk, vp, ldv, Nb, Lq, Lk, mp, mrows, mlen, drop.p, N.ptr(drop.seed), drop.sid,
+                                    O.data_ptr(), 32, LSE.data_ptr(), N.stream_of(q)))
+    return O, LSE
+
+
+def attn_bwd(q, k, v, mask, O, LSE, dO, dq, dk, dv, drop: Drop = NO_DROP):
+    """Writes dq/dk/dv (views shaped like q/k/v)."""
+    Nb, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+    qp, ldq = _attn_operand(q, "q"); kp, ldk = _attn_operand(k, "k"); vp, ldv = _attn_operand(v, "v")
+    dqp, lddq = _attn_operand(dq, "dq"); dkp, lddk = _attn_operand(dk, "dk"); dvp, lddv = _attn_operand(dv, "dv")
+    dop, lddo = _attn_operand(dO, "dO")
+    mp, mrows, mlen = _mask_args(mask)
+    ws = torch.empty(Nb, 4, Lq, device=q.device, dtype=torch.float32)
+    N.check(N.lib().vaesne_attn_bwd(qp, ldq, kp, ldk, vp, ldv, Nb, Lq, Lk, mp, mrows, mlen, drop.p, N.ptr(drop.seed), drop.sid,
+                                    _c(O, "O"), 32, _c(LSE, "LSE"), dop, lddo, ws.data_ptr(), dqp, lddq, dkp, lddk, dvp, lddv,
+                                    N.stream_of(q)))
+
+
+# ------------------------------------------------------------------------------------------------
+def sincos_feat(x: torch.Tensor, div: torch.Tensor, out: torch.Tensor):
+    """x [T] -> out[:, 0:2*nf] (row-strided view)."""
+    op, ld = _rows(out, "out")
+    N.check(N.lib().vaesne_sincos_feat(_c(_f32(x, "x"), "x"), x.numel(), _c(div, "div"), div.numel(), op, ld, N.stream_of(x)))
+
+
+def gather_rows(idx: torch.Tensor, table: torch.Tensor, out: torch.Tensor, accumulate=False):
+    if idx.dtype != torch.int64:
+        raise TypeError("band indices must be int64")
+    op, ld = _rows(out, "out")
+    N.check(N.lib().vaesne_gather_rows(_c(idx, "idx"), idx.numel(), _c(table, "table"), table.shape[0], op, ld, int(accumulate), N.stream_of(out)))
+
+
+def scatter_rows(idx: torch.Tensor, dout: torch.Tensor, dtable: torch.Tensor):
+    dp, ld = _rows(dout, "dout")
+    N.check(N.lib().vaesne_scatter_rows(_c(idx, "idx"), idx.numel(), dp, ld, _c(dtable, "dtable"), dtable.shape[0], N.stream_of(dout)))
+
+
+def expand_rows(src: torch.Tensor, copies: int) -> torch.Tensor:
+    """[Bs, ...] -> [copies*Bs, ...] with row r reading source row r % Bs."""
+    Bs = src.shape[0]
+    dst = torch.empty((copies * Bs,) + tuple(src.shape[1:]), device=src.device, dtype=torch.float32)
+    row = src.numel() // max(Bs, 1)
+    N.check(N.lib().vaesne_expand_rows(_c(_f32(src, "src"), "src"), row, Bs, copies, dst.data_ptr(), N.stream_of(src)))
+    return dst
+
+
+def expand_rows_bwd(ddst: torch.Tensor, Bs: int, copies: int, dsrc: Optional[torch.Tensor] = None, accumulate=False) -> torch.Tensor:
+    row = ddst.numel() // max(Bs * copies, 1)
+    if dsrc is None:
+        dsrc = torch.empty((Bs,) + tuple(ddst.shape[1:]), device=ddst.device, dtype=torch.float32)
+    N.check(N.lib().vaesne_expand_rows_bwd(_c(ddst, "ddst"), row, Bs, copies, _c(dsrc, "dsrc"), int(accumulate), N.stream_of(ddst)))
+    return dsrc
+
+
+def copy3d(src, sgs, srs, dst, dgs, drs, G, R, Cc, accumulate=False, src_off=0, dst_off=0):
+    N.check(N.lib().vaesne_copy3d(src.data_ptr() + 4 * src_off, sgs, srs, dst.data_ptr() + 4 * dst_off, dgs, drs, G, R, Cc,
+                                  int(accumulate), N.stream_of(src)))
+
+
+# ------------------------------------------------------------------------------------------------
+def latent_fwd(botts: Sequence[torch.Tensor], noises: Sequence[torch.Tensor], fams: Sequence[int], T: int,
+               fam_prior: int = 0, pz_mu=None, pz_s=None, want_lat=False):
+    M = len(botts)
+    B, twoT, Z = botts[0].shape
+    K = noises[0].shape[0]
+    dev = botts[0].device
+    z = torch.empty(M, K, B, T, Z, device=dev, dtype=torch.float32)
+    mus = [torch.empty(B, T, Z, device=dev, dtype=torch.float32) for _ in range(M)]
+    ss = [torch.empty(B, T, Z, device=dev, dtype=torch.float32) for _ in range(M)]
+    lat = torch.empty(M, K, B, device=dev, dtype=torch.float32) if want_lat else None
+    pi = torch.empty(M, K, B, M, device=dev, dtype=torch.float32) if want_lat else None
+    for t in list(botts) + list(noises):
+        _c(_f32(t, "latent input"), "latent input")
+    bt, nt, mt, st, ft = N.ptr_table(botts), N.ptr_table(noises), N.ptr_table(mus), N.ptr_table(ss), N.int_table(fams)
+    N.check(N.lib().vaesne_latent_fwd(M, K, B, T, Z, bt, nt, ft, fam_prior, N.ptr(pz_mu), N.ptr(pz_s), z.data_ptr(), mt, st,
+                                      N.ptr(lat), N.ptr(pi), N.stream_of(z)))
+    return z, mus, ss, lat, pi
+
+
+def latent_bwd(botts, noises, fams, T, fam_prior, pz_mu, pz_s, dz, dlat, pi, dmu_ext=None, ds_ext=None, kl_coef=0.0):
+    M = len(botts)
+    B, twoT, Z = botts[0].shape
+    K = noises[0].shape[0]
+    dbotts = [torch.empty_like(b) for b in botts]
+    bt, nt, ft, dt = N.ptr_table(botts), N.ptr_table(noises), N.int_table(fams), N.ptr_table(dbotts)
+    me = N.ptr_table(dmu_ext) if dmu_ext is not None else None
+    se = N.ptr_table(ds_ext) if ds_ext is not None else None
+    N.check(N.lib().vaesne_latent_bwd(M, K, B, T, Z, bt, nt, ft, fam_prior, N.ptr(pz_mu), N.ptr(pz_s), N.ptr(dz), N.ptr(dlat), N.ptr(pi),
+                                      me, se, float(kl_coef), dt, N.stream_of(botts[0])))
+    return dbotts
+
+
+def kl_fwd(mu, s, fam, pz_mu, pz_s):
+    B = mu.shape[0]
+    kld = torch.empty(B, device=mu.device, dtype=torch.float32)
+    N.check(N.lib().vaesne_kl_fwd(_c(mu, "mu"), _c(s, "s"), fam, _c(pz_mu, "pz_mu"), _c(pz_s, "pz_s"), B, mu[0].numel(), kld.data_ptr(), N.stream_of(mu)))
+    return kld
+
+
+def loglik_fwd(loc, x, mask, fam, scale_masked, scaling, lpx, accumulate):
+    """loc [R,B,L], x [B,L], mask bool [B,L] -> lpx [R,B]."""
+    R, B, L = loc.shape
+    N.check(N.lib().vaesne_loglik_fwd(_c(loc, "loc"), _c(_f32(x, "x"), "x"), _c(mask, "mask"), R, B, L, fam, float(scale_masked), float(scaling),
+                                      _c(lpx, "lpx"), int(accumulate), N.stream_of(loc)))
+
+
+def loglik_bwd(loc, x, mask, fam, scale_masked, scaling, coef, gscale):
+    R, B, L = loc.shape
+    dloc = torch.empty_like(loc)
+    N.check(N.lib().vaesne_loglik_bwd(_c(loc, "loc"), _c(x, "x"), _c(mask, "mask"), R, B, L, fam, float(scale_masked), float(scaling),
+                                      _c(coef, "coef"), float(gscale), dloc.data_ptr(), N.stream_of(loc)))
+    return dloc
+
+
+def iwae_combine(lat, lpx, want_lw=False):
+    R, B = lpx.shape
+    w = torch.empty_like(lpx)
+    lw = torch.empty_like(lpx) if want_lw else None
+    obj = torch.empty((), device=lpx.device, dtype=torch.float32)
+    N.check(N.lib().vaesne_iwae_combine(N.ptr(lat), _c(lpx, "lpx"), R, B, w.data_ptr(), N.ptr(lw), obj.data_ptr(), N.stream_of(lpx)))
+    return obj, w, lw
+
+
+def elbo_combine(lpx, kld):
+    K, B = lpx.shape
+    obj = torch.empty((), device=lpx.device, dtype=torch.float32)
+    N.check(N.lib().vaesne_elbo_combine(_c(lpx, "lpx"), _c(kld, "kld"), K, B, obj.data_ptr(), N.stream_of(lpx)))
+    return obj
+
+
+def adamw_flat(p, g, m, v, lr, b1, b2, eps, wd, step, grad_scale=1.0):
+    N.check(N.lib().vaesne_adamw_flat(_c(p, "p"), _c(g, "g"), _c(m, "m"), _c(v, "v"), p.numel(), lr, b1, b2, eps, wd,
+                                      _c(step, "step"), float(grad_scale), N.stream_of(p)))
+
+
+def step_advance(step, seed):
+    t = step if step is not None else seed
+    N.check(N.lib().vaesne_step_advance(N.ptr(step), N.ptr(seed), N.stream_of(t)))
+
+
+def masked_scale(kind_big: float) -> float:
+    """fp32 value of ``1 + big`` — what ``torch.ones_like(x) + big*mask`` holds on masked entries."""
+    return float(torch.tensor(1.0, dtype=torch.float32) + torch.tensor(kind_big, dtype=torch.float32))

@@ -117,7 +117,13 @@ int vaesne_kl_fwd(const float* mu, const float* s, int fam, const float* pz_mu, 
 int vaesne_loglik_fwd(const float* loc, const float* x, const unsigned char* mask, int R, int B, int L, int fam,
                       float scale_masked, float scaling, float* lpx, int accumulate, void* stream);
 int vaesne_loglik_bwd(const float* loc, const float* x, const unsigned char* mask, int R, int B, int L, int fam,
-                      float scale_masked, float scaling, const float* coef, float gscale, float* dloc, void* stream);
+                      float scale_masked, float scaling, const float* coef, float gscale, const float* gptr /* device scalar, nullable */,
+                      float* dloc, void* stream);
+/* gradient of coef * (*gptr) * KL(q||p) wrt (mu, s): closed forms of torch/distributions/kl.py:330-338,468-471 */
+int vaesne_kl_bwd(const float* mu, const float* s, int fam, const float* pz_mu, const float* pz_s, int B, int TZ,
+                  float coef, const float* gptr, float* dmu, float* ds, void* stream);
+/* dst = mult * (*gptr) * src — applies the upstream scalar gradient without a host read-back */
+int vaesne_scale(const float* src, long long n, float mult, const float* gptr, float* dst, void* stream);
 int vaesne_iwae_combine(const float* lat, const float* lpx, int R, int B, float* w, float* lw, float* obj, void* stream);
 int vaesne_elbo_combine(const float* lpx, const float* kld, int K, int B, float* obj, void* stream);
 
@@ -128,6 +134,9 @@ int vaesne_elbo_combine(const float* lpx, const float* kld, int K, int B, float*
 int vaesne_adamw_flat(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                       float eps, float weight_decay, const int* step, float grad_scale, void* stream);
 int vaesne_step_advance(int* step, unsigned long long* seed, void* stream);
+/* Dropout seed management: *cell = lcg(*cell), *out = *cell.  nn.Dropout / MHA dropout draw from torch's
+ * global Philox stream (util_layers.py:265-271,283); here every forward call takes one fresh 64-bit seed. */
+int vaesne_seed_next(unsigned long long* cell, unsigned long long* out, void* stream);
 
 #ifdef __cplusplus
 }

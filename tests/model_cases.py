@@ -1,0 +1,159 @@
+"""End-to-end parity cases against the live-reference goldens, shared by the CPU-emulator tests and
+the GPU tests (test infrastructure).  Tolerances are stated per case; the goldens are fp32 reference
+outputs, so the bound is fp32 round-off amplified through 4 post-LN layers (never looser than the
+1e-3 the north star allows for the fp32/TF32 path)."""
+import torch
+import torch.distributions as dist
+
+from helpers import load_golden, golden_params, golden_x, golden_grads, rel_err
+
+FWD_TOL = 2e-4
+GRAD_TOL = 1e-3
+
+
+def _to(x, device):
+    return tuple(t.to(device) for t in x)
+
+
+def _check_grads(model, g, tol=GRAD_TOL, strip=""):
+    want = golden_grads(g)
+    worst = (0.0, None)
+    for n, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        assert p.grad is not None, f"no grad for {n}"
+        e = rel_err(p.grad.cpu(), want[n])
+        if e > worst[0]:
+            worst = (e, n)
+    assert worst[0] < tol, worst
+    return worst
+
+
+def run_elbo_case(name, device):
+    from VAESNe import _noise
+    from VAESNe.PhotometricVAE import PhotometricVAE
+    from VAESNe.SpectraVAE import SpectraVAE
+    from VAESNe.losses import elbo
+    g = load_golden(name)
+    if name == "photo_elbo":
+        m = PhotometricVAE(num_bands=6, latent_len=4, latent_dim=2, model_dim=32, num_heads=4, ff_dim=32, num_layers=4,
+                           dropout=0.0, selfattn=False, beta=0.5)
+    else:
+        m = SpectraVAE(latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=4, dropout=0.0,
+                       selfattn=False, beta=1.0, concat=True)
+    m.load_state_dict(golden_params(g))
+    m.to(device).train()
+    x = _to(golden_x(g, "x"), device)
+    u = torch.from_numpy(g["u"])
+    _noise.clear(); _noise.inject([u])
+    loss = elbo(m, x, K=1)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < FWD_TOL * abs(float(g["loss"])), (loss.item(), float(g["loss"]))
+    worst = _check_grads(m, g)
+    # forward API: distributions + samples
+    _noise.inject([u])
+    with torch.no_grad():
+        qz, px, zs = m(x, 1)
+    assert rel_err(qz.loc.cpu(), g["mu"]) < FWD_TOL and rel_err(qz.scale.cpu(), g["scale"]) < FWD_TOL
+    assert rel_err(zs.cpu(), g["zs"]) < FWD_TOL and rel_err(px.loc.cpu(), g["loc"]) < FWD_TOL
+    big = 1e8 if name == "photo_elbo" else 1e10
+    want_scale = torch.ones(x[3].shape) + big * x[3].cpu()
+    assert torch.equal(px.scale[0].cpu(), want_scale)            # bit-exact mask -> scale logic
+    assert rel_err(m.encode(x).cpu(), g["enc_mean"]) < FWD_TOL
+    assert not m.training                                          # encode() leaves the module in eval mode
+    return loss.item(), worst
+
+
+def build_mm(g, device, dropout=0.0):
+    from VAESNe.PhotometricVAE import PhotometricVAE
+    from VAESNe.SpectraVAE import SpectraVAE
+    from VAESNe.mmVAE import photospecMMVAE
+    fam = dist.Laplace if str(g["family"]) == "laplace" else dist.Normal
+    pv = PhotometricVAE(num_bands=int(g["num_bands"]), latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32,
+                        num_layers=4, dropout=dropout, selfattn=False, concat=True, prior=fam, likelihood=fam, posterior=fam)
+    sv = SpectraVAE(latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=4, dropout=dropout,
+                    selfattn=bool(int(g["selfattn"])), concat=True, prior=fam, likelihood=fam, posterior=fam)
+    m = photospecMMVAE([pv, sv], prior_dist=fam, beta=float(g["beta"]))
+    m.load_state_dict(golden_params(g))
+    return m.to(device)
+
+
+def run_mm_case(name, device):
+    from VAESNe import _noise
+    from VAESNe.losses import m_iwae, _m_iwae
+    g = load_golden(name)
+    m = build_mm(g, device).train()
+    x = [_to(golden_x(g, "x0"), device), _to(golden_x(g, "x1"), device)]
+    K = int(g["K"])
+    us = [torch.from_numpy(g["u0"]), torch.from_numpy(g["u1"])]
+    _noise.clear(); _noise.inject(us)
+    loss = m_iwae(m, x, K=K)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < FWD_TOL * abs(float(g["loss"])), (loss.item(), float(g["loss"]))
+    worst = _check_grads(m, g)
+    _noise.inject(us)
+    with torch.no_grad():
+        qz, px, zss = m(x, K)
+    for e in range(2):
+        assert rel_err(zss[e].cpu(), g[f"zs{e}"]) < FWD_TOL
+        for d in range(2):
+            assert rel_err(px[e][d].loc.cpu(), g[f"loc.{e}.{d}"]) < FWD_TOL, (e, d)
+    assert rel_err(qz[0].scale.cpu(), g["s0"]) < FWD_TOL and rel_err(qz[1].loc.cpu(), g["mu1"]) < FWD_TOL
+    # the generic (torch.distributions) objective on top of the same kernels agrees with the fused one
+    _noise.inject(us)
+    with torch.no_grad():
+        from VAESNe.util_layers import log_mean_exp
+        lw = _m_iwae(m, x, K)
+    assert abs(log_mean_exp(lw).sum().item() - float(g["loss"])) < FWD_TOL * abs(float(g["loss"]))
+    return loss.item(), worst
+
+
+def run_contrast_case(device):
+    from VAESNe.contrastiveNets import ContraPhotSpec
+    from VAESNe.losses import negInfoNCE
+    g = load_golden("contrast")
+    m = ContraPhotSpec(4, 4, 8, 6, 32, 4, 32, 4, 0.0, 32, 4, 4, 32, 0.0, False)
+    m.load_state_dict(golden_params(g))
+    m.to(device).train()
+    x = [_to(golden_x(g, "x0"), device), _to(golden_x(g, "x1"), device)]
+    loss = negInfoNCE(m, x, temperature=0.1)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 1e-4, (loss.item(), float(g["loss"]))
+    return _check_grads(m, g)
+
+
+def run_end2end_case(name, device):
+    from VAESNe.regression import photoend2endregression, specend2endregression
+    g = load_golden(name)
+    if name == "photo_end2end":
+        m = photoend2endregression(5, 6, 4, 4, 32, 4, 32, 4, 0.0, False)
+    else:
+        m = specend2endregression(5, 4, 4, 32, 4, 4, 32, 0.0, False)
+    m.load_state_dict(golden_params(g))
+    m.to(device).train()
+    x = _to(golden_x(g, "x"), device)
+    y = m(x)
+    assert rel_err(y.detach().cpu(), g["y"]) < FWD_TOL
+    torch.nn.functional.mse_loss(y, torch.from_numpy(g["target"]).to(device)).backward()
+    return _check_grads(m, g)
+
+
+def run_reghead_case(device):
+    """encode path: VAEregressionHead(frozen vaes[0]) (photometry2goldstein_mmvae.py:55-57)."""
+    import json
+    from oracle import vaesne_oracle as O
+    from VAESNe.regression import VAEregressionHead
+    g = load_golden("mm_goldstein")
+    h = load_golden("mm_goldstein_reghead")
+    m = build_mm(g, device)
+    head = VAEregressionHead(m.vaes[0], 5, MLPlatent=[128] * 4)
+    head.outfc.load_state_dict(O.random_params(json.loads(str(h["shapes"])), int(h["seed"])))
+    head.to(device)
+    x = [_to(golden_x(g, "x0"), device), _to(golden_x(g, "x1"), device)]
+    y = head(x[0])
+    assert rel_err(y.detach().cpu(), h["y"]) < FWD_TOL
+    assert rel_err(m.vaes[0].encode(x[0]).cpu(), h["enc0"]) < FWD_TOL
+    assert rel_err(m.vaes[1].encode(x[1]).cpu(), h["enc1"]) < FWD_TOL
+    y.sum().backward()
+    assert all(p.grad is None for p in m.vaes[0].parameters())      # frozen encoder
+    assert all(p.grad is not None for p in head.outfc.parameters())

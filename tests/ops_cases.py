@@ -289,6 +289,13 @@ def run_latent_case(fam, device):
     db = P.latent_bwd(bt, nt, [f] * M, T, f, pz_mu.to(device), pz_s.to(device), dz_ext.to(device), dlat.to(device), pi, kl_coef=0.37)
     for m in range(M):
         assert rel_err(db[m].cpu(), bd[m].grad) < 5e-5, rel_err(db[m].cpu(), bd[m].grad)
+    # stand-alone KL gradient kernel against the same autograd reference (only the KL term)
+    mq = mus[0].detach().clone().requires_grad_(); sq = ss[0].detach().clone().requires_grad_()
+    (0.37 * O.kl(fam, mq, sq, fam, pz_mu.double(), pz_s.double()).sum()).backward()
+    gsc = torch.tensor(0.5, device=device)
+    dmu_k, ds_k = P.kl_bwd(mu_o[0], s_o[0], f, pz_mu.to(device), pz_s.to(device), 0.74, gsc)
+    assert rel_err(dmu_k.cpu(), mq.grad) < 5e-5 and rel_err(ds_k.cpu(), sq.grad) < 5e-5
+    assert rel_err(P.scale(mu_o[0], 2.0, gsc).cpu(), mus[0].detach()) < 1e-6
     kld = P.kl_fwd(mu_o[0], s_o[0], f, pz_mu.to(device), pz_s.to(device))
     assert rel_err(kld.cpu(), O.kl(fam, mus[0], ss[0], fam, pz_mu.double(), pz_s.double()).sum((-1, -2)).detach()) < TOL
 

@@ -1,0 +1,21 @@
+"""Whole-model parity of the product path against the live-reference goldens, executed through the
+CPU emulator of the CUDA kernels (same checks run on the B200 in test_gpu_model.py)."""
+import pytest
+
+import model_cases as MC
+
+
+def test_photo_elbo(emu):
+    MC.run_elbo_case("photo_elbo", "cpu")
+
+
+def test_spec_elbo(emu):
+    MC.run_elbo_case("spec_elbo", "cpu")
+
+
+def test_mm_normal(emu):
+    MC.run_mm_case("mm_normal", "cpu")
+
+
+def test_photo_end2end(emu):
+    MC.run_end2end_case("photo_end2end", "cpu")

@@ -1,0 +1,182 @@
+"""torch.autograd bridges: one Function per stack, one for the latent step, one per objective.
+
+Parameter gradients of a stack are produced as views of ONE freshly zeroed flat fp32 buffer laid
+out in ``named_parameters()`` order — autograd's AccumulateGrad adopts the views as ``.grad`` (no
+extra kernels), the fused AdamW and the data-parallel all-reduce then see a few large buffers
+instead of ~350 small tensors.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+
+from . import _ops as P
+from . import _stacks as S
+
+
+def _prep(t: Optional[torch.Tensor], dtype=None):
+    if t is None:
+        return None
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _StackFn(torch.autograd.Function):
+    """forward(runner, names, n_data, *data, *params) -> output tensor.
+
+    `runner(tape, pv, *data)` enqueues the kernels; tensors in `data` that require grad (the latent
+    samples fed to a decoder) get their gradient from the tape."""
+
+    @staticmethod
+    def forward(ctx, runner: Callable, names: Sequence[str], n_data: int, drop_p: float, *args):
+        data, params = args[:n_data], args[n_data:]
+        need = any(ctx.needs_input_grad)
+        dev = params[0].device
+        tape = S.Tape(need, drop_p, dev)
+        pv = S.PView(names, [p.detach() for p in params])
+        out = runner(tape, pv, *[d.detach() if isinstance(d, torch.Tensor) else d for d in data])
+        ctx.tape, ctx.names, ctx.n_data = tape, names, n_data
+        ctx.data = data
+        ctx.pshapes = [tuple(p.shape) for p in params]
+        ctx.pdev = dev
+        ctx.out_ref = out
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        n_data, names = ctx.n_data, ctx.names
+        need = ctx.needs_input_grad[4:]
+        sizes = [int(torch.Size(s).numel()) for s in ctx.pshapes]
+        flat = torch.zeros(sum(sizes), device=ctx.pdev, dtype=torch.float32)
+        pg, views, off = {}, [], 0
+        for i, (name, shp, n) in enumerate(zip(names, ctx.pshapes, sizes)):
+            v = flat[off:off + n].view(shp)
+            off += n
+            views.append(v)
+            pg[name] = v if need[n_data + i] else None
+        bw = S._Bwd(pg)
+        bw.seed(ctx.out_ref, _prep(dout))
+        ctx.tape.backward(bw)
+        dgrads = []
+        for i, d in enumerate(ctx.data):
+            if isinstance(d, torch.Tensor) and need[i]:
+                g = bw.take(d.detach())
+                dgrads.append(g if g is not None else torch.zeros_like(d))
+            else:
+                dgrads.append(None)
+        pgrads = [v if need[n_data + i] else None for i, v in enumerate(views)]
+        ctx.tape = None
+        ctx.out_ref = None
+        return (None, None, None, None, *dgrads, *pgrads)
+
+
+def run_stack(module: torch.nn.Module, runner: Callable, data: Sequence):
+    names, params = zip(*module.named_parameters())
+    drop_p = float(getattr(module, "_drop_p", 0.0)) if module.training else 0.0
+    return _StackFn.apply(runner, names, len(data), drop_p, *data, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+class _LatentFn(torch.autograd.Function):
+    """(bott_0..bott_{M-1}) -> z [M,K,B,T,Z], lat [M*K,B] (or an empty tensor), mu_0.., s_0..
+
+    PhotometricVAE.py:53-54,162-163 / SpectraVAE.py:48-49,152-153 / losses.py:53-54."""
+
+    @staticmethod
+    def forward(ctx, fams, T, fam_prior, pz_mu, pz_s, want_lat, noises, *botts):
+        M = len(botts)
+        z, mus, ss, lat, pi = P.latent_fwd([b.detach() for b in botts], noises, fams, T, fam_prior, pz_mu, pz_s, want_lat)
+        ctx.cfg = (fams, T, fam_prior, pz_mu, pz_s, want_lat, noises, pi)
+        ctx.botts = [b.detach() for b in botts]
+        if lat is None:
+            lat = z.new_empty(0)
+        else:
+            lat = lat.view(M * noises[0].shape[0], -1)
+        ctx.set_materialize_grads(False)
+        return (z, lat, *mus, *ss)
+
+    @staticmethod
+    def backward(ctx, dz, dlat, *dms):
+        fams, T, fam_prior, pz_mu, pz_s, want_lat, noises, pi = ctx.cfg
+        M = len(ctx.botts)
+        dmu = [_prep(g) for g in dms[:M]]
+        ds = [_prep(g) for g in dms[M:]]
+        dbotts = P.latent_bwd(ctx.botts, noises, fams, T, fam_prior, pz_mu, pz_s, _prep(dz),
+                              _prep(dlat) if (want_lat and dlat is not None) else None, pi,
+                              dmu if any(g is not None for g in dmu) else None,
+                              ds if any(g is not None for g in ds) else None)
+        return (None, None, None, None, None, None, None, *dbotts)
+
+
+def latent_step(botts, noises, fams, T, fam_prior=0, pz_mu=None, pz_s=None, want_lat=False):
+    M = len(botts)
+    out = _LatentFn.apply(list(fams), T, fam_prior, pz_mu, pz_s, want_lat, [_prep(n) for n in noises], *[_prep(b) for b in botts])
+    z, lat = out[0], out[1]
+    return z, (lat if want_lat else None), list(out[2:2 + M]), list(out[2 + M:2 + 2 * M])
+
+
+# ------------------------------------------------------------------------------------------------
+class LikSpec:
+    """Likelihood of one modality: data, mask, family, fp32(1 + big), llik_scaling."""
+    __slots__ = ("x", "mask", "fam", "scale_masked", "scaling")
+
+    def __init__(self, x, mask, fam, scale_masked, scaling):
+        self.x, self.mask, self.fam, self.scale_masked, self.scaling = _prep(x, torch.float32), _prep(mask), fam, scale_masked, scaling
+
+
+class _IwaeFn(torch.autograd.Function):
+    """objective = sum_b ( logsumexp_r (lat[r,b] + sum_d scaling_d * loglik_d[r,b]) - log R )   losses.py:55-62,93"""
+
+    @staticmethod
+    def forward(ctx, specs: List[LikSpec], lat, *locs):
+        R, B = locs[0].shape[0], locs[0].shape[1]
+        lpx = torch.empty(R, B, device=locs[0].device, dtype=torch.float32)
+        locs = [_prep(l.detach()) for l in locs]
+        for i, (sp, loc) in enumerate(zip(specs, locs)):
+            P.loglik_fwd(loc, sp.x, sp.mask, sp.fam, sp.scale_masked, sp.scaling, lpx, accumulate=i > 0)
+        lat_c = _prep(lat.detach()) if lat is not None and lat.numel() else None
+        obj, w, _ = P.iwae_combine(lat_c, lpx)
+        ctx.specs, ctx.locs, ctx.w, ctx.has_lat = specs, locs, w, lat_c is not None
+        return obj
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _prep(g)
+        dlat = P.scale(ctx.w, 1.0, g) if ctx.has_lat else None
+        dlocs = [P.loglik_bwd(loc, sp.x, sp.mask, sp.fam, sp.scale_masked, sp.scaling, ctx.w, 1.0, g)
+                 for sp, loc in zip(ctx.specs, ctx.locs)]
+        return (None, dlat, *dlocs)
+
+
+def iwae_objective(specs, lat, locs):
+    return _IwaeFn.apply(specs, lat, *locs)
+
+
+class _ElboFn(torch.autograd.Function):
+    """objective = mean_{k,b} sum_l scaling*loglik - mean_b sum_{t,z} KL(q||p)   losses.py:16-24"""
+
+    @staticmethod
+    def forward(ctx, spec: LikSpec, fam_q, pz_mu, pz_s, loc, mu, s):
+        K, B = loc.shape[0], loc.shape[1]
+        loc, mu, s = _prep(loc.detach()), _prep(mu.detach()), _prep(s.detach())
+        lpx = torch.empty(K, B, device=loc.device, dtype=torch.float32)
+        P.loglik_fwd(loc, spec.x, spec.mask, spec.fam, spec.scale_masked, spec.scaling, lpx, False)
+        kld = P.kl_fwd(mu, s, fam_q, pz_mu, pz_s)
+        ctx.saved = (spec, fam_q, pz_mu, pz_s, loc, mu, s)
+        ctx.parts = (lpx, kld)
+        return P.elbo_combine(lpx, kld)
+
+    @staticmethod
+    def backward(ctx, g):
+        spec, fam_q, pz_mu, pz_s, loc, mu, s = ctx.saved
+        K, B = loc.shape[0], loc.shape[1]
+        g = _prep(g)
+        dloc = P.loglik_bwd(loc, spec.x, spec.mask, spec.fam, spec.scale_masked, spec.scaling, None, 1.0 / (K * B), g)
+        dmu, ds = P.kl_bwd(mu, s, fam_q, pz_mu, pz_s, -1.0 / B, g)
+        return (None, None, None, None, dloc, dmu, ds)
+
+
+def elbo_objective(spec, fam_q, pz_mu, pz_s, loc, mu, s):
+    return _ElboFn.apply(spec, fam_q, pz_mu, pz_s, loc, mu, s)

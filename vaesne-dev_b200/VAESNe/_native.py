@@ -38,11 +38,14 @@ _SIGS = {
     "vaesne_latent_bwd": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp],
     "vaesne_kl_fwd": [_vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp],
     "vaesne_loglik_fwd": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _i, _vp],
-    "vaesne_loglik_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _f, _vp, _vp],
+    "vaesne_loglik_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _vp, _f, _vp, _vp, _vp],
+    "vaesne_kl_bwd": [_vp, _vp, _i, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, _vp],
+    "vaesne_scale": [_vp, _ll, _f, _vp, _vp, _vp],
     "vaesne_iwae_combine": [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp],
     "vaesne_elbo_combine": [_vp, _vp, _i, _i, _vp, _vp],
     "vaesne_adamw_flat": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _vp, _f, _vp],
     "vaesne_step_advance": [_vp, _vp, _vp],
+    "vaesne_seed_next": [_vp, _vp, _vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["vaesne_last_error", "vaesne_abi_version", "vaesne_is_emulated"])
 

@@ -214,12 +214,26 @@ def loglik_fwd(loc, x, mask, fam, scale_masked, scaling, lpx, accumulate):
                                       _c(lpx, "lpx"), int(accumulate), N.stream_of(loc)))
 
 
-def loglik_bwd(loc, x, mask, fam, scale_masked, scaling, coef, gscale):
+def loglik_bwd(loc, x, mask, fam, scale_masked, scaling, coef, gscale, gptr=None):
     R, B, L = loc.shape
     dloc = torch.empty_like(loc)
     N.check(N.lib().vaesne_loglik_bwd(_c(loc, "loc"), _c(x, "x"), _c(mask, "mask"), R, B, L, fam, float(scale_masked), float(scaling),
-                                      _c(coef, "coef"), float(gscale), dloc.data_ptr(), N.stream_of(loc)))
+                                      _c(coef, "coef"), float(gscale), N.ptr(gptr), dloc.data_ptr(), N.stream_of(loc)))
     return dloc
+
+
+def kl_bwd(mu, s, fam, pz_mu, pz_s, coef, gptr=None):
+    B = mu.shape[0]
+    dmu, ds = torch.empty_like(mu), torch.empty_like(s)
+    N.check(N.lib().vaesne_kl_bwd(_c(mu, "mu"), _c(s, "s"), fam, _c(pz_mu, "pz_mu"), _c(pz_s, "pz_s"), B, mu[0].numel(), float(coef),
+                                  N.ptr(gptr), dmu.data_ptr(), ds.data_ptr(), N.stream_of(mu)))
+    return dmu, ds
+
+
+def scale(src, mult=1.0, gptr=None):
+    dst = torch.empty_like(src)
+    N.check(N.lib().vaesne_scale(_c(src, "src"), src.numel(), float(mult), N.ptr(gptr), dst.data_ptr(), N.stream_of(src)))
+    return dst
 
 
 def iwae_combine(lat, lpx, want_lw=False):
@@ -246,6 +260,23 @@ def adamw_flat(p, g, m, v, lr, b1, b2, eps, wd, step, grad_scale=1.0):
 def step_advance(step, seed):
     t = step if step is not None else seed
     N.check(N.lib().vaesne_step_advance(N.ptr(step), N.ptr(seed), N.stream_of(t)))
+
+
+_SEED_CELLS = {}
+
+
+def next_seed(device) -> torch.Tensor:
+    """A fresh device-resident 64-bit dropout seed (int64[1]); the per-device cell is initialised from
+    torch's global generator, so torch.manual_seed controls it."""
+    key = str(device)
+    cell = _SEED_CELLS.get(key)
+    if cell is None:
+        init = int(torch.empty((), dtype=torch.int64).random_().item())
+        cell = torch.tensor([init], dtype=torch.int64, device=device)
+        _SEED_CELLS[key] = cell
+    out = torch.empty(1, dtype=torch.int64, device=device)
+    N.check(N.lib().vaesne_seed_next(cell.data_ptr(), out.data_ptr(), N.stream_of(cell)))
+    return out
 
 
 def masked_scale(kind_big: float) -> float:

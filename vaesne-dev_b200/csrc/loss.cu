@@ -193,6 +193,32 @@ __global__ void kl_fwd_kernel(const float* mu, const float* s, int fam, const fl
   }
 }
 
+// (dmu, ds)[b,e] = coef * (*gptr) * d KL(q||p)[b,e] / d(mu, s)
+__global__ void kl_bwd_kernel(const float* mu, const float* s, int fam, const float* pz_mu, const float* pz_s, long long n, int TZ,
+                              float coef, const float* gptr, float* dmu, float* ds) {
+  if (gptr) coef *= *gptr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % TZ);
+    const float sq = s[i], sp = pz_s[e], d = mu[i] - pz_mu[e];
+    float kmu, ks;
+    if (fam == 0) {
+      const float ex = expf(-fabsf(d) / sq);
+      kmu = sgn(d) / sp * (1.f - ex);
+      ks = -1.f / sq + ex / sp * (1.f + fabsf(d) / sq);
+    } else {
+      kmu = d / (sp * sp);
+      ks = sq / (sp * sp) - 1.f / sq;
+    }
+    dmu[i] = coef * kmu; ds[i] = coef * ks;
+  }
+}
+
+// dst[i] = mult * (*gptr) * src[i]
+__global__ void scale_kernel(const float* src, long long n, float mult, const float* gptr, float* dst) {
+  if (gptr) mult *= *gptr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = mult * src[i];
+}
+
 // lpx[r, b] (+)= scaling * sum_l log p(x[b,l] | loc[r,b,l], scale(mask[b,l]))   — one warp per (r,b)
 __global__ void __launch_bounds__(256) loglik_fwd_kernel(const float* loc, const float* x, const unsigned char* mask, int R, int B, int L,
                                                          int fam, float scale_masked, float scaling, float* lpx, int acc) {
@@ -214,7 +240,8 @@ __global__ void __launch_bounds__(256) loglik_fwd_kernel(const float* loc, const
 
 // dloc[r,b,l] = gscale * coef[r,b] * scaling * d log p / d loc
 __global__ void loglik_bwd_kernel(const float* loc, const float* x, const unsigned char* mask, int R, int B, int L, int fam,
-                                  float scale_masked, float scaling, const float* coef, float gscale, float* dloc) {
+                                  float scale_masked, float scaling, const float* coef, float gscale, const float* gptr, float* dloc) {
+  if (gptr) gscale *= *gptr;
   const long long total = (long long)R * B * L;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / L; const int l = (int)(i - row * L); const int b = (int)(row % B);
@@ -350,11 +377,11 @@ extern "C" int vaesne_loglik_fwd(const float* loc, const float* x, const unsigne
 }
 
 extern "C" int vaesne_loglik_bwd(const float* loc, const float* x, const unsigned char* mask, int R, int B, int L, int fam,
-                                 float scale_masked, float scaling, const float* coef, float gscale, float* dloc, void* stream) {
+                                 float scale_masked, float scaling, const float* coef, float gscale, const float* gptr, float* dloc, void* stream) {
   V_REQUIRE(loc && x && dloc, V_ENULL, "loglik_bwd: null argument");
   if ((long long)R * B * L == 0) return V_OK;
   auto k = loglik_bwd_kernel;
-  VLAUNCH(k, dim3(ew_grid2((long long)R * B * L, 256)), dim3(256), 0, (cudaStream_t)stream, loc, x, mask, R, B, L, fam, scale_masked, scaling, coef, gscale, dloc);
+  VLAUNCH(k, dim3(ew_grid2((long long)R * B * L, 256)), dim3(256), 0, (cudaStream_t)stream, loc, x, mask, R, B, L, fam, scale_masked, scaling, coef, gscale, gptr, dloc);
   return check_launch("loglik_bwd");
 }
 
@@ -372,4 +399,21 @@ extern "C" int vaesne_elbo_combine(const float* lpx, const float* kld, int K, in
   auto k = elbo_kernel;
   VLAUNCH(k, dim3(1), dim3(256), 0, (cudaStream_t)stream, lpx, kld, K, B, obj);
   return check_launch("elbo_combine");
+}
+
+extern "C" int vaesne_kl_bwd(const float* mu, const float* s, int fam, const float* pz_mu, const float* pz_s, int B, int TZ,
+                             float coef, const float* gptr, float* dmu, float* ds, void* stream) {
+  V_REQUIRE(mu && s && pz_mu && pz_s && dmu && ds, V_ENULL, "kl_bwd: null argument");
+  if (B == 0) return V_OK;
+  auto k = kl_bwd_kernel;
+  VLAUNCH(k, dim3(ew_grid2((long long)B * TZ, 128)), dim3(128), 0, (cudaStream_t)stream, mu, s, fam, pz_mu, pz_s, (long long)B * TZ, TZ, coef, gptr, dmu, ds);
+  return check_launch("kl_bwd");
+}
+
+extern "C" int vaesne_scale(const float* src, long long n, float mult, const float* gptr, float* dst, void* stream) {
+  V_REQUIRE(src && dst, V_ENULL, "scale: null argument");
+  if (n == 0) return V_OK;
+  auto k = scale_kernel;
+  VLAUNCH(k, dim3(ew_grid2(n, 256)), dim3(256), 0, (cudaStream_t)stream, src, n, mult, gptr, dst);
+  return check_launch("scale");
 }

@@ -106,6 +106,15 @@ __global__ void step_inc_kernel(int* step, unsigned long long* seed) {
   }
 }
 
+// cell = lcg(cell); out = cell   (one dropout seed per forward call, replayable inside a CUDA graph)
+__global__ void seed_next_kernel(unsigned long long* cell, unsigned long long* out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned long long s = *cell * 6364136223846793005ULL + 1442695040888963407ULL;
+    *cell = s;
+    *out = s;
+  }
+}
+
 static inline int ew_grid(long long total, int block) {
   long long g = (total + block - 1) / block;
   if (g > 148 * 16) g = 148 * 16;
@@ -184,4 +193,11 @@ extern "C" int vaesne_step_advance(int* step, unsigned long long* seed, void* st
   auto k = step_inc_kernel;
   VLAUNCH(k, dim3(1), dim3(32), 0, (cudaStream_t)stream, step, seed);
   return check_launch("step_advance");
+}
+
+extern "C" int vaesne_seed_next(unsigned long long* cell, unsigned long long* out, void* stream) {
+  V_REQUIRE(cell && out, V_ENULL, "seed_next: null argument");
+  auto k = seed_next_kernel;
+  VLAUNCH(k, dim3(1), dim3(32), 0, (cudaStream_t)stream, cell, out);
+  return check_launch("seed_next");
 }

@@ -19,3 +19,23 @@ def test_mm_normal(emu):
 
 def test_photo_end2end(emu):
     MC.run_end2end_case("photo_end2end", "cpu")
+
+
+def test_spec_end2end(emu):
+    MC.run_end2end_case("spec_end2end", "cpu")
+
+
+def test_contrastive(emu):
+    MC.run_contrast_case("cpu")
+
+
+def test_regression_head_encode_path(emu):
+    MC.run_reghead_case("cpu")
+
+
+def test_mm_goldstein(emu):
+    MC.run_mm_case("mm_goldstein", "cpu")
+
+
+def test_mm_ztf(emu):
+    MC.run_mm_case("mm_ztf", "cpu")

@@ -1,0 +1,30 @@
+"""Whole-model parity on the B200 against the live-reference goldens (loss, reconstructions, every
+parameter gradient; dropout 0, injected noise)."""
+import pytest
+
+import model_cases as MC
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["photo_elbo", "spec_elbo"])
+def test_elbo(name):
+    MC.run_elbo_case(name, "cuda")
+
+
+@pytest.mark.parametrize("name", ["mm_goldstein", "mm_ztf", "mm_normal"])
+def test_m_iwae(name):
+    MC.run_mm_case(name, "cuda")
+
+
+def test_contrastive():
+    MC.run_contrast_case("cuda")
+
+
+@pytest.mark.parametrize("name", ["photo_end2end", "spec_end2end"])
+def test_end2end(name):
+    MC.run_end2end_case(name, "cuda")
+
+
+def test_regression_head_encode_path():
+    MC.run_reghead_case("cuda")

@@ -1,0 +1,40 @@
+"""Per-op parity of the sm_100a kernels on the B200, called through the C ABI."""
+import pytest
+import torch
+
+import ops_cases as OC
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", OC.LIN_CASES, ids=lambda c: c["id"])
+def test_lin(case):
+    OC.run_lin_case(case, "cuda")
+
+
+@pytest.mark.parametrize("case", OC.ATTN_CASES_FULL, ids=lambda c: c["id"])
+def test_attn(case):
+    OC.run_attn_case(case, "cuda")
+
+
+def test_misc():
+    OC.run_misc_cases("cuda")
+
+
+@pytest.mark.parametrize("fam", ["laplace", "normal"])
+def test_latent_and_objectives(fam):
+    OC.run_latent_case(fam, "cuda")
+    OC.run_loglik_case(fam, "cuda")
+
+
+def test_dropout_statistics():
+    OC.run_dropout_case("cuda")
+
+
+def test_adamw():
+    OC.run_adamw_case("cuda")
+
+
+def test_native_library_is_the_cuda_build():
+    from VAESNe import _native
+    assert not _native.is_emulated()

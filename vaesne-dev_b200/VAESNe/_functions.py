@@ -13,6 +13,7 @@ import torch
 
 from . import _ops as P
 from . import _stacks as S
+from . import parallel
 
 
 def _prep(t: Optional[torch.Tensor], dtype=None):
@@ -59,6 +60,7 @@ class _StackFn(torch.autograd.Function):
         bw = S._Bwd(pg)
         bw.seed(ctx.out_ref, _prep(dout))
         ctx.tape.backward(bw)
+        parallel.bucket_ready(flat)
         dgrads = []
         for i, d in enumerate(ctx.data):
             if isinstance(d, torch.Tensor) and need[i]:

@@ -1,0 +1,85 @@
+"""Batch-sharded data parallelism (one process per GPU, NCCL over NVLink; gloo on CPU for tests).
+
+The reference has no distributed code; the step shards naturally over the batch
+(every sample is independent through encoders, sampling, decoders and lw[:, b]) and has exactly
+one exchange: the sum of the parameter gradients.  Each stack's backward produces ONE flat
+gradient buffer; as soon as it is final it is all-reduced asynchronously, so the decoders'
+buckets travel while the encoders' backward is still running.  `m_iwae` is a SUM over the batch,
+so a SUM all-reduce reproduces the single-process gradient of the concatenated batch; for
+mean-type objectives (`elbo`) the optimiser divides by the world size (``grad_average=True``).
+"""
+from __future__ import annotations
+
+import os
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+_enabled = False
+_pending: List = []
+
+
+def init_from_env(backend: str | None = None) -> tuple[int, int, int]:
+    """Initialise torch.distributed from RANK / WORLD_SIZE / LOCAL_RANK / MASTER_* (torchrun contract)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    enable(world > 1)
+    return rank, world, local
+
+
+def enable(flag: bool = True) -> None:
+    global _enabled
+    _enabled = bool(flag) and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def enabled() -> bool:
+    return _enabled
+
+
+def world_size() -> int:
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def bucket_ready(flat: torch.Tensor) -> None:
+    """Called by a stack's backward when its flat gradient bucket is final."""
+    if _enabled:
+        _pending.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
+
+
+def wait_all() -> None:
+    """Called by the optimiser before it reads gradients."""
+    while _pending:
+        _pending.pop().wait()
+
+
+def shard(x, rank: int, world: int, multimodal: bool):
+    """Contiguous split of a global batch along dim 0 (equal shards)."""
+    def cut(t):
+        n = t.shape[0] // world
+        return t[rank * n:(rank + 1) * n]
+    if multimodal:
+        return [tuple(cut(t) for t in mod) for mod in x]
+    return tuple(cut(t) for t in x)
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
+    if world_size() > 1:
+        for p in module.parameters():
+            dist.broadcast(p.data, src)
+
+
+def all_reduce_scalar(t: torch.Tensor, average: bool = False) -> torch.Tensor:
+    if world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if average:
+            t = t / world_size()
+    return t

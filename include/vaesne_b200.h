@@ -36,6 +36,7 @@ extern "C" {
 
 const char* vaesne_last_error(void);
 int vaesne_abi_version(void);
+long long vaesne_launch_count(void);   /* kernels enqueued by this library since load (process-wide) */
 int vaesne_is_emulated(void);   /* 1 only for the CPU test build under tests/emu */
 
 /* ---- token-wise linear (+activation | +dropout+residual+LayerNorm) --------------------------

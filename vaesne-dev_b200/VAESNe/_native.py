@@ -47,7 +47,7 @@ _SIGS = {
     "vaesne_step_advance": [_vp, _vp, _vp],
     "vaesne_seed_next": [_vp, _vp, _vp],
 }
-EXPORTS = sorted(list(_SIGS) + ["vaesne_last_error", "vaesne_abi_version", "vaesne_is_emulated"])
+EXPORTS = sorted(list(_SIGS) + ["vaesne_last_error", "vaesne_abi_version", "vaesne_is_emulated", "vaesne_launch_count"])
 
 
 def _bind(path: str):
@@ -59,6 +59,7 @@ def _bind(path: str):
     lib.vaesne_last_error.restype = C.c_char_p
     lib.vaesne_abi_version.restype = C.c_int
     lib.vaesne_is_emulated.restype = C.c_int
+    lib.vaesne_launch_count.restype = C.c_longlong
     return lib
 
 
@@ -78,6 +79,10 @@ def lib():
                 "(or vaesne-dev_b200/build.py); there is no CPU fallback.")
         use_library(LIB_PATH)
     return _lib
+
+
+def launch_count() -> int:
+    return int(lib().vaesne_launch_count())
 
 
 def is_emulated() -> bool:

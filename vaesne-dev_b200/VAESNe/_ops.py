@@ -30,6 +30,54 @@ class Drop:
 NO_DROP = Drop(0.0, None, 0)
 
 
+class Profiler:
+    """Optional per-call CUDA-event timing of the heavy ops (used by bench.py for the roofline line).
+    Events are recorded on torch's current stream, the one the kernels are enqueued on."""
+
+    def __init__(self):
+        self.records = {}          # key -> list of (start_event, end_event)
+
+    def span(self, key):
+        return _Span(self, key)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for key, evs in self.records.items():
+            ms = [a.elapsed_time(b) for a, b in evs]
+            out[key] = dict(calls=len(ms), total_ms=sum(ms), avg_ms=sum(ms) / max(len(ms), 1))
+        return out
+
+
+class _Span:
+    def __init__(self, prof, key):
+        self.prof, self.key = prof, key
+
+    def __enter__(self):
+        self.a = torch.cuda.Event(enable_timing=True); self.b = torch.cuda.Event(enable_timing=True)
+        self.a.record()
+
+    def __exit__(self, *exc):
+        self.b.record()
+        self.prof.records.setdefault(self.key, []).append((self.a, self.b))
+
+
+class _NullSpan:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullSpan()
+PROFILER = None
+
+
+def _span(name, *dims):
+    return PROFILER.span((name,) + tuple(int(d) for d in dims)) if PROFILER is not None else _NULL
+
+
 def _f32(t: torch.Tensor, name: str) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise TypeError(f"{name}: expected float32, got {t.dtype}")
@@ -64,9 +112,10 @@ def lin_fwd(X, W, b, *, Xadd=None, act=ACT_NONE, H=None, R=None, gamma=None, bet
     if Y is None:
         Y = torch.empty(T, Nn, device=X.device, dtype=torch.float32)
     xp, ldx = _rows(X, "X"); ap, lda = _rows(Xadd, "Xadd"); hp, ldh = _rows(H, "H"); rp, ldr = _rows(R, "R"); yp, ldy = _rows(Y, "Y")
-    N.check(N.lib().vaesne_lin_fwd(xp, ldx, ap, lda, T, K, Nn, _c(W, "W"), _c(b, "b"), act, hp, ldh, rp, ldr,
-                                   _c(gamma, "gamma"), _c(beta, "beta"), LN_EPS, _c(S, "S"),
-                                   drop.p, N.ptr(drop.seed), drop.sid, yp, ldy, N.stream_of(X)))
+    with _span("lin_fwd_ln" if R is not None else "lin_fwd", T, K, Nn):
+        N.check(N.lib().vaesne_lin_fwd(xp, ldx, ap, lda, T, K, Nn, _c(W, "W"), _c(b, "b"), act, hp, ldh, rp, ldr,
+                                       _c(gamma, "gamma"), _c(beta, "beta"), LN_EPS, _c(S, "S"),
+                                       drop.p, N.ptr(drop.seed), drop.sid, yp, ldy, N.stream_of(X)))
     return Y
 
 
@@ -76,9 +125,10 @@ def lin_bwd(dY, X, W, *, Xadd=None, S=None, gamma=None, dgamma=None, dbeta=None,
     K = W.shape[1]
     dyp, lddy = _rows(dY, "dY"); xp, ldx = _rows(X, "X"); xap, ldxa = _rows(Xadd, "Xadd")
     ap, lda = _rows(A, "A"); drp, lddr = _rows(dR, "dR"); dxp, lddx = _rows(dX, "dX")
-    N.check(N.lib().vaesne_lin_bwd(dyp, lddy, T, K, Nn, _c(S, "S"), _c(gamma, "gamma"), LN_EPS, _c(dgamma, "dgamma"), _c(dbeta, "dbeta"),
-                                   drp, lddr, int(dR_acc), drop.p, N.ptr(drop.seed), drop.sid, act, ap, lda,
-                                   xp, ldx, xap, ldxa, _c(W, "W"), _c(dW, "dW"), _c(db, "db"), dxp, lddx, int(dX_acc), N.stream_of(dY)))
+    with _span("lin_bwd_ln" if S is not None else "lin_bwd", T, K, Nn):
+        N.check(N.lib().vaesne_lin_bwd(dyp, lddy, T, K, Nn, _c(S, "S"), _c(gamma, "gamma"), LN_EPS, _c(dgamma, "dgamma"), _c(dbeta, "dbeta"),
+                                       drp, lddr, int(dR_acc), drop.p, N.ptr(drop.seed), drop.sid, act, ap, lda,
+                                       xp, ldx, xap, ldxa, _c(W, "W"), _c(dW, "dW"), _c(db, "db"), dxp, lddx, int(dX_acc), N.stream_of(dY)))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -108,8 +158,9 @@ def attn_fwd(q, k, v, mask, drop: Drop = NO_DROP):
     LSE = torch.empty(Nb, 4, Lq, device=q.device, dtype=torch.float32)
     qp, ldq = _attn_operand(q, "q"); kp, ldk = _attn_operand(k, "k"); vp, ldv = _attn_operand(v, "v")
     mp, mrows, mlen = _mask_args(mask)
-    N.check(N.lib().vaesne_attn_fwd(qp, ldq, kp, ldk, vp, ldv, Nb, Lq, Lk, mp, mrows, mlen, drop.p, N.ptr(drop.seed), drop.sid,
-                                    O.data_ptr(), 32, LSE.data_ptr(), N.stream_of(q)))
+    with _span("attn_fwd", Nb, Lq, Lk):
+        N.check(N.lib().vaesne_attn_fwd(qp, ldq, kp, ldk, vp, ldv, Nb, Lq, Lk, mp, mrows, mlen, drop.p, N.ptr(drop.seed), drop.sid,
+                                        O.data_ptr(), 32, LSE.data_ptr(), N.stream_of(q)))
     return O, LSE
 
 
@@ -121,9 +172,10 @@ def attn_bwd(q, k, v, mask, O, LSE, dO, dq, dk, dv, drop: Drop = NO_DROP):
     dop, lddo = _attn_operand(dO, "dO")
     mp, mrows, mlen = _mask_args(mask)
     ws = torch.empty(Nb, 4, Lq, device=q.device, dtype=torch.float32)
-    N.check(N.lib().vaesne_attn_bwd(qp, ldq, kp, ldk, vp, ldv, Nb, Lq, Lk, mp, mrows, mlen, drop.p, N.ptr(drop.seed), drop.sid,
-                                    _c(O, "O"), 32, _c(LSE, "LSE"), dop, lddo, ws.data_ptr(), dqp, lddq, dkp, lddk, dvp, lddv,
-                                    N.stream_of(q)))
+    with _span("attn_bwd", Nb, Lq, Lk):
+        N.check(N.lib().vaesne_attn_bwd(qp, ldq, kp, ldk, vp, ldv, Nb, Lq, Lk, mp, mrows, mlen, drop.p, N.ptr(drop.seed), drop.sid,
+                                        _c(O, "O"), 32, _c(LSE, "LSE"), dop, lddo, ws.data_ptr(), dqp, lddq, dkp, lddk, dvp, lddv,
+                                        N.stream_of(q)))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -4,8 +4,11 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+
 namespace vaesne {
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -15,6 +18,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
@@ -26,6 +30,8 @@ int check_launch(const char* what) {
 }  // namespace vaesne
 
 extern "C" const char* vaesne_last_error(void) { return vaesne::g_err; }
+
+extern "C" long long vaesne_launch_count(void) { return vaesne::g_launches.load(); }
 
 extern "C" int vaesne_abi_version(void) { return VAESNE_B200_ABI_VERSION; }
 

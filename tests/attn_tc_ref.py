@@ -1,0 +1,72 @@
+"""Checker for the tcgen05 attention kernels (test infrastructure): numpy restatement of their dropout
+mask (vaesne-dev_b200/csrc/attn_tc.cu: drop_row_word / drop_col_word / keep rule; common.cuh: mix32,
+hash_ctr) and an fp64 torch reference of masked attention with an explicit dropout mask."""
+import math
+
+import numpy as np
+import torch
+
+M32 = np.uint64(0xFFFFFFFF)
+
+
+def _u32(x):
+    return np.asarray(x, dtype=np.uint64) & M32
+
+
+def mix32(h):
+    h = _u32(h)
+    h = h ^ (h >> np.uint64(16)); h = _u32(h * np.uint64(0x7feb352d))
+    h = h ^ (h >> np.uint64(15)); h = _u32(h * np.uint64(0x846ca68b))
+    h = h ^ (h >> np.uint64(16))
+    return h
+
+
+def hash_ctr(s0, s1, stream, ctr):
+    ctr = np.asarray(ctr, dtype=np.uint64)
+    lo, hi = ctr & M32, ctr >> np.uint64(32)
+    h = mix32(_u32(lo * np.uint64(0x9E3779B1)) + np.uint64(s0))
+    h = mix32(h ^ _u32(_u32(hi * np.uint64(0x85EBCA77)) + np.uint64(s1)))
+    h = mix32(h + _u32(np.uint64(stream) * np.uint64(0xC2B2AE3D)))
+    return h
+
+
+def drop_threshold(p):
+    t = float(p) * 4294967296.0
+    thr = 0xFFFFFFFF if t >= 4294967295.0 else int(t)
+    scale = np.float32(1.0 / (1.0 - thr / 4294967296.0))
+    return thr, float(scale)
+
+
+def keep_mask(seed, stream, p, N, H, Lq, key_mask_full, Lk):
+    """bool [N, H, Lq, Lk]: True = kept.  Dropout is indexed by COMPACTED key slot (masked keys removed),
+    so the per-row key-padding mask enters; masked keys are reported as kept (their probability is 0)."""
+    s0, s1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    thr, _ = drop_threshold(p)
+    out = np.ones((N, H, Lq, Lk), dtype=bool)
+    for n in range(N):
+        kept = np.arange(Lk) if key_mask_full is None else np.nonzero(~key_mask_full[n])[0]
+        slots = np.arange(len(kept), dtype=np.uint64)
+        for h in range(H):
+            nh = n * H + h
+            A = hash_ctr(s0, s1, stream, np.uint64(nh) * np.uint64(Lq) + np.arange(Lq, dtype=np.uint64)) | np.uint64(1)
+            B = hash_ctr(s1, s0, (stream ^ 0x5bd1e995) & 0xFFFFFFFF, (np.uint64(nh) << np.uint64(32)) | slots)
+            prod = _u32(A[:, None] * B[None, :])
+            out[n, h][:, kept] = prod >= np.uint64(thr)
+    return out
+
+
+def attn_reference_drop(q, k, v, mask_full, dO, keep, drop_scale):
+    """fp64 reference with an explicit dropout mask `keep` [N,4,Lq,Lk] (bool tensor) applied to softmax(P)."""
+    q = q.double().requires_grad_(); k = k.double().requires_grad_(); v = v.double().requires_grad_()
+    N, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+    qh = q.view(N, Lq, 4, 8).transpose(1, 2) * math.sqrt(1 / 8)
+    kh = k.view(N, Lk, 4, 8).transpose(1, 2)
+    vh = v.view(N, Lk, 4, 8).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2)
+    if mask_full is not None:
+        s = s.masked_fill(mask_full[:, None, None, :], float("-inf"))
+    lse = torch.logsumexp(s, -1)
+    p = torch.softmax(s, -1) * keep.double() * drop_scale
+    o = (p @ vh).transpose(1, 2).reshape(N, Lq, 32)
+    o.backward(dO.double())
+    return o.detach(), lse.detach(), q.grad, k.grad, v.grad

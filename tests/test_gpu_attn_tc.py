@@ -1,0 +1,75 @@
+"""Parity of the tcgen05 attention kernels (attn_tc.cu: forward, dQ pass, dK/dV pass) on the B200, through
+the C ABI.  Tolerance: rel 1e-3 (north_star's fp32/TF32 bound) on max|err|/max|ref| per tensor; the
+measured errors are ~2e-4 (P and dS enter the second product as tf32).  Dropout: the kernels' mask is
+restated bit-exactly in numpy (tests/attn_tc_ref.py) and fed to an fp64 reference."""
+import numpy as np
+import pytest
+import torch
+
+import ops_cases as OC
+import attn_tc_ref as R
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+TC_TOL = 1e-3
+
+CASES = [c for c in OC.ATTN_CASES_FULL if c["Lq"] >= 256 and c["Lk"] >= 256] + [
+    dict(id="self_982_nomask", N=2, Lq=982, Lk=982, mask=False, packed="qkv"),
+    dict(id="self_300x260_mask", N=3, Lq=300, Lk=260, mask=True, packed="q+kv"),
+    dict(id="self_1024_mask", N=2, Lq=1024, Lk=1024, mask=True, packed="qkv"),
+    dict(id="self_257_mask", N=2, Lq=257, Lk=257, mask=True, packed="qkv"),
+    dict(id="cross_640x385", N=2, Lq=640, Lk=385, mask=True, mask_len=300, packed="q+kv"),
+]
+
+
+def _grads(c, dev):
+    if c["packed"] == "qkv":
+        dqkv = torch.full((c["N"], c["Lq"], 96), float("nan"), device=dev)
+        return dqkv[..., :32], dqkv[..., 32:64], dqkv[..., 64:]
+    dq = torch.full((c["N"], c["Lq"], 32), float("nan"), device=dev)
+    dkv = torch.full((c["N"], c["Lk"], 64), float("nan"), device=dev)
+    return dq, dkv[..., :32], dkv[..., 32:]
+
+
+@pytest.mark.parametrize("scale", [1.0, 3.0])
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c["id"])
+def test_tc_attention_matches_fp64(case, scale):
+    OC.run_attn_case(case, "cuda", tol=TC_TOL, scale=scale)
+
+
+@pytest.mark.parametrize("case", CASES[:2] + CASES[-2:], ids=lambda c: c["id"])
+def test_tc_attention_dropout_mask_is_the_restated_one(case):
+    from VAESNe import _ops as P
+    dev = "cuda"
+    (q, k, v, mask, mask_full, dO), (qd, kd, vd) = OC.make_attn_inputs(case, dev)
+    seed_val, sid, p = 0x1234ABCD5678EF01, 77, 0.1
+    seed = torch.tensor([seed_val], dtype=torch.int64, device=dev)
+    drop = P.Drop(p, seed, sid)
+    N, Lq, Lk = case["N"], case["Lq"], case["Lk"]
+    keep = R.keep_mask(seed_val, sid, p, N, 4, Lq, None if mask_full is None else mask_full.numpy(), Lk)
+    _, dscale = R.drop_threshold(p)
+    unmasked = ~mask_full.numpy() if mask_full is not None else np.ones((N, Lk), bool)
+    rate = 1.0 - keep[np.broadcast_to(unmasked[:, None, None, :], keep.shape)].mean()
+    assert abs(rate - p) < 2e-3, rate                       # the mask really drops ~p of the live entries
+    o_ref, lse_ref, dq_ref, dk_ref, dv_ref = R.attn_reference_drop(q, k, v, mask_full, dO, torch.from_numpy(keep), dscale)
+    md = mask.to(dev) if mask is not None else None
+    O, LSE = P.attn_fwd(qd, kd, vd, md, drop)
+    assert rel_err(O.cpu(), o_ref) < TC_TOL, ("O", rel_err(O.cpu(), o_ref))
+    assert rel_err(LSE.cpu(), lse_ref) < TC_TOL
+    dq, dk, dv = _grads(case, dev)
+    P.attn_bwd(qd, kd, vd, md, O, LSE, dO.to(dev), dq, dk, dv, drop)
+    for name, got, ref in (("dq", dq, dq_ref), ("dk", dk, dk_ref), ("dv", dv, dv_ref)):
+        assert rel_err(got.cpu(), ref) < TC_TOL, (name, rel_err(got.cpu(), ref))
+
+
+def test_tc_masked_keys_get_exact_zero_gradients():
+    from VAESNe import _ops as P
+    case = CASES[0]
+    (q, k, v, mask, mask_full, dO), (qd, kd, vd) = OC.make_attn_inputs(case, "cuda")
+    md = mask.to("cuda")
+    O, LSE = P.attn_fwd(qd, kd, vd, md)
+    dq, dk, dv = _grads(case, "cuda")
+    P.attn_bwd(qd, kd, vd, md, O, LSE, dO.to("cuda"), dq, dk, dv)
+    mf = mask_full.to("cuda")
+    assert torch.equal(dk[mf], torch.zeros_like(dk[mf])) and torch.equal(dv[mf], torch.zeros_like(dv[mf]))
+    assert torch.isfinite(dq).all() and torch.isfinite(dk).all() and torch.isfinite(dv).all()

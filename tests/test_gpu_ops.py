@@ -14,7 +14,9 @@ def test_lin(case):
 
 @pytest.mark.parametrize("case", OC.ATTN_CASES_FULL, ids=lambda c: c["id"])
 def test_attn(case):
-    OC.run_attn_case(case, "cuda")
+    # shapes served by the tcgen05 kernels carry tf32 second-product operands (see test_gpu_attn_tc.py)
+    tc = case["Lq"] >= 256 and case["Lk"] >= 256
+    OC.run_attn_case(case, "cuda", tol=1e-3 if tc else OC.TOL)
 
 
 def test_misc():

@@ -16,27 +16,11 @@
 // Q/dO/lse/delta) tiles of 128 rows are staged in shared memory and read as broadcasts.
 #include "common.cuh"
 #include "vaesne_b200.h"
+#include "attn_args.cuh"
 
 namespace vaesne {
 
 constexpr int AT = 128;    // threads per CTA and rows per shared-memory tile
-
-struct AttnArgs {
-  const float* q; long long ldq;
-  const float* k; long long ldk;
-  const float* v; long long ldv;
-  int N, Lq, Lk;
-  const unsigned char* mask; int mask_rows; int mask_len;
-  float p_drop; const uint64_t* seed; uint32_t stream_id;
-  float* O; long long ldo;
-  float* LSE;                 // [N,H,Lq], natural log
-  // backward only
-  const float* dO; long long lddo;
-  float* delta;               // [N,H,Lq] workspace (written by dq pass, read by dkv pass)
-  float* dq; long long lddq;
-  float* dk; long long lddk;
-  float* dv; long long lddv;
-};
 
 __device__ __forceinline__ void ld8(float* d, const float* p) {
   if (((uintptr_t)p & 15) == 0) {
@@ -317,6 +301,10 @@ extern "C" int vaesne_attn_fwd(const float* q, long long ldq, const float* k, lo
   V_REQUIRE(O && LSE, V_ENULL, "attn_fwd: null O/LSE");
   if (N == 0) return V_OK;
   cudaStream_t st = (cudaStream_t)stream;
+#ifndef VAESNE_EMU
+  // the forward and backward of one attention call must pick the same path (their dropout masks differ)
+  if (attn_tc_eligible(a) && (a.p_drop == 0.f || attn_tc_has_bwd())) return attn_tc_fwd(a, st);
+#endif
   dim3 block(AT);
   if (Lq <= 32) { dim3 grid((Lq + 3) / 4, kH, N); auto kf = attn_fwd_kernel<32>; VLAUNCH(kf, grid, block, 0, st, a); }
   else { dim3 grid((Lq + AT - 1) / AT, kH, N); auto kf = attn_fwd_kernel<1>; VLAUNCH(kf, grid, block, 0, st, a); }
@@ -338,6 +326,9 @@ extern "C" int vaesne_attn_bwd(const float* q, long long ldq, const float* k, lo
   V_REQUIRE(O && LSE && dO && delta_ws && dq && dk && dv, V_ENULL, "attn_bwd: null argument");
   if (N == 0) return V_OK;
   cudaStream_t st = (cudaStream_t)stream;
+#ifndef VAESNE_EMU
+  if (attn_tc_eligible(a) && attn_tc_has_bwd()) return attn_tc_bwd(a, st);
+#endif
   dim3 block(AT);
   if (Lq <= 32) { dim3 grid((Lq + 3) / 4, kH, N); auto kf = attn_bwd_dq_kernel<32>; VLAUNCH(kf, grid, block, 0, st, a); }
   else { dim3 grid((Lq + AT - 1) / AT, kH, N); auto kf = attn_bwd_dq_kernel<1>; VLAUNCH(kf, grid, block, 0, st, a); }

@@ -1,0 +1,33 @@
+// Argument block shared by the general attention kernels (attn.cu) and the tcgen05 kernels (attn_tc.cu).
+#pragma once
+#include <stdint.h>
+
+namespace vaesne {
+
+struct AttnArgs {
+  const float* q; long long ldq;
+  const float* k; long long ldk;
+  const float* v; long long ldv;
+  int N, Lq, Lk;
+  const unsigned char* mask; int mask_rows; int mask_len;
+  float p_drop; const uint64_t* seed; uint32_t stream_id;
+  float* O; long long ldo;
+  float* LSE;                 // [N,H,Lq], natural log
+  // backward only
+  const float* dO; long long lddo;
+  float* delta;               // [N,H,Lq] workspace (written by dq pass, read by dkv pass)
+  float* dq; long long lddq;
+  float* dk; long long lddk;
+  float* dv; long long lddv;
+};
+
+#ifndef VAESNE_EMU
+// tcgen05 path (attn_tc.cu): returns V_OK after enqueueing, or a negative code. `eligible` says whether the
+// shape is served by the Blackwell-native kernels (long self-attention); fwd and bwd use the same predicate.
+bool attn_tc_eligible(const AttnArgs& a);
+bool attn_tc_has_bwd();
+int attn_tc_fwd(const AttnArgs& a, cudaStream_t st);
+int attn_tc_bwd(const AttnArgs& a, cudaStream_t st);
+#endif
+
+}  // namespace vaesne

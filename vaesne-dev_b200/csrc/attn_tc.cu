@@ -1,0 +1,785 @@
+// Blackwell-native masked self-attention for the long sequences of the spectra stacks
+// (982 decoder tokens / 983 encoder-context tokens, 4 heads x head_dim 8) — forward and backward.
+//
+// Same arithmetic as attn.cu (nn.MultiheadAttention core, util_layers.py:289,297): q*sqrt(1/8), QK^T,
+// key-padding mask, softmax, dropout(P), PV — restructured for sm_100a.  Three kernels share one skeleton:
+//
+//   pass   TMEM lanes (rows)   staged once per CTA (columns)        per tile
+//   fwd    128 queries         K (hi+lo), V of all unmasked keys    S=QK^T -> P=2^(S-m) -> O += P[V|1]
+//   dq     128 queries         K (hi+lo), V, K                      S, T=dO V^T -> dS=P(T-delta) -> dQ += dS K
+//   dkv    128 keys            Q (hi+lo), dO, Q, dO, lse, delta     S^T, T^T -> P^T, dS^T -> dV += P^T dO, dK += dS^T Q
+//
+//   * one CTA per (batch row, head); the column-side operands are staged ONCE in shared memory as K-major
+//     tcgen05 operand tiles.  Masked keys are compacted away while staging — the key-padding mask is never
+//     materialised and masked keys cost nothing.
+//   * the score products run on the tensor core (tcgen05.mma kind::tf32, M=128, K=8) with fp32 accumulation in
+//     TMEM.  kind::tf32 truncates its inputs to 10 mantissa bits, so the operands of S are pre-split into
+//     tf32 hi + lo parts (3 MMAs) which restores fp32-level scores; the other operands are rounded to nearest.
+//   * the row-side operands (Q or K/V/dO rows) live in TMEM: each thread stores its own row, no smem staging.
+//   * two 128-row tiles are in flight, each owned by one warpgroup whose thread r holds row r (32x32b TMEM
+//     loads: max / exp / sum need no shuffles).  P (and dS) are written back over S (and T) in TMEM and used
+//     directly as the A operand of the second product (tcgen05.mma .ts form, N=16).
+//   * a ninth warp issues all MMAs from ONE ELECTED lane (elect.sync: without it ptxas wraps every UTCMMA in
+//     a divergence loop, 103 instead of 24 clk per issue — tests/probe/tc_rates.cu) and tracks completion
+//     with tcgen05.commit -> mbarrier.
+//   * dropout keeps element (query i, key slot c) iff  A_i * B_c >= p * 2^32  (A_i odd per-query hash word,
+//     B_c per-slot hash word): two integer ops per element in either orientation, so the row-major passes and
+//     the key-major pass regenerate identical masks.  tests/attn_tc_ref.py restates it in numpy.
+//
+// At head_dim 8 the kernel is bound by MUFU.EX2 (16/clk/SM: 32 tensor FLOP per exponential); see DESIGN.md.
+#include "common.cuh"
+#include "vaesne_b200.h"
+#include "attn_args.cuh"
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace vaesne {
+using namespace tc;
+
+constexpr int TCQ = 128;            // rows per tile (= TMEM lanes)
+constexpr int FK = 128;             // fwd: keys per tile
+constexpr int BK = 64;              // bwd: columns per tile
+constexpr int MAXL = 1024;          // staged column-side length
+constexpr int NTHREADS = 288;       // 8 softmax warps + 1 MMA warp
+constexpr float kScale = 0.35355339059327373f;             // sqrt(1/8)
+constexpr float kQScale = kScale * 1.4426950408889634f;    // ... * log2(e)
+constexpr float kLazy = 8.f;        // rescale O only when the row max grows by more than 2^8
+constexpr int TILE_F = MAXL * 8;    // floats of one staged operand array (32 KB)
+
+struct TcDrop { uint32_t s0, s1, stream, thr; float scale; bool on; };
+__device__ __forceinline__ TcDrop make_tcdrop(float p, const uint64_t* seed, uint32_t stream) {
+  TcDrop d; d.on = (p > 0.f) && seed != nullptr; d.s0 = d.s1 = 0; d.stream = stream; d.thr = 0; d.scale = 1.f;
+  if (d.on) {
+    uint64_t s = *seed; d.s0 = (uint32_t)s; d.s1 = (uint32_t)(s >> 32);
+    const double t = (double)p * 4294967296.0;
+    d.thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+    d.scale = (float)(1.0 / (1.0 - (double)d.thr * (1.0 / 4294967296.0)));
+  }
+  return d;
+}
+__device__ __forceinline__ uint32_t drop_row_word(const TcDrop& d, int nh, int Lq, int i) {
+  return hash_ctr(d.s0, d.s1, d.stream, (uint64_t)nh * (uint64_t)Lq + (uint64_t)i) | 1u;
+}
+__device__ __forceinline__ uint32_t drop_col_word(const TcDrop& d, int nh, int c) {
+  return hash_ctr(d.s1, d.s0, d.stream ^ 0x5bd1e995u, ((uint64_t)nh << 32) | (uint64_t)c);
+}
+
+__device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rn_tf32(float x) { uint32_t h; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x)); return __uint_as_float(h); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void ld8g(float* d, const float* p) {
+  if (((uintptr_t)p & 15) == 0) {
+    const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) d[c] = p[c];
+  }
+}
+__device__ __forceinline__ void st8g(float* p, const float* d) {
+  if (((uintptr_t)p & 15) == 0) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(d[0], d[1], d[2], d[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(d[4], d[5], d[6], d[7]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) p[c] = d[c];
+  }
+}
+// layout L1: [rows x 8] K-major operand (contraction over the 8 features): two float4 per row
+__device__ __forceinline__ void put_l1(float* dst, int row, const float* x) {
+  float* p = dst + (row >> 3) * 64 + (row & 7) * 4;
+  *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+  *reinterpret_cast<float4*>(p + 32) = make_float4(x[4], x[5], x[6], x[7]);
+}
+// layout L2: for every 8 consecutive rows one [8 features x 8 rows] K-major operand (contraction over rows)
+__device__ __forceinline__ void put_l2(float* dst, int row, const float* x) {
+  float* p = dst + (row >> 3) * 64 + ((row & 7) >> 2) * 32 + (row & 3);
+#pragma unroll
+  for (int d = 0; d < 8; ++d) p[d * 4] = x[d];
+}
+__device__ __forceinline__ void split8(const float* x, float* hi, float* lo) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) split_tf32(x[c], hi[c], lo[c]);
+}
+__device__ __forceinline__ void rn8(const float* x, float* y) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) y[c] = rn_tf32(x[c]);
+}
+__device__ __forceinline__ void tmem_put8(uint32_t taddr, const float* x) {
+  uint32_t u[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) u[c] = __float_as_uint(x[c]);
+  tmem_st8(taddr, u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory carve-up: `narr` operand arrays of 32 KB, then the small tables
+// ------------------------------------------------------------------------------------------------
+struct TcSmem {
+  float* arr[5];
+  float* pad;            // [64] second 8-row group of the N=16 operands: ones row (fwd) or zeros (bwd)
+  float* f0; float* f1;  // [MAXL] per-column floats (dkv: lse2, delta)
+  uint32_t* w0;          // [MAXL] per-column dropout words
+  uint16_t* idx;         // [MAXL] compacted slot -> key index
+  uint32_t* ballot; uint32_t* pre; uint64_t* bars; uint32_t* tmem;
+};
+__host__ __device__ constexpr size_t tc_smem_bytes(int narr, bool cols) {
+  return 128 + (size_t)narr * TILE_F * 4 + 256 + (cols ? 2 * MAXL * 4 : 0) + MAXL * 4 + MAXL * 2 + 32 * 4 + 36 * 4 + 8 * 8 + 16;
+}
+__device__ __forceinline__ TcSmem carve(unsigned char* raw, int narr, bool cols) {
+  uintptr_t p = ((uintptr_t)raw + 127) & ~(uintptr_t)127;
+  TcSmem s;
+  float* f = (float*)p;
+  for (int i = 0; i < 5; ++i) s.arr[i] = i < narr ? f + (size_t)i * TILE_F : nullptr;
+  f += (size_t)narr * TILE_F;
+  s.pad = f; f += 64;
+  s.f0 = s.f1 = nullptr;
+  if (cols) { s.f0 = f; f += MAXL; s.f1 = f; f += MAXL; }
+  s.w0 = (uint32_t*)f; f += MAXL;
+  s.idx = (uint16_t*)f; f += MAXL / 2;
+  s.ballot = (uint32_t*)f; s.pre = s.ballot + 32;    // pre[0..31] exclusive prefix, pre[32] total
+  s.bars = (uint64_t*)(s.pre + 36);
+  s.tmem = (uint32_t*)(s.bars + 8);
+  return s;
+}
+
+// key compaction: ballot of kept keys per 32-key chunk + exclusive prefix.  Returns the number of kept keys.
+__device__ __forceinline__ int compact_keys(const AttnArgs& a, const TcSmem& s, int n, int tid, int warp, int lane) {
+  const unsigned char* mrow = a.mask ? a.mask + (long long)(n % a.mask_rows) * a.mask_len : nullptr;
+  for (int it = warp; it < 32; it += NTHREADS / 32) {
+    const int j = it * 32 + lane;
+    const bool keep = j < a.Lk && !(mrow && j < a.mask_len && mrow[j]);
+    const uint32_t b = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s.ballot[it] = b;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int v = __popc(s.ballot[lane]);
+    int incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+    s.pre[lane] = incl - v;
+    if (lane == 31) s.pre[32] = incl;
+  }
+  __syncthreads();
+  return (int)s.pre[32];
+}
+__device__ __forceinline__ int key_slot(const TcSmem& s, int j) {     // -1 if masked
+  const uint32_t bw = s.ballot[j >> 5];
+  if (!((bw >> (j & 31)) & 1u)) return -1;
+  return (int)s.pre[j >> 5] + __popc(bw & ((1u << (j & 31)) - 1u));
+}
+
+// Stage the unmasked keys of (n, h).  Khi/Klo: L1 split of K.  V1: L1 of V (rn).  V2 / K2: L2 of V / K (rn).
+__device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, int n, int h, int tid, int LkC, int tile,
+                                           float* Khi, float* Klo, float* V1, float* V2, float* K2,
+                                           const TcDrop& dc) {
+  const int Lpad = ((LkC + tile - 1) / tile) * tile;
+  float z[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) z[c] = 0.f;
+  for (int c = LkC + tid; c < Lpad; c += NTHREADS) {
+    put_l1(Khi, c, z); put_l1(Klo, c, z);
+    if (V1) put_l1(V1, c, z);
+    if (V2) put_l2(V2, c, z);
+    if (K2) put_l2(K2, c, z);
+  }
+  const int nh = n * kH + h;
+  if (dc.on) for (int c = tid; c < Lpad; c += NTHREADS) s.w0[c] = drop_col_word(dc, nh, c);
+  for (int j = tid; j < a.Lk; j += NTHREADS) {
+    const int c = key_slot(s, j);
+    if (c < 0) continue;
+    float kk[8], vv[8], hi[8], lo[8];
+    ld8g(kk, a.k + ((long long)n * a.Lk + j) * a.ldk + h * 8);
+    ld8g(vv, a.v + ((long long)n * a.Lk + j) * a.ldv + h * 8);
+    split8(kk, hi, lo);
+    put_l1(Khi, c, hi); put_l1(Klo, c, lo);
+    if (K2) put_l2(K2, c, hi);
+    rn8(vv, vv);
+    if (V1) put_l1(V1, c, vv);
+    if (V2) put_l2(V2, c, vv);
+  }
+}
+
+__device__ __forceinline__ void init_common(const TcSmem& s, int tid, int warp, float pad_row0) {
+  uint64_t* b = s.bars;
+  if (tid == 0) {
+    for (int w = 0; w < 2; ++w) { mbar_init(&b[w], 128); mbar_init(&b[2 + w], 1); mbar_init(&b[4 + w], 128); mbar_init(&b[6 + w], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < 64) s.pad[tid] = ((tid & 31) < 4) ? pad_row0 : 0.f;    // row 0 of both 16-byte K chunks
+  if (warp == 8) tmem_alloc<512>(s.tmem);
+}
+
+// =================================================================================================
+// forward
+// =================================================================================================
+constexpr size_t FWD_SMEM = tc_smem_bytes(3, false);
+
+__global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  const TcSmem s = carve(tc_smem_raw, 3, false);
+  float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V2 = s.arr[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
+  uint64_t* x_ready = s.bars;       // [2] count 128 : row operands (Q) stored in TMEM
+  uint64_t* s_ready = s.bars + 2;   // [2] count 1   : tcgen05.commit after S
+  uint64_t* p_ready = s.bars + 4;   // [2] count 128 : P stored in TMEM
+  uint64_t* o_ready = s.bars + 6;   // [2] count 1   : tcgen05.commit after the last PV
+  const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
+
+  init_common(s, tid, warp, 1.f);
+  const int LkC = compact_keys(a, s, n, tid, warp, lane);
+  stage_keys(a, s, n, h, tid, LkC, FK, Khi, Klo, nullptr, V2, nullptr, dc);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = *s.tmem;
+  const int T = (LkC + FK - 1) / FK;
+  const int nQT = (a.Lq + TCQ - 1) / TCQ;
+  const int NIT = (nQT + 1) / 2;
+  // TMEM columns: S[w] = w*128 (128) ; O[w] = 256 + w*16 (16) ; Q[w] = 288 + w*16 (hi 8 | lo 8)
+
+  if (warp == 8) {
+    // ------------------------------- MMA issuer -------------------------------------------------
+    const uint32_t idQK = idesc_tf32(128, FK), idPV = idesc_tf32(128, 16);
+    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV2 = smem_u32(V2), aPad = smem_u32(s.pad);
+    uint32_t pcount[2] = {0, 0};
+    auto issue_qk = [&](int w, int j) {
+      const uint32_t d = tb + (uint32_t)w * 128, q = tb + 288 + (uint32_t)w * 16;
+      const uint64_t dKhi = smem_desc(aKhi + j * (FK * 32), 128, 256), dKlo = smem_desc(aKlo + j * (FK * 32), 128, 256);
+      mma_ts(d, q, dKhi, idQK, 0);
+      mma_ts(d, q + 8, dKhi, idQK, 1);
+      mma_ts(d, q, dKlo, idQK, 1);
+    };
+    auto issue_pv = [&](int w, int j) {
+      const int nsteps = (min(FK, LkC - j * FK) + 7) >> 3;
+      const uint32_t dO = tb + 256 + (uint32_t)w * 16;
+      for (int t = 0; t < nsteps; ++t) {
+        const uint32_t v = aV2 + (uint32_t)(j * (FK / 8) + t) * 256;
+        mma_ts(dO, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(v, 128, aPad - v), idPV, (j > 0 || t > 0) ? 1u : 0u);
+      }
+    };
+    for (int it = 0; it < NIT && T > 0; ++it) {
+      for (int w = 0; w < 2; ++w) {
+        if (2 * it + w >= nQT) continue;
+        mbar_wait(&x_ready[w], it & 1);
+        fence_after();
+        if (elect_one()) { issue_qk(w, 0); commit(&s_ready[w]); }
+        __syncwarp();
+      }
+      for (int j = 0; j < T; ++j) {
+        for (int w = 0; w < 2; ++w) {
+          if (2 * it + w >= nQT) continue;
+          mbar_wait(&p_ready[w], pcount[w] & 1); pcount[w]++;
+          fence_after();
+          if (elect_one()) {
+            issue_pv(w, j);
+            if (j + 1 < T) { issue_qk(w, j + 1); commit(&s_ready[w]); }
+            else commit(&o_ready[w]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------- softmax warpgroups ------------------------------------------
+    const int wg = warp >> 2, r = tid & 127;
+    const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tb + tlane + (uint32_t)wg * 128, tO = tb + tlane + 256 + (uint32_t)wg * 16, tQ = tb + tlane + 288 + (uint32_t)wg * 16;
+    uint32_t scount = 0;
+    for (int it = 0; it < NIT; ++it) {
+      const int qt = 2 * it + wg;
+      if (qt >= nQT) break;
+      const int i = qt * TCQ + r;
+      const bool valid = i < a.Lq;
+      if (T == 0) {       // every key masked: softmax of an empty set (the reference yields NaN)
+        if (valid) {
+          float* op = a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8;
+          for (int c = 0; c < 8; ++c) op[c] = __int_as_float(0x7fc00000);
+          a.LSE[(long long)nh * a.Lq + i] = -INFINITY;
+        }
+        continue;
+      }
+      {   // Q row -> TMEM (scaled, hi/lo split)
+        float q[8], hi[8], lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) q[c] = 0.f;
+        if (valid) {
+          ld8g(q, a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) q[c] *= kQScale;
+        }
+        split8(q, hi, lo);
+        tmem_put8(tQ, hi); tmem_put8(tQ + 8, lo);
+        tmem_wait_st();
+        fence_before();
+        mbar_arrive(&x_ready[wg]);
+      }
+      const uint32_t rw = dc.on ? drop_row_word(dc, nh, a.Lq, valid ? i : 0) : 1u;
+      float m_used = -1e30f, lsum = 0.f;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(&s_ready[wg], scount & 1); scount++;
+        fence_after();
+        const int nvalid = min(FK, LkC - j * FK);
+        uint32_t sr[128];
+        tmem_ld32(tS, sr); tmem_ld32(tS + 32, sr + 32); tmem_ld32(tS + 64, sr + 64); tmem_ld32(tS + 96, sr + 96);
+        tmem_wait_ld();
+        float mt = -1e30f;
+        if (nvalid == FK) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) mt = fmaxf(mt, __uint_as_float(sr[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 128; ++c) { if (c >= nvalid) sr[c] = 0xff800000u; mt = fmaxf(mt, __uint_as_float(sr[c])); }
+        }
+        const float m_new = fmaxf(m_used, mt);
+        const bool need = (m_new > m_used + kLazy);
+        if (__any_sync(0xffffffffu, need)) {         // warp-uniform: TMEM ld/st are warp-collective
+          const float alpha = ex2(m_used - m_new);   // first tile: 2^(-1e30 - m) = 0, O not yet written
+          if (j > 0) {
+            uint32_t o[16];
+            tmem_ld16(tO, o); tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st16(tO, o);
+          }
+          lsum *= alpha;
+          m_used = m_new;
+        }
+        if (!dc.on) {
+          // P is truncated to tf32 by the MMA; the ones column of [V|1] sums the SAME truncated values,
+          // so the normalisation cancels the truncation bias
+#pragma unroll
+          for (int c = 0; c < 128; ++c) sr[c] = __float_as_uint(ex2(__uint_as_float(sr[c]) - m_used));
+        } else {
+          const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * FK);
+#pragma unroll
+          for (int cc = 0; cc < 32; ++cc) {
+            const uint4 b = bw[cc];
+            const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float p = ex2(__uint_as_float(sr[cc * 4 + e]) - m_used);
+              lsum += p;
+              sr[cc * 4 + e] = (rw * bb[e] >= dc.thr) ? (__float_as_uint(p) + 0x1000u) : 0u;   // RN to tf32
+            }
+          }
+        }
+        tmem_st32(tS, sr); tmem_st32(tS + 32, sr + 32); tmem_st32(tS + 64, sr + 64); tmem_st32(tS + 96, sr + 96);
+        tmem_wait_st();
+        fence_before();
+        mbar_arrive(&p_ready[wg]);
+      }
+      // epilogue: O / l  (l from the ones column when no dropout, from the register sum otherwise)
+      mbar_wait(&o_ready[wg], it & 1);
+      fence_after();
+      uint32_t o[16];
+      tmem_ld16(tO, o); tmem_wait_ld();
+      if (valid) {
+        const float l = dc.on ? lsum : __uint_as_float(o[8]);
+        const float inv = dc.scale / l;
+        float out[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) out[c] = __uint_as_float(o[c]) * inv;
+        st8g(a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8, out);
+        a.LSE[(long long)nh * a.Lq + i] = (m_used + log2f(l)) * kLn2;
+      }
+      fence_before();
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 8) { fence_after(); tmem_dealloc<512>(tb); }
+}
+
+// =================================================================================================
+// backward, pass 1: rows = queries.  delta = dO.O ; dQ = scale * sum_j dS_ij K_j
+// =================================================================================================
+constexpr size_t DQ_SMEM = tc_smem_bytes(4, false);
+
+__global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  const TcSmem s = carve(tc_smem_raw, 4, false);
+  float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V1 = s.arr[2]; float* K2 = s.arr[3];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
+  uint64_t* x_ready = s.bars; uint64_t* s_ready = s.bars + 2; uint64_t* p_ready = s.bars + 4; uint64_t* o_ready = s.bars + 6;
+  const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
+
+  init_common(s, tid, warp, 0.f);
+  const int LkC = compact_keys(a, s, n, tid, warp, lane);
+  stage_keys(a, s, n, h, tid, LkC, BK, Khi, Klo, V1, nullptr, K2, dc);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = *s.tmem;
+  const int T = (LkC + BK - 1) / BK;
+  const int nQT = (a.Lq + TCQ - 1) / TCQ;
+  const int NIT = (nQT + 1) / 2;
+  // TMEM columns: S[w] = w*128 (64) ; T[w] = w*128 + 64 (64) ; ACC[w] = 256 + w*16 ; X[w] = 288 + w*32 (Qhi | Qlo | dO)
+
+  if (warp == 8) {
+    const uint32_t idS = idesc_tf32(128, BK), idA = idesc_tf32(128, 16);
+    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV1 = smem_u32(V1), aK2 = smem_u32(K2), aPad = smem_u32(s.pad);
+    uint32_t pcount[2] = {0, 0};
+    auto issue_st = [&](int w, int j) {
+      const uint32_t d = tb + (uint32_t)w * 128, x = tb + 288 + (uint32_t)w * 32;
+      const uint64_t dKhi = smem_desc(aKhi + j * (BK * 32), 128, 256), dKlo = smem_desc(aKlo + j * (BK * 32), 128, 256);
+      mma_ts(d, x, dKhi, idS, 0);
+      mma_ts(d, x + 8, dKhi, idS, 1);
+      mma_ts(d, x, dKlo, idS, 1);
+      mma_ts(d + 64, x + 16, smem_desc(aV1 + j * (BK * 32), 128, 256), idS, 0);
+    };
+    auto issue_acc = [&](int w, int j) {
+      const int nsteps = (min(BK, LkC - j * BK) + 7) >> 3;
+      const uint32_t dA = tb + 256 + (uint32_t)w * 16;
+      for (int t = 0; t < nsteps; ++t) {
+        const uint32_t k2 = aK2 + (uint32_t)(j * (BK / 8) + t) * 256;
+        mma_ts(dA, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(k2, 128, aPad - k2), idA, (j > 0 || t > 0) ? 1u : 0u);
+      }
+    };
+    for (int it = 0; it < NIT && T > 0; ++it) {
+      for (int w = 0; w < 2; ++w) {
+        if (2 * it + w >= nQT) continue;
+        mbar_wait(&x_ready[w], it & 1);
+        fence_after();
+        if (elect_one()) { issue_st(w, 0); commit(&s_ready[w]); }
+        __syncwarp();
+      }
+      for (int j = 0; j < T; ++j) {
+        for (int w = 0; w < 2; ++w) {
+          if (2 * it + w >= nQT) continue;
+          mbar_wait(&p_ready[w], pcount[w] & 1); pcount[w]++;
+          fence_after();
+          if (elect_one()) {
+            issue_acc(w, j);
+            if (j + 1 < T) { issue_st(w, j + 1); commit(&s_ready[w]); }
+            else commit(&o_ready[w]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    const int wg = warp >> 2, r = tid & 127;
+    const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tb + tlane + (uint32_t)wg * 128, tA = tb + tlane + 256 + (uint32_t)wg * 16, tX = tb + tlane + 288 + (uint32_t)wg * 32;
+    uint32_t scount = 0;
+    for (int it = 0; it < NIT; ++it) {
+      const int qt = 2 * it + wg;
+      if (qt >= nQT) break;
+      const int i = qt * TCQ + r;
+      const bool valid = i < a.Lq;
+      float q[8], g[8], hi[8], lo[8];
+      float lse2 = INFINITY, delta = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { q[c] = 0.f; g[c] = 0.f; }
+      if (valid) {
+        float o[8];
+        ld8g(q, a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
+        ld8g(g, a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
+        ld8g(o, a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { q[c] *= kQScale; delta = fmaf(g[c], o[c], delta); }
+        lse2 = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
+        a.delta[(long long)nh * a.Lq + i] = delta;
+      }
+      if (T == 0) {       // every key masked: the reference's gradients are NaN
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) q[c] = __int_as_float(0x7fc00000);
+          st8g(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, q);
+        }
+        continue;
+      }
+      split8(q, hi, lo);
+      rn8(g, g);
+      tmem_put8(tX, hi); tmem_put8(tX + 8, lo); tmem_put8(tX + 16, g);
+      tmem_wait_st();
+      fence_before();
+      mbar_arrive(&x_ready[wg]);
+      const uint32_t rw = dc.on ? drop_row_word(dc, nh, a.Lq, valid ? i : 0) : 1u;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(&s_ready[wg], scount & 1); scount++;
+        fence_after();
+        uint32_t sr[64], tr[64];
+        tmem_ld32(tS, sr); tmem_ld32(tS + 32, sr + 32); tmem_ld32(tS + 64, tr); tmem_ld32(tS + 96, tr + 32);
+        tmem_wait_ld();
+        if (!dc.on) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const float p = ex2(__uint_as_float(sr[c]) - lse2);
+            sr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - delta)) + 0x1000u;
+          }
+        } else {
+          const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * BK);
+#pragma unroll
+          for (int cc = 0; cc < 16; ++cc) {
+            const uint4 b = bw[cc];
+            const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = cc * 4 + e;
+              const float p = ex2(__uint_as_float(sr[c]) - lse2);
+              const float dp = (rw * bb[e] >= dc.thr) ? __uint_as_float(tr[c]) * dc.scale : 0.f;
+              sr[c] = __float_as_uint(p * (dp - delta)) + 0x1000u;
+            }
+          }
+        }
+        const int nvalid = min(BK, LkC - j * BK);
+        if (nvalid < BK) {      // padded key slots: exactly zero (2^(-lse) may overflow and inf * 0 would poison the row)
+#pragma unroll
+          for (int c = 0; c < 64; ++c) if (c >= nvalid) sr[c] = 0u;
+        }
+        tmem_st32(tS, sr); tmem_st32(tS + 32, sr + 32);
+        tmem_wait_st();
+        fence_before();
+        mbar_arrive(&p_ready[wg]);
+      }
+      mbar_wait(&o_ready[wg], it & 1);
+      fence_after();
+      uint32_t o[8];
+      tmem_ld8(tA, o); tmem_wait_ld();
+      if (valid) {
+        float out[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) out[c] = __uint_as_float(o[c]) * kScale;
+        st8g(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, out);
+      }
+      fence_before();
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 8) { fence_after(); tmem_dealloc<512>(tb); }
+}
+
+// =================================================================================================
+// backward, pass 2: rows = (unmasked) keys.  dV = sum_i Pd_ij dO_i ; dK = scale * sum_i dS_ij Q_i
+// =================================================================================================
+constexpr size_t DKV_SMEM = tc_smem_bytes(5, true);
+
+__global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  const TcSmem s = carve(tc_smem_raw, 5, true);
+  float* Qhi = s.arr[0]; float* Qlo = s.arr[1]; float* G1 = s.arr[2]; float* Q2 = s.arr[3]; float* G2 = s.arr[4];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
+  uint64_t* x_ready = s.bars; uint64_t* s_ready = s.bars + 2; uint64_t* p_ready = s.bars + 4; uint64_t* o_ready = s.bars + 6;
+  const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
+
+  init_common(s, tid, warp, 0.f);
+  const int LkC = compact_keys(a, s, n, tid, warp, lane);
+  // slot -> key index, zero gradients of the masked keys
+  for (int j = tid; j < a.Lk; j += NTHREADS) {
+    const int c = key_slot(s, j);
+    if (c >= 0) { s.idx[c] = (uint16_t)j; continue; }
+    float z[8];
+#pragma unroll
+    for (int c2 = 0; c2 < 8; ++c2) z[c2] = 0.f;
+    st8g(a.dk + ((long long)n * a.Lk + j) * a.lddk + h * 8, z);
+    st8g(a.dv + ((long long)n * a.Lk + j) * a.lddv + h * 8, z);
+  }
+  // stage the query side: Q (scaled; L1 hi/lo + L2), dO (L1 + L2), lse2, delta, dropout row words
+  const int NQ = (a.Lq + BK - 1) / BK;
+  for (int i = tid; i < NQ * BK; i += NTHREADS) {
+    float q[8], g[8], hi[8], lo[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { q[c] = 0.f; g[c] = 0.f; }
+    float lse2 = INFINITY, delta = 0.f;
+    if (i < a.Lq) {
+      ld8g(q, a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
+      ld8g(g, a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) q[c] *= kQScale;
+      lse2 = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
+      delta = a.delta[(long long)nh * a.Lq + i];
+    }
+    split8(q, hi, lo);
+    rn8(g, g);
+    put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l1(G1, i, g);
+    put_l2(Q2, i, hi); put_l2(G2, i, g);
+    s.f0[i] = lse2; s.f1[i] = delta;
+    s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = *s.tmem;
+  const int nKT = (LkC + TCQ - 1) / TCQ;
+  const int NIT = (nKT + 1) / 2;
+  // TMEM columns: S[w] = w*128 (64) ; T[w] = w*128 + 64 (64) ; dK[w] = 256 + w*32 ; dV[w] = 272 + w*32 ; X[w] = 320 + w*32 (Khi | Klo | V)
+
+  if (warp == 8) {
+    const uint32_t idS = idesc_tf32(128, BK), idA = idesc_tf32(128, 16);
+    const uint32_t aQhi = smem_u32(Qhi), aQlo = smem_u32(Qlo), aG1 = smem_u32(G1), aQ2 = smem_u32(Q2), aG2 = smem_u32(G2), aPad = smem_u32(s.pad);
+    uint32_t pcount[2] = {0, 0};
+    auto issue_st = [&](int w, int j) {
+      const uint32_t d = tb + (uint32_t)w * 128, x = tb + 320 + (uint32_t)w * 32;
+      const uint64_t dQhi = smem_desc(aQhi + j * (BK * 32), 128, 256), dQlo = smem_desc(aQlo + j * (BK * 32), 128, 256);
+      mma_ts(d, x, dQhi, idS, 0);
+      mma_ts(d, x + 8, dQhi, idS, 1);
+      mma_ts(d, x, dQlo, idS, 1);
+      mma_ts(d + 64, x + 16, smem_desc(aG1 + j * (BK * 32), 128, 256), idS, 0);
+    };
+    auto issue_acc = [&](int w, int j) {
+      const int nsteps = (min(BK, a.Lq - j * BK) + 7) >> 3;
+      const uint32_t dK = tb + 256 + (uint32_t)w * 32, dV = dK + 16;
+      for (int t = 0; t < nsteps; ++t) {
+        const uint32_t off = (uint32_t)(j * (BK / 8) + t) * 256;
+        const uint32_t g2 = aG2 + off, q2 = aQ2 + off;
+        const uint32_t acc = (j > 0 || t > 0) ? 1u : 0u;
+        mma_ts(dV, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(g2, 128, aPad - g2), idA, acc);
+        mma_ts(dK, tb + (uint32_t)w * 128 + 64 + (uint32_t)t * 8, smem_desc(q2, 128, aPad - q2), idA, acc);
+      }
+    };
+    for (int it = 0; it < NIT; ++it) {
+      for (int w = 0; w < 2; ++w) {
+        if (2 * it + w >= nKT) continue;
+        mbar_wait(&x_ready[w], it & 1);
+        fence_after();
+        if (elect_one()) { issue_st(w, 0); commit(&s_ready[w]); }
+        __syncwarp();
+      }
+      for (int j = 0; j < NQ; ++j) {
+        for (int w = 0; w < 2; ++w) {
+          if (2 * it + w >= nKT) continue;
+          mbar_wait(&p_ready[w], pcount[w] & 1); pcount[w]++;
+          fence_after();
+          if (elect_one()) {
+            issue_acc(w, j);
+            if (j + 1 < NQ) { issue_st(w, j + 1); commit(&s_ready[w]); }
+            else commit(&o_ready[w]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    const int wg = warp >> 2, r = tid & 127;
+    const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tb + tlane + (uint32_t)wg * 128, tA = tb + tlane + 256 + (uint32_t)wg * 32, tX = tb + tlane + 320 + (uint32_t)wg * 32;
+    uint32_t scount = 0;
+    for (int it = 0; it < NIT; ++it) {
+      const int kt = 2 * it + wg;
+      if (kt >= nKT) break;
+      const int cs = kt * TCQ + r;
+      const bool valid = cs < LkC;
+      const int jk = valid ? (int)s.idx[cs] : 0;
+      float k[8], v[8], hi[8], lo[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { k[c] = 0.f; v[c] = 0.f; }
+      if (valid) {
+        ld8g(k, a.k + ((long long)n * a.Lk + jk) * a.ldk + h * 8);
+        ld8g(v, a.v + ((long long)n * a.Lk + jk) * a.ldv + h * 8);
+      }
+      split8(k, hi, lo);
+      rn8(v, v);
+      tmem_put8(tX, hi); tmem_put8(tX + 8, lo); tmem_put8(tX + 16, v);
+      tmem_wait_st();
+      fence_before();
+      mbar_arrive(&x_ready[wg]);
+      const uint32_t cw = dc.on ? drop_col_word(dc, nh, cs) : 1u;
+      for (int j = 0; j < NQ; ++j) {
+        mbar_wait(&s_ready[wg], scount & 1); scount++;
+        fence_after();
+        uint32_t sr[64], tr[64];
+        tmem_ld32(tS, sr); tmem_ld32(tS + 32, sr + 32); tmem_ld32(tS + 64, tr); tmem_ld32(tS + 96, tr + 32);
+        tmem_wait_ld();
+        const float4* l4 = reinterpret_cast<const float4*>(s.f0 + j * BK);
+        const float4* d4 = reinterpret_cast<const float4*>(s.f1 + j * BK);
+        const uint4* w4 = reinterpret_cast<const uint4*>(s.w0 + j * BK);
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) {
+          const float4 lv = l4[cc], dv = d4[cc];
+          const float ll[4] = {lv.x, lv.y, lv.z, lv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+          if (!dc.on) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = cc * 4 + e;
+              const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
+              sr[c] = __float_as_uint(p) + 0x1000u;
+              tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - dd[e])) + 0x1000u;
+            }
+          } else {
+            const uint4 wv = w4[cc];
+            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = cc * 4 + e;
+              const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
+              const float dm = (ww[e] * cw >= dc.thr) ? dc.scale : 0.f;
+              sr[c] = __float_as_uint(p * dm) + 0x1000u;
+              tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) * dm - dd[e])) + 0x1000u;
+            }
+          }
+        }
+        tmem_st32(tS, sr); tmem_st32(tS + 32, sr + 32); tmem_st32(tS + 64, tr); tmem_st32(tS + 96, tr + 32);
+        tmem_wait_st();
+        fence_before();
+        mbar_arrive(&p_ready[wg]);
+      }
+      mbar_wait(&o_ready[wg], it & 1);
+      fence_after();
+      uint32_t o[32];
+      tmem_ld32(tA, o); tmem_wait_ld();
+      if (valid) {
+        float dk[8], dv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { dk[c] = __uint_as_float(o[c]) * kLn2; dv[c] = __uint_as_float(o[16 + c]); }   // Q carried log2(e)
+        st8g(a.dk + ((long long)n * a.Lk + jk) * a.lddk + h * 8, dk);
+        st8g(a.dv + ((long long)n * a.Lk + jk) * a.lddv + h * 8, dv);
+      }
+      fence_before();
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 8) { fence_after(); tmem_dealloc<512>(tb); }
+}
+
+// ------------------------------------------------------------------------------------------------
+static bool env_flag(const char* name) { const char* e = getenv(name); return e && e[0] && e[0] != '0'; }
+
+bool attn_tc_eligible(const AttnArgs& a) {
+  static const bool off = env_flag("VAESNE_NO_TC");
+  if (off) return false;
+  // long attention only: the tile machinery needs >= 2 row tiles to be worth a CTA
+  return a.Lq >= 256 && a.Lk >= 256 && a.Lk <= MAXL && a.Lq <= MAXL && a.N <= 65535;
+}
+bool attn_tc_has_bwd() { return true; }
+
+template <typename K>
+static int tc_configure(K k, size_t bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) { set_error("%s: cannot reserve %zu B of shared memory: %s", what, bytes, cudaGetErrorString(e)); return V_ECUDA; }
+  return V_OK;
+}
+
+int attn_tc_fwd(const AttnArgs& a, cudaStream_t st) {
+  static int cfg = tc_configure(attn_tc_fwd_kernel, FWD_SMEM, "attn_tc_fwd");
+  if (cfg) return cfg;
+  attn_tc_fwd_kernel<<<dim3(kH, a.N), dim3(NTHREADS), FWD_SMEM, st>>>(a);
+  return check_launch("attn_tc_fwd");
+}
+
+int attn_tc_bwd(const AttnArgs& a, cudaStream_t st) {
+  static int cfg1 = tc_configure(attn_tc_dq_kernel, DQ_SMEM, "attn_tc_dq");
+  static int cfg2 = tc_configure(attn_tc_dkv_kernel, DKV_SMEM, "attn_tc_dkv");
+  if (cfg1) return cfg1;
+  if (cfg2) return cfg2;
+  attn_tc_dq_kernel<<<dim3(kH, a.N), dim3(NTHREADS), DQ_SMEM, st>>>(a);
+  int rc = check_launch("attn_tc_dq"); if (rc) return rc;
+  attn_tc_dkv_kernel<<<dim3(kH, a.N), dim3(NTHREADS), DKV_SMEM, st>>>(a);
+  return check_launch("attn_tc_dkv");
+}
+
+}  // namespace vaesne

@@ -31,7 +31,7 @@ def hash_ctr(s0, s1, stream, ctr):
 
 
 def drop_threshold(p):
-    t = float(p) * 4294967296.0
+    t = float(np.float32(p)) * 4294967296.0      # the C ABI carries p as a float
     thr = 0xFFFFFFFF if t >= 4294967295.0 else int(t)
     scale = np.float32(1.0 / (1.0 - thr / 4294967296.0))
     return thr, float(scale)

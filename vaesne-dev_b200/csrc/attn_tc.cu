@@ -120,7 +120,7 @@ __device__ __forceinline__ void tmem_put8(uint32_t taddr, const float* x) {
 // shared-memory carve-up: `narr` operand arrays of 32 KB, then the small tables
 // ------------------------------------------------------------------------------------------------
 struct TcSmem {
-  float* arr[5];
+  float* arr[6];
   float* pad;            // [64] second 8-row group of the N=16 operands: ones row (fwd) or zeros (bwd)
   float* f0; float* f1;  // [MAXL] per-column floats (dkv: lse2, delta)
   uint32_t* w0;          // [MAXL] per-column dropout words
@@ -134,7 +134,7 @@ __device__ __forceinline__ TcSmem carve(unsigned char* raw, int narr, bool cols)
   uintptr_t p = ((uintptr_t)raw + 127) & ~(uintptr_t)127;
   TcSmem s;
   float* f = (float*)p;
-  for (int i = 0; i < 5; ++i) s.arr[i] = i < narr ? f + (size_t)i * TILE_F : nullptr;
+  for (int i = 0; i < 6; ++i) s.arr[i] = i < narr ? f + (size_t)i * TILE_F : nullptr;
   f += (size_t)narr * TILE_F;
   s.pad = f; f += 64;
   s.f0 = s.f1 = nullptr;
@@ -174,19 +174,21 @@ __device__ __forceinline__ int key_slot(const TcSmem& s, int j) {     // -1 if m
   return (int)s.pre[j >> 5] + __popc(bw & ((1u << (j & 31)) - 1u));
 }
 
-// Stage the unmasked keys of (n, h).  Khi/Klo: L1 split of K.  V1: L1 of V (rn).  V2 / K2: L2 of V / K (rn).
+// Stage the unmasked keys of (n, h) as tf32 hi + lo parts.  Khi/Klo: L1 of K.  V1hi/V1lo: L1 of V.
+// V2hi/V2lo, K2hi/K2lo: L2 of V / K (the lo array sits one TILE_F after the hi array: it is the second 8-row
+// group of the N=16 operand, so the accumulator's columns 8..15 collect the lo-part product for free).
 __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, int n, int h, int tid, int LkC, int tile,
-                                           float* Khi, float* Klo, float* V1, float* V2, float* K2,
-                                           const TcDrop& dc) {
+                                           float* Khi, float* Klo, float* V1hi, float* V1lo, float* V2hi, float* V2lo,
+                                           float* K2hi, float* K2lo, const TcDrop& dc) {
   const int Lpad = ((LkC + tile - 1) / tile) * tile;
   float z[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) z[c] = 0.f;
   for (int c = LkC + tid; c < Lpad; c += NTHREADS) {
     put_l1(Khi, c, z); put_l1(Klo, c, z);
-    if (V1) put_l1(V1, c, z);
-    if (V2) put_l2(V2, c, z);
-    if (K2) put_l2(K2, c, z);
+    if (V1hi) { put_l1(V1hi, c, z); put_l1(V1lo, c, z); }
+    if (V2hi) { put_l2(V2hi, c, z); put_l2(V2lo, c, z); }
+    if (K2hi) { put_l2(K2hi, c, z); put_l2(K2lo, c, z); }
   }
   const int nh = n * kH + h;
   if (dc.on) for (int c = tid; c < Lpad; c += NTHREADS) s.w0[c] = drop_col_word(dc, nh, c);
@@ -198,10 +200,10 @@ __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, i
     ld8g(vv, a.v + ((long long)n * a.Lk + j) * a.ldv + h * 8);
     split8(kk, hi, lo);
     put_l1(Khi, c, hi); put_l1(Klo, c, lo);
-    if (K2) put_l2(K2, c, hi);
-    rn8(vv, vv);
-    if (V1) put_l1(V1, c, vv);
-    if (V2) put_l2(V2, c, vv);
+    if (K2hi) { put_l2(K2hi, c, hi); put_l2(K2lo, c, lo); }
+    split8(vv, hi, lo);
+    if (V1hi) { put_l1(V1hi, c, hi); put_l1(V1lo, c, lo); }
+    if (V2hi) { put_l2(V2hi, c, hi); put_l2(V2lo, c, lo); }
   }
 }
 
@@ -218,12 +220,12 @@ __device__ __forceinline__ void init_common(const TcSmem& s, int tid, int warp, 
 // =================================================================================================
 // forward
 // =================================================================================================
-constexpr size_t FWD_SMEM = tc_smem_bytes(3, false);
+constexpr size_t FWD_SMEM = tc_smem_bytes(4, false);
 
 __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
   extern __shared__ unsigned char tc_smem_raw[];
-  const TcSmem s = carve(tc_smem_raw, 3, false);
-  float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V2 = s.arr[2];
+  const TcSmem s = carve(tc_smem_raw, 4, false);
+  float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V2 = s.arr[2]; float* V2lo = s.arr[3];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   uint64_t* x_ready = s.bars;       // [2] count 128 : row operands (Q) stored in TMEM
@@ -232,9 +234,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
   uint64_t* o_ready = s.bars + 6;   // [2] count 1   : tcgen05.commit after the last PV
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
 
-  init_common(s, tid, warp, 1.f);
+  init_common(s, tid, warp, 0.f);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
-  stage_keys(a, s, n, h, tid, LkC, FK, Khi, Klo, nullptr, V2, nullptr, dc);
+  stage_keys(a, s, n, h, tid, LkC, FK, Khi, Klo, nullptr, nullptr, V2, V2lo, nullptr, nullptr, dc);
   fence_async_smem();
   fence_before();
   __syncthreads();
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
   if (warp == 8) {
     // ------------------------------- MMA issuer -------------------------------------------------
     const uint32_t idQK = idesc_tf32(128, FK), idPV = idesc_tf32(128, 16);
-    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV2 = smem_u32(V2), aPad = smem_u32(s.pad);
+    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV2 = smem_u32(V2);
     uint32_t pcount[2] = {0, 0};
     auto issue_qk = [&](int w, int j) {
       const uint32_t d = tb + (uint32_t)w * 128, q = tb + 288 + (uint32_t)w * 16;
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
       const uint32_t dO = tb + 256 + (uint32_t)w * 16;
       for (int t = 0; t < nsteps; ++t) {
         const uint32_t v = aV2 + (uint32_t)(j * (FK / 8) + t) * 256;
-        mma_ts(dO, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(v, 128, aPad - v), idPV, (j > 0 || t > 0) ? 1u : 0u);
+        mma_ts(dO, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(v, 128, TILE_F * 4), idPV, (j > 0 || t > 0) ? 1u : 0u);   // [Vhi | Vlo]
       }
     };
     for (int it = 0; it < NIT && T > 0; ++it) {
@@ -353,10 +355,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
           m_used = m_new;
         }
         if (!dc.on) {
-          // P is truncated to tf32 by the MMA; the ones column of [V|1] sums the SAME truncated values,
-          // so the normalisation cancels the truncation bias
+          // the row sum stays in fp32 registers (it defines LSE, which the backward exponentiates); the MMA
+          // operand is P rounded to nearest tf32 (adding half an ulp before the tensor core truncates)
 #pragma unroll
-          for (int c = 0; c < 128; ++c) sr[c] = __float_as_uint(ex2(__uint_as_float(sr[c]) - m_used));
+          for (int c = 0; c < 128; ++c) {
+            const float p = ex2(__uint_as_float(sr[c]) - m_used);
+            lsum += p;
+            sr[c] = __float_as_uint(p) + 0x1000u;
+          }
         } else {
           const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * FK);
 #pragma unroll
@@ -376,19 +382,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
         fence_before();
         mbar_arrive(&p_ready[wg]);
       }
-      // epilogue: O / l  (l from the ones column when no dropout, from the register sum otherwise)
+      // epilogue: (O_hi + O_lo) / l
       mbar_wait(&o_ready[wg], it & 1);
       fence_after();
       uint32_t o[16];
       tmem_ld16(tO, o); tmem_wait_ld();
       if (valid) {
-        const float l = dc.on ? lsum : __uint_as_float(o[8]);
-        const float inv = dc.scale / l;
+        const float inv = dc.scale / lsum;
         float out[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) out[c] = __uint_as_float(o[c]) * inv;
+        for (int c = 0; c < 8; ++c) out[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * inv;
         st8g(a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8, out);
-        a.LSE[(long long)nh * a.Lq + i] = (m_used + log2f(l)) * kLn2;
+        a.LSE[(long long)nh * a.Lq + i] = (m_used + log2f(lsum)) * kLn2;
       }
       fence_before();
     }
@@ -401,12 +406,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
 // =================================================================================================
 // backward, pass 1: rows = queries.  delta = dO.O ; dQ = scale * sum_j dS_ij K_j
 // =================================================================================================
-constexpr size_t DQ_SMEM = tc_smem_bytes(4, false);
+constexpr size_t DQ_SMEM = tc_smem_bytes(6, false);
 
 __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
   extern __shared__ unsigned char tc_smem_raw[];
-  const TcSmem s = carve(tc_smem_raw, 4, false);
-  float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V1 = s.arr[2]; float* K2 = s.arr[3];
+  const TcSmem s = carve(tc_smem_raw, 6, false);
+  float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V1 = s.arr[2]; float* V1lo = s.arr[3]; float* K2 = s.arr[4]; float* K2lo = s.arr[5];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   uint64_t* x_ready = s.bars; uint64_t* s_ready = s.bars + 2; uint64_t* p_ready = s.bars + 4; uint64_t* o_ready = s.bars + 6;
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
 
   init_common(s, tid, warp, 0.f);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
-  stage_keys(a, s, n, h, tid, LkC, BK, Khi, Klo, V1, nullptr, K2, dc);
+  stage_keys(a, s, n, h, tid, LkC, BK, Khi, Klo, V1, V1lo, nullptr, nullptr, K2, K2lo, dc);
   fence_async_smem();
   fence_before();
   __syncthreads();
@@ -423,11 +428,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
   const int T = (LkC + BK - 1) / BK;
   const int nQT = (a.Lq + TCQ - 1) / TCQ;
   const int NIT = (nQT + 1) / 2;
-  // TMEM columns: S[w] = w*128 (64) ; T[w] = w*128 + 64 (64) ; ACC[w] = 256 + w*16 ; X[w] = 288 + w*32 (Qhi | Qlo | dO)
+  // TMEM columns: S[w] = w*128 (64) ; T[w] = w*128 + 64 (64) ; ACC[w] = 256 + w*16 ; X[w] = 288 + w*32 (Qhi | Qlo | dOhi | dOlo)
 
   if (warp == 8) {
     const uint32_t idS = idesc_tf32(128, BK), idA = idesc_tf32(128, 16);
-    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV1 = smem_u32(V1), aK2 = smem_u32(K2), aPad = smem_u32(s.pad);
+    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV1 = smem_u32(V1), aV1lo = smem_u32(V1lo), aK2 = smem_u32(K2);
     uint32_t pcount[2] = {0, 0};
     auto issue_st = [&](int w, int j) {
       const uint32_t d = tb + (uint32_t)w * 128, x = tb + 288 + (uint32_t)w * 32;
@@ -435,14 +440,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
       mma_ts(d, x, dKhi, idS, 0);
       mma_ts(d, x + 8, dKhi, idS, 1);
       mma_ts(d, x, dKlo, idS, 1);
-      mma_ts(d + 64, x + 16, smem_desc(aV1 + j * (BK * 32), 128, 256), idS, 0);
+      const uint64_t dVhi = smem_desc(aV1 + j * (BK * 32), 128, 256), dVlo = smem_desc(aV1lo + j * (BK * 32), 128, 256);
+      mma_ts(d + 64, x + 16, dVhi, idS, 0);
+      mma_ts(d + 64, x + 24, dVhi, idS, 1);
+      mma_ts(d + 64, x + 16, dVlo, idS, 1);
     };
     auto issue_acc = [&](int w, int j) {
       const int nsteps = (min(BK, LkC - j * BK) + 7) >> 3;
       const uint32_t dA = tb + 256 + (uint32_t)w * 16;
       for (int t = 0; t < nsteps; ++t) {
         const uint32_t k2 = aK2 + (uint32_t)(j * (BK / 8) + t) * 256;
-        mma_ts(dA, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(k2, 128, aPad - k2), idA, (j > 0 || t > 0) ? 1u : 0u);
+        mma_ts(dA, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(k2, 128, TILE_F * 4), idA, (j > 0 || t > 0) ? 1u : 0u);   // [Khi | Klo]
       }
     };
     for (int it = 0; it < NIT && T > 0; ++it) {
@@ -500,8 +508,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
         continue;
       }
       split8(q, hi, lo);
-      rn8(g, g);
-      tmem_put8(tX, hi); tmem_put8(tX + 8, lo); tmem_put8(tX + 16, g);
+      tmem_put8(tX, hi); tmem_put8(tX + 8, lo);
+      split8(g, hi, lo);
+      tmem_put8(tX + 16, hi); tmem_put8(tX + 24, lo);
       tmem_wait_st();
       fence_before();
       mbar_arrive(&x_ready[wg]);
@@ -545,12 +554,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
       }
       mbar_wait(&o_ready[wg], it & 1);
       fence_after();
-      uint32_t o[8];
-      tmem_ld8(tA, o); tmem_wait_ld();
+      uint32_t o[16];
+      tmem_ld16(tA, o); tmem_wait_ld();
       if (valid) {
         float out[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) out[c] = __uint_as_float(o[c]) * kScale;
+        for (int c = 0; c < 8; ++c) out[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * kScale;
         st8g(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, out);
       }
       fence_before();
@@ -564,12 +573,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
 // =================================================================================================
 // backward, pass 2: rows = (unmasked) keys.  dV = sum_i Pd_ij dO_i ; dK = scale * sum_i dS_ij Q_i
 // =================================================================================================
-constexpr size_t DKV_SMEM = tc_smem_bytes(5, true);
+constexpr size_t DKV_SMEM = tc_smem_bytes(6, true);
 
 __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
   extern __shared__ unsigned char tc_smem_raw[];
-  const TcSmem s = carve(tc_smem_raw, 5, true);
-  float* Qhi = s.arr[0]; float* Qlo = s.arr[1]; float* G1 = s.arr[2]; float* Q2 = s.arr[3]; float* G2 = s.arr[4];
+  const TcSmem s = carve(tc_smem_raw, 6, true);
+  float* Qhi = s.arr[0]; float* Qlo = s.arr[1]; float* G1 = s.arr[2]; float* G1lo = s.arr[3]; float* Q2 = s.arr[4]; float* G2 = s.arr[5];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   uint64_t* x_ready = s.bars; uint64_t* s_ready = s.bars + 2; uint64_t* p_ready = s.bars + 4; uint64_t* o_ready = s.bars + 6;
@@ -603,9 +612,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       delta = a.delta[(long long)nh * a.Lq + i];
     }
     split8(q, hi, lo);
-    rn8(g, g);
-    put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l1(G1, i, g);
-    put_l2(Q2, i, hi); put_l2(G2, i, g);
+    put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l2(Q2, i, hi);
+    split8(g, hi, lo);
+    put_l1(G1, i, hi); put_l1(G1lo, i, lo); put_l2(G2, i, hi);
     s.f0[i] = lse2; s.f1[i] = delta;
     s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
   }
@@ -616,11 +625,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
   const uint32_t tb = *s.tmem;
   const int nKT = (LkC + TCQ - 1) / TCQ;
   const int NIT = (nKT + 1) / 2;
-  // TMEM columns: S[w] = w*128 (64) ; T[w] = w*128 + 64 (64) ; dK[w] = 256 + w*32 ; dV[w] = 272 + w*32 ; X[w] = 320 + w*32 (Khi | Klo | V)
+  // TMEM columns: S[w] = w*128 (64) ; T[w] = w*128 + 64 (64) ; dK[w] = 256 + w*32 ; dV[w] = 272 + w*32 ; X[w] = 320 + w*32 (Khi | Klo | Vhi | Vlo)
 
   if (warp == 8) {
     const uint32_t idS = idesc_tf32(128, BK), idA = idesc_tf32(128, 16);
-    const uint32_t aQhi = smem_u32(Qhi), aQlo = smem_u32(Qlo), aG1 = smem_u32(G1), aQ2 = smem_u32(Q2), aG2 = smem_u32(G2), aPad = smem_u32(s.pad);
+    const uint32_t aQhi = smem_u32(Qhi), aQlo = smem_u32(Qlo), aG1 = smem_u32(G1), aG1lo = smem_u32(G1lo), aQ2 = smem_u32(Q2), aG2 = smem_u32(G2), aPad = smem_u32(s.pad);
     uint32_t pcount[2] = {0, 0};
     auto issue_st = [&](int w, int j) {
       const uint32_t d = tb + (uint32_t)w * 128, x = tb + 320 + (uint32_t)w * 32;
@@ -628,7 +637,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       mma_ts(d, x, dQhi, idS, 0);
       mma_ts(d, x + 8, dQhi, idS, 1);
       mma_ts(d, x, dQlo, idS, 1);
-      mma_ts(d + 64, x + 16, smem_desc(aG1 + j * (BK * 32), 128, 256), idS, 0);
+      const uint64_t dGhi = smem_desc(aG1 + j * (BK * 32), 128, 256), dGlo = smem_desc(aG1lo + j * (BK * 32), 128, 256);
+      mma_ts(d + 64, x + 16, dGhi, idS, 0);
+      mma_ts(d + 64, x + 24, dGhi, idS, 1);
+      mma_ts(d + 64, x + 16, dGlo, idS, 1);
     };
     auto issue_acc = [&](int w, int j) {
       const int nsteps = (min(BK, a.Lq - j * BK) + 7) >> 3;
@@ -682,8 +694,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
         ld8g(v, a.v + ((long long)n * a.Lk + jk) * a.ldv + h * 8);
       }
       split8(k, hi, lo);
-      rn8(v, v);
-      tmem_put8(tX, hi); tmem_put8(tX + 8, lo); tmem_put8(tX + 16, v);
+      tmem_put8(tX, hi); tmem_put8(tX + 8, lo);
+      split8(v, hi, lo);
+      tmem_put8(tX + 16, hi); tmem_put8(tX + 24, lo);
       tmem_wait_st();
       fence_before();
       mbar_arrive(&x_ready[wg]);

@@ -43,7 +43,20 @@ LIN_CASES = [
     dict(id="32x32_ln", T=300, K=32, N=32, act=0, ln=True),
     dict(id="32x32_ln_strided", T=65, K=32, N=32, act=0, ln=True, strided=True),
     dict(id="32x64_strided_out", T=65, K=32, N=64, act=0, strided=True),
+    # many tiles per persistent CTA + a ragged tail (the tcgen05 kernels keep dW in TMEM across tiles)
+    dict(id="32x32_ln_big", T=128 * 700 + 37, K=32, N=32, act=0, ln=True, big=True),
+    dict(id="32x96_none_big", T=128 * 300 + 1, K=32, N=96, act=0, big=True),
+    dict(id="32x64_none_big_strided", T=128 * 300 + 127, K=32, N=64, act=0, strided=True, big=True),
+    dict(id="32x32_gelu_H_big", T=128 * 610 + 5, K=32, N=32, act=2, H=True, big=True),
+    dict(id="32x32_relu_xadd_big", T=128 * 300 + 64, K=32, N=32, act=1, xadd=True, big=True),
 ]
+LIN_CASES_SMALL = [c for c in LIN_CASES if not c.get("big")]
+
+
+def lin_dw_tol(c, device):
+    """dW of the tcgen05 path (K=32, N in 32/64/96, CUDA only) contracts tf32-rounded operands over the tokens."""
+    tc = str(device).startswith("cuda") and c["K"] == 32 and c["N"] in (32, 64, 96) and not c.get("xadd")
+    return TOL
 
 
 def run_lin_case(c, device):
@@ -114,7 +127,7 @@ def run_lin_case(c, device):
     dYc = strided(dY.to(device), Nn + 8) if st else dY.to(device)
     P.lin_bwd(dYc, Xc, W.to(device), Xadd=_dev(Xadd, device), act=act, A=A, dW=dW, db=db, dX=dX, dX_acc=True, **kw)
     assert rel_err(dX.cpu() - 0.5, refs["dX"]) < TOL, ("dX", rel_err(dX.cpu() - 0.5, refs["dX"]))
-    assert rel_err(dW.cpu(), refs["dW"]) < TOL, ("dW", rel_err(dW.cpu(), refs["dW"]))
+    assert rel_err(dW.cpu(), refs["dW"]) < lin_dw_tol(c, device), ("dW", rel_err(dW.cpu(), refs["dW"]))
     assert rel_err(db.cpu(), refs["db"]) < TOL
     if ln:
         assert rel_err(kw["dR"].cpu(), refs["dR"]) < TOL

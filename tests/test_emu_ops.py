@@ -9,7 +9,7 @@ from helpers import rel_err
 import ops_cases as OC
 
 
-@pytest.mark.parametrize("case", OC.LIN_CASES, ids=lambda c: c["id"])
+@pytest.mark.parametrize("case", OC.LIN_CASES_SMALL, ids=lambda c: c["id"])
 def test_lin(emu, case):
     OC.run_lin_case(case, "cpu")
 

@@ -10,6 +10,7 @@
 // flushed with one atomicAdd per element per CTA.
 #include "common.cuh"
 #include "vaesne_b200.h"
+#include "lin_args.cuh"
 
 namespace vaesne {
 
@@ -43,18 +44,6 @@ __host__ __device__ __forceinline__ bool vec_ok(const void* p, long long ld) {
   return p == nullptr || ((((uintptr_t)p) & 15) == 0 && (ld & 3) == 0);
 }
 
-struct LinFwd {
-  const float* X; long long ldx; const float* Xadd; long long ldxa;
-  int T, K, N;
-  const float* W; const float* b;
-  int act;
-  float* H; long long ldh;
-  const float* R; long long ldr;
-  const float* gamma; const float* beta; float eps;
-  float* S;
-  float p_drop; const uint64_t* seed; uint32_t stream_id;
-  float* Y; long long ldy;
-};
 
 template <int NC, bool LN>
 __global__ void __launch_bounds__(TT) lin_fwd_kernel(LinFwd a) {
@@ -158,23 +147,6 @@ __global__ void __launch_bounds__(TT) lin_fwd_kernel(LinFwd a) {
   }
 }
 
-struct LinBwd {
-  const float* dY; long long lddy;
-  int T, K, N;
-  // LayerNorm + dropout part (S != nullptr enables it)
-  const float* S; const float* gamma; float eps;
-  float* dgamma; float* dbeta;
-  float* dR; long long lddr; int dR_acc;
-  float p_drop; const uint64_t* seed; uint32_t stream_id;
-  // activation
-  int act; const float* A; long long lda;
-  // linear
-  const float* X; long long ldx; const float* Xadd; long long ldxa;
-  const float* W;
-  float* dW; float* db;
-  float* dX; long long lddx; int dX_acc;
-  int smem_acc;     // 1: per-CTA dW accumulators live in shared memory; 0: flush every tile with atomics
-};
 
 template <bool LN>
 __global__ void __launch_bounds__(TT) lin_bwd_kernel(LinBwd a) {
@@ -417,6 +389,9 @@ extern "C" int vaesne_lin_fwd(const float* X, long long ldx, const float* Xadd, 
     V_REQUIRE(act == 0 && H == nullptr, V_EUNSUPPORTED, "lin_fwd: LayerNorm epilogue excludes activation");
   }
   LinFwd a{X, ldx, Xadd, ldxa, T, K, N, W, b, act, H, ldh, R, ldr, gamma, beta, eps, S, p_drop, seed, stream_id, Y, ldy};
+#ifndef VAESNE_EMU
+  if (lin_tc_fwd_eligible(a)) return lin_tc_fwd(a, (cudaStream_t)stream);
+#endif
   const int NC = ln ? 32 : (N <= 4 ? 4 : (N <= 8 ? 8 : 32));
   const int Np = ((N + NC - 1) / NC) * NC;
   const size_t smem = sizeof(float) * ((size_t)K * Np + Np + 64 + (size_t)TT * (K + 1));
@@ -446,6 +421,9 @@ extern "C" int vaesne_lin_bwd(const float* dY, long long lddy, int T, int K, int
   if (ln) V_REQUIRE(N == 32 && gamma && act == 0, V_EUNSUPPORTED, "lin_bwd: LayerNorm path needs N==32, gamma, act none");
   LinBwd a{dY, lddy, T, K, N, S, gamma, eps, dgamma, dbeta, dR, lddr, dR_acc, p_drop, seed, stream_id,
            act, A, lda, X, ldx, Xadd, ldxa, W, dW, db, dX, lddx, dX_acc, 1};
+#ifndef VAESNE_EMU
+  if (lin_tc_bwd_eligible(a)) return lin_tc_bwd(a, (cudaStream_t)stream);
+#endif
   const int Kp = ((K + 7) / 8) * 8;
   a.smem_acc = (N * Kp <= 96 * 96) ? 1 : 0;
   const size_t smem = sizeof(float) * ((size_t)(1 + a.smem_acc) * N * Kp + ((N + 3) / 4) * 4 + 96 + (size_t)TT * (Kp + 4) + (size_t)TT * (N + 1));

@@ -1,0 +1,555 @@
+// Blackwell-native token-wise linear layers of the transformer blocks (model_dim 32):
+//   forward   Y = act(X W^T + b)            N in {32, 64, 96}   (in_proj, q / kv projections, ffn.0, MLP heads)
+//             Y = LayerNorm(R + dropout(X W^T + b))   N = 32    (out_proj / ffn.2 + residual + LN, util_layers.py:292,303,307)
+//   backward  dZ from (LayerNorm+dropout | activation) ; dX = dZ W ; dW += dZ^T X ; db, dgamma, dbeta
+// Same arithmetic as lin.cu (its docstring cites the reference lines); restructured for sm_100a because these
+// kernels move 384..640 B per token and must run at HBM speed:
+//
+//   * every global access is coalesced: 128-token tiles travel global -> shared with 16-byte cp.async into
+//     rows padded to 144 B, and results leave through the same padded tiles with 16-byte coalesced stores.
+//     A thread then reads / writes ITS row with conflict-free 16-byte shared accesses (stride 36 words).
+//   * thread r owns token r of the tile = TMEM lane r: the LayerNorm / activation / dropout epilogues are
+//     plain per-thread register code, no shuffles.
+//   * the 32-wide contractions run on the tensor core: the row is split into tf32 hi + lo parts and stored
+//     to TMEM as the A operand (tcgen05.st), W (hi + lo, K-major canonical layout) is staged once per CTA,
+//     3 MMAs per 8-wide K step restore fp32-level products (kind::tf32 truncates its inputs), fp32
+//     accumulation in TMEM, one elected lane issues, tcgen05.commit -> mbarrier.
+//   * dW is a contraction over the 128 tokens of the tile: dZ^T and X^T are written (conflict-free, 144-byte
+//     chunk stride) as K-major operands, 16 MMAs per tile accumulate into TMEM across ALL tiles of the
+//     persistent CTA, and are flushed with one atomicAdd per element per CTA at the end.  Operands are
+//     rounded to nearest tf32 (unbiased; the sum runs over every token of the batch).
+//   * db / dgamma / dbeta: fp32 butterfly transpose-reductions (31 shuffles per 32 columns), shared-memory
+//     accumulators, one atomicAdd per element per CTA.
+#include "common.cuh"
+#include "vaesne_b200.h"
+#include "lin_args.cuh"
+#include "tc_common.cuh"
+#include <stdlib.h>
+
+namespace vaesne {
+using namespace tc;
+
+constexpr int LT = 128;              // tokens per tile == threads per CTA == TMEM lanes
+constexpr int PITCH = 36;            // floats per padded shared-memory row (144 B)
+constexpr int TILE = LT * PITCH;     // floats per staged tile (18 KB)
+
+__device__ __forceinline__ bool lelect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void cp_async16(float* smem, const float* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// rows [t0, t0 + rows) x 32 floats of a row-strided matrix -> padded tile (coalesced: 8 lanes per 128-byte row)
+__device__ __forceinline__ void load_tile(float* dst, const float* src, long long ld, long long t0, int rows, int tid) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int id = it * LT + tid, r = id >> 3, c = id & 7;
+    if (r < rows) cp_async16(dst + r * PITCH + c * 4, src + (t0 + r) * ld + c * 4);
+  }
+}
+template <bool ACC>
+__device__ __forceinline__ void store_tile(float* dst, long long ld, const float* src, long long t0, int rows, int tid) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int id = it * LT + tid, r = id >> 3, c = id & 7;
+    if (r < rows) {
+      float4 v = *reinterpret_cast<const float4*>(src + r * PITCH + c * 4);
+      float4* g = reinterpret_cast<float4*>(dst + (t0 + r) * ld + c * 4);
+      if (ACC) { const float4 o = *g; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+      *g = v;
+    }
+  }
+}
+__device__ __forceinline__ void lds_row(float* v, const float* row) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = reinterpret_cast<const float4*>(row)[j];
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void sts_row(float* row, const float* v) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(row)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void tmem_put32(uint32_t taddr, const float* x) {
+  uint32_t u[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) u[c] = __float_as_uint(x[c]);
+  tmem_st32(taddr, u);
+}
+__device__ __forceinline__ float rna_tf32(float x) { uint32_t h; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x)); return __uint_as_float(h); }
+
+// lane l <- sum over the warp of v[l]   (v is destroyed)
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// K-major canonical (no swizzle) operand of a [rows x 32] matrix, contraction over the 32 columns:
+// 8-row groups of 1 KB, inside a group 8 chunks (4 columns = 16 B) of 128 B.   LBO = 128 B, SBO = 1024 B.
+__device__ __forceinline__ int wcanon(int row, int k) { return (row >> 3) * 256 + (k >> 2) * 32 + (row & 7) * 4 + (k & 3); }
+// transposed operand of a 128-token tile, contraction over the tokens: element (row, token t); chunks of 4 tokens
+// 144 B apart (conflict-free scalar stores by 32 consecutive tokens), 8-row groups 4608 B apart.
+__device__ __forceinline__ int tcanon(int row, int t) { return (row >> 3) * 1152 + (t >> 2) * 36 + (row & 7) * 4 + (t & 3); }
+
+// =================================================================================================
+// forward
+// =================================================================================================
+template <int NCH>
+__host__ __device__ constexpr size_t lin_tc_fwd_smem() { return 128 + sizeof(float) * (2 * NCH * 1024 + 96 + 64 + 2 * TILE) + 32; }
+
+template <int NCH, bool LN>
+__global__ void __launch_bounds__(LT, 2) lin_tc_fwd_kernel(LinFwd a) {
+  constexpr int N = NCH * 32;
+  constexpr int COLS = (64 + N) <= 128 ? 128 : 256;
+  extern __shared__ unsigned char lin_tc_raw[];
+  float* Whi = reinterpret_cast<float*>(((uintptr_t)lin_tc_raw + 127) & ~(uintptr_t)127);
+  float* Wlo = Whi + NCH * 1024;
+  float* sB = Wlo + NCH * 1024;      // [96]
+  float* sG = sB + 96;               // [32]
+  float* sBe = sG + 32;              // [32]
+  float* bufX = sBe + 32;            // X tile, later output staging
+  float* bufR = bufX + TILE;         // R (LN) or Xadd tile, later output staging
+  uint64_t* bar = reinterpret_cast<uint64_t*>(bufR + TILE);
+  uint32_t* tmem_s = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  for (int i = tid; i < N * 32; i += LT) {
+    const int n = i >> 5, k = i & 31;
+    float hi, lo;
+    split_tf32(a.W[i], hi, lo);
+    Whi[wcanon(n, k)] = hi; Wlo[wcanon(n, k)] = lo;
+  }
+  for (int i = tid; i < N; i += LT) sB[i] = a.b ? a.b[i] : 0.f;
+  if (LN && tid < 32) { sG[tid] = a.gamma[tid]; sBe[tid] = a.beta[tid]; }
+  if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc<COLS>(tmem_s);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = *tmem_s;
+  const uint32_t tl = tb + ((uint32_t)(warp * 32) << 16);      // this thread's lane
+  const uint32_t idesc = idesc_tf32(128, N);
+  const uint32_t aWhi = smem_u32(Whi), aWlo = smem_u32(Wlo);
+  const DropCfg dc = make_drop(LN ? a.p_drop : 0.f, a.seed, a.stream_id);
+  float* myX = bufX + tid * PITCH; float* myR = bufR + tid * PITCH;
+  uint32_t ph = 0;
+
+  const int ntiles = (a.T + LT - 1) / LT;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long t0 = (long long)tile * LT;
+    const int rows = min(LT, a.T - (int)t0);
+    const long long t = t0 + tid;
+    load_tile(bufX, a.X, a.ldx, t0, rows, tid);
+    if (LN) load_tile(bufR, a.R, a.ldr, t0, rows, tid);
+    else if (a.Xadd) load_tile(bufR, a.Xadd, a.ldxa, t0, rows, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    {
+      float x[32], hi[32], lo[32];
+      lds_row(x, myX);
+      if (!LN && a.Xadd) {
+        float xa[32];
+        lds_row(xa, myR);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] += xa[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) split_tf32(x[j], hi[j], lo[j]);
+      tmem_put32(tl, hi); tmem_put32(tl + 32, lo);
+      tmem_wait_st();
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      fence_after();
+      if (lelect_one()) {
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const uint64_t bhi = smem_desc(aWhi + s * 256, 128, 1024), blo = smem_desc(aWlo + s * 256, 128, 1024);
+          mma_ts(tb + 64, tb + s * 8, bhi, idesc, s > 0 ? 1u : 0u);
+          mma_ts(tb + 64, tb + 32 + s * 8, bhi, idesc, 1u);
+          mma_ts(tb + 64, tb + s * 8, blo, idesc, 1u);
+        }
+        commit(bar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(bar, ph); ph ^= 1u;
+    fence_after();
+    if (LN) {
+      uint32_t d[32];
+      tmem_ld32(tl + 64, d); tmem_wait_ld();
+      float s[32];
+      lds_row(s, myR);
+      float mean = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float v = __uint_as_float(d[j]) + sB[j];
+        if (dc.on) v *= drop_mult(dc, (uint64_t)t * 32 + j);
+        s[j] += v;
+        mean += s[j];
+      }
+      mean *= (1.f / 32);
+      float var = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { const float dd = s[j] - mean; var = fmaf(dd, dd, var); }
+      const float rstd = 1.f / sqrtf(var * (1.f / 32) + a.eps);
+      if (a.S) sts_row(myX, s);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s[j] = (s[j] - mean) * rstd * sG[j] + sBe[j];
+      sts_row(myR, s);
+      __syncthreads();
+      if (a.S) store_tile<false>(a.S, 32, bufX, t0, rows, tid);
+      store_tile<false>(a.Y, a.ldy, bufR, t0, rows, tid);
+    } else {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t d[32];
+        tmem_ld32(tl + 64 + c * 32, d); tmem_wait_ld();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(d[j]) + sB[c * 32 + j];
+        if (c > 0) __syncthreads();                 // previous chunk's coalesced stores have read the staging tiles
+        if (a.H) sts_row(myR, v);
+        if (a.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (a.act == 2) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        sts_row(myX, v);
+        __syncthreads();
+        if (a.H) store_tile<false>(a.H + c * 32, a.ldh, bufR, t0, rows, tid);
+        store_tile<false>(a.Y + c * 32, a.ldy, bufX, t0, rows, tid);
+      }
+    }
+    fence_before();
+    __syncthreads();        // staging tiles are free again; D has been read by every thread
+    fence_after();
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) { fence_after(); tmem_dealloc<COLS>(tb); }
+}
+
+// =================================================================================================
+// backward
+// =================================================================================================
+// shared memory (tiles of 18 KB):  dZT_hi | B1 = dZT_lo | XT_hi | B2 = XT_lo | B0   then W^T hi/lo and the small tables.
+//   B0: dY chunk (cp.async) -> dR staging.   B1: S / activation input (cp.async), then, once every thread has read
+//   its row, the lo half of dZ^T.   B2: X tile (cp.async), then the lo half of X^T, then (after the MMAs) dX staging.
+// dW for one 32-row chunk of W: ONE MMA per 8-token K step with A = [dZ^T_hi ; dZ^T_lo] stacked along M (rows 0-31 /
+// 32-63) and B = [X^T_hi ; X^T_lo] stacked along N (64 columns): D[n][k] + D[n][32+k] + D[32+n][k] is the fp32-level
+// product (hi*hi + hi*lo + lo*hi), accumulated in TMEM across all tiles of the CTA.
+template <int NCH>
+__host__ __device__ constexpr size_t lin_tc_bwd_smem() { return 128 + sizeof(float) * (2 * NCH * 1024 + 5 * TILE + 32 * 3 + 64) + 32; }
+
+template <int NCH, bool LN>
+__global__ void __launch_bounds__(LT, 2) lin_tc_bwd_kernel(LinBwd a) {
+  constexpr int N = NCH * 32;
+  constexpr int COLS = 256;            // A hi|lo 64 + dX 32 + dW 64*NCH  (NCH <= 2)
+  extern __shared__ unsigned char lin_tc_raw[];
+  float* dZT = reinterpret_cast<float*>(((uintptr_t)lin_tc_raw + 127) & ~(uintptr_t)127);   // first: the M=128 MMA reads 16 row groups from here
+  float* B1 = dZT + TILE;
+  float* XT = B1 + TILE;
+  float* B2 = XT + TILE;
+  float* B0 = B2 + TILE;
+  float* WThi = B0 + TILE;            // [32 rows k][N] canonical: (k>>3)*(N*8) + (n>>2)*32 + (k&7)*4 + (n&3)
+  float* WTlo = WThi + NCH * 1024;
+  float* sG = WTlo + NCH * 1024;      // [32]
+  float* sDg = sG + 32; float* sDbe = sDg + 32;   // [32] each
+  float* sDb = sDbe + 32;             // [64]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sDb + 64);
+  uint32_t* tmem_s = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool wgrad = a.dW != nullptr;
+
+  for (int i = tid; i < N * 32; i += LT) {
+    const int n = i >> 5, k = i & 31;
+    float hi, lo;
+    split_tf32(a.W[i], hi, lo);
+    const int o = (k >> 3) * (N * 8) + (n >> 2) * 32 + (k & 7) * 4 + (n & 3);
+    WThi[o] = hi; WTlo[o] = lo;
+  }
+  if (tid < 32) { sG[tid] = LN ? a.gamma[tid] : 0.f; sDg[tid] = 0.f; sDbe[tid] = 0.f; }
+  if (tid < 64) sDb[tid] = 0.f;
+  if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 0) tmem_alloc<COLS>(tmem_s);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = *tmem_s;
+  const uint32_t tl = tb + ((uint32_t)(warp * 32) << 16);
+  const uint32_t idX = idesc_tf32(128, 32), idW = idesc_tf32(128, 64);
+  const uint32_t aWThi = smem_u32(WThi), aWTlo = smem_u32(WTlo), aZT = smem_u32(dZT), aXT = smem_u32(XT);
+  const DropCfg dc = make_drop(LN ? a.p_drop : 0.f, a.seed, a.stream_id);
+  float* my0 = B0 + tid * PITCH; float* my1 = B1 + tid * PITCH; float* my2 = B2 + tid * PITCH;
+  uint32_t ph = 0;
+  bool pending = false;          // an MMA batch has been committed and not yet waited for
+  bool first_tile = true;
+
+  const int ntiles = (a.T + LT - 1) / LT;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long t0 = (long long)tile * LT;
+    const int rows = min(LT, a.T - (int)t0);
+    const long long t = t0 + tid;
+    const bool active = tid < rows;
+    // the previous tile's MMAs read dZT (incl. B1) and XT (incl. B2): they must be done before the loads land
+    if (pending) { mbar_wait(bar, ph); ph ^= 1u; pending = false; fence_after(); }
+    __syncthreads();
+    if (wgrad) load_tile(B2, a.X, a.ldx, t0, rows, tid);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      if (c > 0) {               // chunk c-1's MMAs read B1 (= dZT_lo); B0 was consumed before its barrier
+        if (pending) { mbar_wait(bar, ph); ph ^= 1u; pending = false; fence_after(); }
+        __syncthreads();
+      }
+      load_tile(B0, a.dY + c * 32, a.lddy, t0, rows, tid);
+      if (LN) load_tile(B1, a.S, 32, t0, rows, tid);
+      else if (a.act != 0) load_tile(B1, a.A + c * 32, a.lda, t0, rows, tid);
+      cp_async_wait_all();
+      __syncthreads();
+      float dz[32];
+      lds_row(dz, my0);
+      if (LN) {
+        float s[32], g[32];
+        lds_row(s, my1);
+        float mean = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mean += s[j];
+        mean *= (1.f / 32);
+        float var = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s[j] -= mean; var = fmaf(s[j], s[j], var); }
+        const float rstd = 1.f / sqrtf(var * (1.f / 32) + a.eps);
+        float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          s[j] *= rstd;                       // xhat
+          g[j] = dz[j] * sG[j];
+          m1 += g[j]; m2 = fmaf(g[j], s[j], m2);
+        }
+        m1 *= (1.f / 32); m2 *= (1.f / 32);
+        if (a.dgamma) {
+          float r1[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r1[j] = active ? dz[j] * s[j] : 0.f;
+          const float cs = warp_colsum32(r1, lane);
+          atomicAdd(&sDg[lane], cs);
+        }
+        if (a.dbeta) {
+          float r2[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r2[j] = active ? dz[j] : 0.f;
+          const float cs = warp_colsum32(r2, lane);
+          atomicAdd(&sDbe[lane], cs);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dz[j] = rstd * (g[j] - m1 - s[j] * m2);     // dS = dR
+        if (a.dR) sts_row(my0, dz);           // own row of B0: already consumed by this thread
+        if (dc.on) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dz[j] *= drop_mult(dc, (uint64_t)t * 32 + j);
+        }
+      } else if (a.act != 0) {
+        float av[32];
+        lds_row(av, my1);
+        if (a.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dz[j] = av[j] > 0.f ? dz[j] : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dz[j] *= gelu_erf_grad(av[j]);
+        }
+      }
+      if (!active) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dz[j] = 0.f;
+      }
+      if (wgrad && a.db) {
+        float r3[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r3[j] = dz[j];
+        const float cs = warp_colsum32(r3, lane);
+        atomicAdd(&sDb[c * 32 + lane], cs);
+      }
+      if (c == 0 && wgrad) {
+        // X row -> X^T hi / lo.  XT_lo aliases the X tile: every thread must have read its row first.
+        float x[32];
+        lds_row(x, my2);
+        __syncthreads();                      // also: every thread has read its B1 row (dZT_lo aliases B1)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float hi, lo;
+          split_tf32(active ? x[j] : 0.f, hi, lo);
+          XT[tcanon(j, tid)] = hi; B2[tcanon(j, tid)] = lo;
+        }
+      } else {
+        __syncthreads();                      // every thread has read its B1 row (dZT_lo aliases B1)
+      }
+      {
+        float hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) split_tf32(dz[j], hi[j], lo[j]);
+        if (a.dX) { tmem_put32(tl, hi); tmem_put32(tl + 32, lo); }
+        if (wgrad) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { dZT[tcanon(j, tid)] = hi[j]; B1[tcanon(j, tid)] = lo[j]; }
+        }
+        tmem_wait_st();
+      }
+      fence_async_smem();
+      fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        fence_after();
+        if (lelect_one()) {
+          if (a.dX) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              const uint32_t off = (uint32_t)(8 * c + 2 * s) * 128;
+              const uint64_t bhi = smem_desc(aWThi + off, 128, N * 32), blo = smem_desc(aWTlo + off, 128, N * 32);
+              mma_ts(tb + 64, tb + s * 8, bhi, idX, (c > 0 || s > 0) ? 1u : 0u);
+              mma_ts(tb + 64, tb + 32 + s * 8, bhi, idX, 1u);
+              mma_ts(tb + 64, tb + s * 8, blo, idX, 1u);
+            }
+          }
+          if (wgrad) {
+#pragma unroll
+            for (int s = 0; s < 16; ++s)
+              mma_ss(tb + 96 + c * 64, smem_desc(aZT + s * 288, 144, 4608), smem_desc(aXT + s * 288, 144, 4608), idW,
+                     (!first_tile || s > 0) ? 1u : 0u);
+          }
+          commit(bar);
+        }
+        __syncwarp();
+      }
+      pending = true;
+      if (LN && a.dR) {        // B0 holds dR rows (written before the barriers above)
+        if (a.dR_acc) store_tile<true>(a.dR, a.lddr, B0, t0, rows, tid);
+        else store_tile<false>(a.dR, a.lddr, B0, t0, rows, tid);
+      }
+    }
+    first_tile = false;
+    if (a.dX) {
+      mbar_wait(bar, ph); ph ^= 1u; pending = false;
+      fence_after();
+      uint32_t d[32];
+      tmem_ld32(tl + 64, d); tmem_wait_ld();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(d[j]);
+      sts_row(my2, v);           // XT_lo (aliased) has been consumed: the MMAs are complete
+      fence_before();
+      __syncthreads();
+      if (a.dX_acc) store_tile<true>(a.dX, a.lddx, B2, t0, rows, tid);
+      else store_tile<false>(a.dX, a.lddx, B2, t0, rows, tid);
+    }
+  }
+  if (pending) { mbar_wait(bar, ph); ph ^= 1u; pending = false; }
+  fence_after();
+  if (wgrad && !first_tile && warp < 2) {
+    // D_dW region c (64 columns): lanes 0-31 hold [hi*hi | hi*lo] of row n = lane, lanes 32-63 hold [lo*hi | lo*lo]
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      uint32_t d[32], e[32];
+      tmem_ld32(tl + 96 + c * 64, d);
+      tmem_ld32(tl + 96 + c * 64 + 32, e);
+      tmem_wait_ld();
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        atomicAdd(&a.dW[(c * 32 + lane) * 32 + k], __uint_as_float(d[k]) + (warp == 0 ? __uint_as_float(e[k]) : 0.f));
+    }
+  }
+  __syncthreads();
+  if (wgrad && a.db && tid < N) atomicAdd(&a.db[tid], sDb[tid]);
+  if (LN && tid < 32) {
+    if (a.dgamma) atomicAdd(&a.dgamma[tid], sDg[tid]);
+    if (a.dbeta) atomicAdd(&a.dbeta[tid], sDbe[tid]);
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) { fence_after(); tmem_dealloc<COLS>(tb); }
+}
+
+// ------------------------------------------------------------------------------------------------
+static bool al16(const void* p, long long ld) { return p == nullptr || ((((uintptr_t)p) & 15) == 0 && (ld & 3) == 0); }
+static bool tc_off() { static const bool off = [] { const char* e = getenv("VAESNE_NO_TC_LIN"); return e && e[0] && e[0] != '0'; }(); return off; }
+
+bool lin_tc_fwd_eligible(const LinFwd& a) {
+  if (tc_off() || a.K != 32 || !(a.N == 32 || a.N == 64 || a.N == 96)) return false;
+  if (a.R && (a.N != 32 || a.Xadd || a.H || a.act != 0)) return false;
+  return al16(a.X, a.ldx) && al16(a.Xadd, a.ldxa) && al16(a.H, a.ldh) && al16(a.R, a.ldr) && al16(a.S, 32) && al16(a.Y, a.ldy);
+}
+bool lin_tc_bwd_eligible(const LinBwd& a) {
+  if (tc_off() || a.K != 32 || !(a.N == 32 || a.N == 64 || a.N == 96) || a.Xadd) return false;
+  if (a.S && (a.N != 32 || a.act != 0)) return false;
+  if (a.N != 32 && a.act != 0) return false;
+  if (!a.dX && !a.dW) return false;
+  return al16(a.dY, a.lddy) && al16(a.S, 32) && al16(a.dR, a.lddr) && al16(a.A, a.lda) && al16(a.X, a.ldx) && al16(a.dX, a.lddx);
+}
+
+static int tc_grid(int T, int ctas_per_sm) {
+  const int ntiles = (T + LT - 1) / LT;
+  return ntiles < 148 * ctas_per_sm ? ntiles : 148 * ctas_per_sm;
+}
+template <typename K, typename A>
+static int tc_launch(K k, size_t smem, int grid, cudaStream_t st, const char* what, const A& args) {
+  static thread_local const void* configured[16] = {};
+  bool done = false;
+  for (auto p : configured) if (p == (const void*)k) done = true;
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("%s: cannot reserve %zu B of shared memory: %s", what, smem, cudaGetErrorString(e)); return V_ECUDA; }
+    for (auto& p : configured) if (!p) { p = (const void*)k; break; }
+  }
+  k<<<grid, LT, smem, st>>>(args);
+  return check_launch(what);
+}
+
+int lin_tc_fwd(const LinFwd& a, cudaStream_t st) {
+  const int g = tc_grid(a.T, a.N <= 64 ? 4 : 2);     // TMEM: 128 columns per CTA up to N = 64, else 256
+  if (a.R) return tc_launch(lin_tc_fwd_kernel<1, true>, lin_tc_fwd_smem<1>(), g, st, "lin_tc_fwd_ln", a);
+  if (a.N == 32) return tc_launch(lin_tc_fwd_kernel<1, false>, lin_tc_fwd_smem<1>(), g, st, "lin_tc_fwd", a);
+  if (a.N == 64) return tc_launch(lin_tc_fwd_kernel<2, false>, lin_tc_fwd_smem<2>(), g, st, "lin_tc_fwd", a);
+  return tc_launch(lin_tc_fwd_kernel<3, false>, lin_tc_fwd_smem<3>(), g, st, "lin_tc_fwd", a);
+}
+static int lin_tc_bwd_one(const LinBwd& a, cudaStream_t st) {
+  const int g = tc_grid(a.T, 2);                     // ~100 KB of shared memory per CTA
+  if (a.S) return tc_launch(lin_tc_bwd_kernel<1, true>, lin_tc_bwd_smem<1>(), g, st, "lin_tc_bwd_ln", a);
+  if (a.N == 32) return tc_launch(lin_tc_bwd_kernel<1, false>, lin_tc_bwd_smem<1>(), g, st, "lin_tc_bwd", a);
+  return tc_launch(lin_tc_bwd_kernel<2, false>, lin_tc_bwd_smem<2>(), g, st, "lin_tc_bwd", a);
+}
+int lin_tc_bwd(const LinBwd& a, cudaStream_t st) {
+  if (a.N <= 64) return lin_tc_bwd_one(a, st);
+  // N = 96 (packed q|k|v projection): rows 0..63 of W, then rows 64..95 accumulating into dX (TMEM holds at most
+  // two 64-column dW regions next to the dX accumulator and the A operand)
+  LinBwd lo = a, hi = a;
+  lo.N = 64;
+  hi.N = 32; hi.dY = a.dY + 64; hi.W = a.W + 64 * 32;
+  if (a.dW) hi.dW = a.dW + 64 * 32;
+  if (a.db) hi.db = a.db + 64;
+  if (a.dX) hi.dX_acc = 1;
+  int rc = lin_tc_bwd_one(lo, st); if (rc) return rc;
+  return lin_tc_bwd_one(hi, st);
+}
+
+}  // namespace vaesne

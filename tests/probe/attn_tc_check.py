@@ -14,7 +14,7 @@ cases = [c for c in OC.ATTN_CASES_FULL if c["Lq"] >= 256 and c["Lk"] >= 256] + [
     dict(id="self_300x260_mask", N=3, Lq=300, Lk=260, mask=True, packed="q+kv"),
     dict(id="self_1024_mask", N=2, Lq=1024, Lk=1024, mask=True, packed="qkv"),
 ]
-for scale in (1.0, 3.0):
+for scale in (() if os.environ.get('ONLY_TIME') else (1.0, 3.0)):
     for c in cases:
         (q, k, v, mask, mask_full, dO), (qd, kd, vd) = OC.make_attn_inputs(c, dev, scale)
         o_ref, lse_ref, dq_ref, dk_ref, dv_ref = OC.attn_reference(q, k, v, mask_full, dO)
@@ -38,7 +38,7 @@ N = int(os.environ.get("TIME_N", "1024"))
 qkv = torch.randn(N, 982, 96, generator=g).to(dev)
 mask = (torch.rand(64, 982, generator=g) < 0.15).to(dev)
 seed = torch.tensor([12345], dtype=torch.int64, device=dev)
-for p in (0.0, 0.1):
+for p in [float(x) for x in os.environ.get('PS', '0.0,0.1').split(',')]:
     drop = P.Drop(p, seed, 7) if p > 0 else P.NO_DROP
     for _ in range(2):
         O, LSE = P.attn_fwd(qkv[..., :32], qkv[..., 32:64], qkv[..., 64:], mask, drop)

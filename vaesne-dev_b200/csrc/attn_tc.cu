@@ -130,10 +130,11 @@ struct TcSmem {
 __host__ __device__ constexpr size_t tc_smem_bytes(int narr, bool cols) {
   return 128 + (size_t)narr * TILE_F * 4 + 256 + (cols ? 2 * MAXL * 4 : 0) + MAXL * 4 + MAXL * 2 + 32 * 4 + 36 * 4 + 8 * 8 + 16;
 }
+// (the dynamic shared window is declared __align__(1024); deriving every pointer from it by plain pointer
+// arithmetic keeps the shared address space visible to ptxas: LDS/STS instead of generic LD/ST)
 __device__ __forceinline__ TcSmem carve(unsigned char* raw, int narr, bool cols) {
-  uintptr_t p = ((uintptr_t)raw + 127) & ~(uintptr_t)127;
   TcSmem s;
-  float* f = (float*)p;
+  float* f = reinterpret_cast<float*>(raw);
   for (int i = 0; i < 6; ++i) s.arr[i] = i < narr ? f + (size_t)i * TILE_F : nullptr;
   f += (size_t)narr * TILE_F;
   s.pad = f; f += 64;
@@ -223,7 +224,7 @@ __device__ __forceinline__ void init_common(const TcSmem& s, int tid, int warp, 
 constexpr size_t FWD_SMEM = tc_smem_bytes(4, false);
 
 __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
-  extern __shared__ unsigned char tc_smem_raw[];
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   const TcSmem s = carve(tc_smem_raw, 4, false);
   float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V2 = s.arr[2]; float* V2lo = s.arr[3];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -409,7 +410,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
 constexpr size_t DQ_SMEM = tc_smem_bytes(6, false);
 
 __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
-  extern __shared__ unsigned char tc_smem_raw[];
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   const TcSmem s = carve(tc_smem_raw, 6, false);
   float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V1 = s.arr[2]; float* V1lo = s.arr[3]; float* K2 = s.arr[4]; float* K2lo = s.arr[5];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -518,36 +519,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
       for (int j = 0; j < T; ++j) {
         mbar_wait(&s_ready[wg], scount & 1); scount++;
         fence_after();
-        uint32_t sr[64], tr[64];
-        tmem_ld32(tS, sr); tmem_ld32(tS + 32, sr + 32); tmem_ld32(tS + 64, tr); tmem_ld32(tS + 96, tr + 32);
-        tmem_wait_ld();
-        if (!dc.on) {
+        const int nvalid = min(BK, LkC - j * BK);
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const float p = ex2(__uint_as_float(sr[c]) - lse2);
-            sr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - delta)) + 0x1000u;
-          }
-        } else {
-          const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * BK);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t sr[32], tr[32];
+          tmem_ld32(tS + half * 32, sr); tmem_ld32(tS + 64 + half * 32, tr);
+          tmem_wait_ld();
+          if (!dc.on) {
 #pragma unroll
-          for (int cc = 0; cc < 16; ++cc) {
-            const uint4 b = bw[cc];
-            const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = cc * 4 + e;
+            for (int c = 0; c < 32; ++c) {
               const float p = ex2(__uint_as_float(sr[c]) - lse2);
-              const float dp = (rw * bb[e] >= dc.thr) ? __uint_as_float(tr[c]) * dc.scale : 0.f;
-              sr[c] = __float_as_uint(p * (dp - delta)) + 0x1000u;
+              sr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - delta)) + 0x1000u;
+            }
+          } else {
+            const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              const uint4 b = bw[cc];
+              const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = cc * 4 + e;
+                const float p = ex2(__uint_as_float(sr[c]) - lse2);
+                const float dp = (rw * bb[e] >= dc.thr) ? __uint_as_float(tr[c]) * dc.scale : 0.f;
+                sr[c] = __float_as_uint(p * (dp - delta)) + 0x1000u;
+              }
             }
           }
-        }
-        const int nvalid = min(BK, LkC - j * BK);
-        if (nvalid < BK) {      // padded key slots: exactly zero (2^(-lse) may overflow and inf * 0 would poison the row)
+          if (nvalid < BK) {      // padded key slots: exactly zero (2^(-lse) may overflow and inf * 0 would poison the row)
 #pragma unroll
-          for (int c = 0; c < 64; ++c) if (c >= nvalid) sr[c] = 0u;
+            for (int c = 0; c < 32; ++c) if (half * 32 + c >= nvalid) sr[c] = 0u;
+          }
+          tmem_st32(tS + half * 32, sr);
         }
-        tmem_st32(tS, sr); tmem_st32(tS + 32, sr + 32);
         tmem_wait_st();
         fence_before();
         mbar_arrive(&p_ready[wg]);
@@ -576,7 +580,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
 constexpr size_t DKV_SMEM = tc_smem_bytes(6, true);
 
 __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
-  extern __shared__ unsigned char tc_smem_raw[];
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   const TcSmem s = carve(tc_smem_raw, 6, true);
   float* Qhi = s.arr[0]; float* Qlo = s.arr[1]; float* G1 = s.arr[2]; float* G1lo = s.arr[3]; float* Q2 = s.arr[4]; float* G2 = s.arr[5];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -704,38 +708,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       for (int j = 0; j < NQ; ++j) {
         mbar_wait(&s_ready[wg], scount & 1); scount++;
         fence_after();
-        uint32_t sr[64], tr[64];
-        tmem_ld32(tS, sr); tmem_ld32(tS + 32, sr + 32); tmem_ld32(tS + 64, tr); tmem_ld32(tS + 96, tr + 32);
-        tmem_wait_ld();
-        const float4* l4 = reinterpret_cast<const float4*>(s.f0 + j * BK);
-        const float4* d4 = reinterpret_cast<const float4*>(s.f1 + j * BK);
-        const uint4* w4 = reinterpret_cast<const uint4*>(s.w0 + j * BK);
 #pragma unroll
-        for (int cc = 0; cc < 16; ++cc) {
-          const float4 lv = l4[cc], dv = d4[cc];
-          const float ll[4] = {lv.x, lv.y, lv.z, lv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
-          if (!dc.on) {
+        for (int half = 0; half < 2; ++half) {
+          uint32_t sr[32], tr[32];
+          tmem_ld32(tS + half * 32, sr); tmem_ld32(tS + 64 + half * 32, tr);
+          tmem_wait_ld();
+          const float4* l4 = reinterpret_cast<const float4*>(s.f0 + j * BK + half * 32);
+          const float4* d4 = reinterpret_cast<const float4*>(s.f1 + j * BK + half * 32);
+          const uint4* w4 = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = cc * 4 + e;
-              const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
-              sr[c] = __float_as_uint(p) + 0x1000u;
-              tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - dd[e])) + 0x1000u;
-            }
-          } else {
-            const uint4 wv = w4[cc];
-            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+          for (int cc = 0; cc < 8; ++cc) {
+            const float4 lv = l4[cc], dv = d4[cc];
+            const float ll[4] = {lv.x, lv.y, lv.z, lv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+            if (!dc.on) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = cc * 4 + e;
-              const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
-              const float dm = (ww[e] * cw >= dc.thr) ? dc.scale : 0.f;
-              sr[c] = __float_as_uint(p * dm) + 0x1000u;
-              tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) * dm - dd[e])) + 0x1000u;
+              for (int e = 0; e < 4; ++e) {
+                const int c = cc * 4 + e;
+                const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
+                sr[c] = __float_as_uint(p) + 0x1000u;
+                tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - dd[e])) + 0x1000u;
+              }
+            } else {
+              const uint4 wv = w4[cc];
+              const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = cc * 4 + e;
+                const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
+                const float dm = (ww[e] * cw >= dc.thr) ? dc.scale : 0.f;
+                sr[c] = __float_as_uint(p * dm) + 0x1000u;
+                tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) * dm - dd[e])) + 0x1000u;
+              }
             }
           }
+          tmem_st32(tS + half * 32, sr); tmem_st32(tS + 64 + half * 32, tr);
         }
-        tmem_st32(tS, sr); tmem_st32(tS + 32, sr + 32); tmem_st32(tS + 64, tr); tmem_st32(tS + 96, tr + 32);
         tmem_wait_st();
         fence_before();
         mbar_arrive(&p_ready[wg]);

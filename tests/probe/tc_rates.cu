@@ -104,6 +104,40 @@ __global__ void __launch_bounds__(NT, 1) rates(long long* out, float* sink, int 
       slot += 2; ph ^= 1u;
     }
   }
+  // realistic per-tile chain of the backward key pass: 6 first-product MMAs (N=32) + 8 accumulation MMAs (N=16), per-tile
+  // commit; (a) alone, (b) while the 8 other warps stream tcgen05.ld/st (TMEM port contention)
+  for (int load = 0; load < 4; ++load) {        // 0: none, 1: ld+st, 2: ld only, 3: st only
+    sync(); t0 = clock64();
+    if (warp == 8) {
+      if (elect_one()) {
+        const long long m0 = clock64();
+        const uint32_t id32 = idesc_tf32(128, 32), id16 = idesc_tf32(128, 16);
+        for (int r = 0; r < reps; ++r) {
+          for (int q = 0; q < 6; ++q) mma_ts(tb + 384 + (q / 3) * 32, tb + 448 + (q % 3) * 8, dB, id32, (q % 3) ? 1u : 0u);
+          for (int q = 0; q < 8; ++q) mma_ts(tb + 480 + (q & 1) * 16, tb + 256 + q * 8, dB, id16, 1u);
+          if (r >= 2) mbar_wait(&bar[2 + (r & 1)], (uint32_t)((((r - 2) >> 1) + load * (reps / 2)) & 1));     // two tiles in flight
+          commit(&bar[2 + (r & 1)]);
+        }
+        for (int r = reps - 2; r < reps; ++r) mbar_wait(&bar[2 + (r & 1)], (uint32_t)(((r >> 1) + load * (reps / 2)) & 1));
+        out[40 + load] = clock64() - m0;
+      }
+      __syncwarp();
+    } else if (load) {
+      const long long w0 = clock64();
+      uint32_t v[64];
+#pragma unroll
+      for (int c = 0; c < 64; ++c) v[c] = (uint32_t)(c + tid);
+      for (int r = 0; r < reps * 2; ++r) {
+        if (load != 3) { tmem_ld32(tl, v); tmem_ld32(tl + 32, v + 32); tmem_wait_ld(); }
+#pragma unroll
+        for (int c = 0; c < 64; ++c) v[c] += 0x1000u;
+        if (load != 2) { tmem_st32(tl + 64, v); tmem_st32(tl + 96, v + 32); tmem_wait_st(); }
+        acc += __uint_as_float(v[r & 63]);
+      }
+      if (tid == 0) out[44 + load] = clock64() - w0;
+    }
+    sync(); t1 = clock64(); rec(t1 - t0);
+  }
   // commit -> wait round trip with a single tiny MMA
   sync();
   if (warp == 8 && elect_one()) {
@@ -139,6 +173,10 @@ int main() {
   const int shapes[5] = {128, 64, 32, 16, 8};
   for (int ts = 0; ts < 2; ++ts) for (int si = 0; si < 4; ++si, i += 2)
     printf("mma.%s M128 N%-3d K8 x%d: issue %.1f clk/mma, issue+complete %.1f clk/mma\n", ts ? "ts" : "ss", shapes[si], reps, (double)h[i] / reps, (double)h[i + 1] / reps);
+  const char* lname[4] = {"no TMEM traffic", "8 warps tcgen05.ld+st", "8 warps tcgen05.ld", "8 warps tcgen05.st"};
+  for (int l = 0; l < 4; ++l, ++i)
+    printf("key-pass tile chain (6 x N32 + 8 x N16 MMAs + commit) with %-22s: issuer %.1f clk/tile ; streaming warps %.1f clk per 64-col ld/st round\n",
+           lname[l], (double)h[40 + l] / reps, (double)h[44 + l] / (2 * reps));
   printf("single mma + commit + wait round trip: %lld clk\n", h[i]);
   return 0;
 }

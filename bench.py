@@ -162,6 +162,7 @@ def time_cpu(B, steps, warmup, dropout=0.1):
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        torch.distributed.destroy_process_group()
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -297,6 +298,7 @@ def main():
                 json.dump({"|".join(map(str, k)): v for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["total_ms"])}, f, indent=1)
 
     if rank != 0:
+        torch.distributed.destroy_process_group()
         return
 
     # ---- CPU baseline (oracle port on the host cores), bounded sample -----------------------------
@@ -321,6 +323,8 @@ def main():
                     "last_loss": last.get("loss")},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -37,13 +37,17 @@ namespace vaesne {
 using namespace tc;
 
 constexpr int TCQ = 128;            // rows per tile (= TMEM lanes)
-constexpr int FK = 64;              // fwd: keys per tile
-constexpr int BK = 32;              // bwd: columns per tile
+constexpr int FK = 128;             // fwd: keys per tile
+constexpr int BK = 64;              // bwd: columns per tile
 constexpr int MAXL = 1024;          // staged column-side length
 constexpr int NTHREADS = 288;       // 8 softmax warps + 1 MMA warp
 constexpr float kScale = 0.35355339059327373f;             // sqrt(1/8)
 constexpr float kQScale = kScale * 1.4426950408889634f;    // ... * log2(e)
 constexpr float kLazy = 8.f;        // rescale O only when the row max grows by more than 2^8
+#ifndef VAESNE_TC_SPLIT_T
+#define VAESNE_TC_SPLIT_T 1
+#endif
+constexpr bool kSplitT = VAESNE_TC_SPLIT_T != 0;   // dP = dO V^T with hi/lo-split operands (3 MMAs) or rounded operands (1 MMA)
 constexpr int TILE_F = MAXL * 8;    // floats of one staged operand array (32 KB)
 
 struct TcDrop { uint32_t s0, s1, stream, thr; float scale; bool on; };
@@ -128,7 +132,7 @@ struct TcSmem {
   uint32_t* ballot; uint32_t* pre; uint64_t* bars; uint32_t* tmem;
 };
 __host__ __device__ constexpr size_t tc_smem_bytes(int narr, bool cols) {
-  return 128 + (size_t)narr * TILE_F * 4 + 256 + (cols ? 2 * MAXL * 4 : 0) + MAXL * 4 + MAXL * 2 + 32 * 4 + 36 * 4 + 16 * 8 + 16;
+  return 128 + (size_t)narr * TILE_F * 4 + 256 + (cols ? 2 * MAXL * 4 : 0) + MAXL * 4 + MAXL * 2 + 32 * 4 + 36 * 4 + 8 * 8 + 16;
 }
 // (the dynamic shared window is declared __align__(1024); deriving every pointer from it by plain pointer
 // arithmetic keeps the shared address space visible to ptxas: LDS/STS instead of generic LD/ST)
@@ -144,7 +148,7 @@ __device__ __forceinline__ TcSmem carve(unsigned char* raw, int narr, bool cols)
   s.idx = (uint16_t*)f; f += MAXL / 2;
   s.ballot = (uint32_t*)f; s.pre = s.ballot + 32;    // pre[0..31] exclusive prefix, pre[32] total
   s.bars = (uint64_t*)(s.pre + 36);
-  s.tmem = (uint32_t*)(s.bars + 16);
+  s.tmem = (uint32_t*)(s.bars + 8);
   return s;
 }
 
@@ -208,76 +212,15 @@ __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, i
   }
 }
 
-
-// =================================================================================================
-// pipeline skeleton shared by the three kernels
-// =================================================================================================
-// TMEM, per warpgroup w (256 columns at w*256):
-//   IN0 [0,64) and IN1 [64,128): score tiles written by the first product (double buffered)
-//   OUT [128,192): what the warpgroup writes back (P, dS) = A operand of the second product
-//   ACC [192,224): accumulators of the second product          X [224,256): this warpgroup's row operands
-// mbarriers, per warpgroup (6): x_ready (128 arrivals), s_ready[2] (commit), p_ready (128), out_free (commit), o_ready (commit)
-// Because IN is double buffered and OUT is separate, the issuer has the first product of tile j+1 (and j+2)
-// in flight while the warpgroup is still exponentiating tile j: the only wait on the critical path is
-// "second product of tile j-1 finished" (out_free), which completes long before it is needed.
-constexpr int C_IN0 = 0, C_IN1 = 64, C_OUT = 128, C_ACC = 192, C_X = 224, C_WG = 256;
-constexpr int B_X = 0, B_S0 = 1, B_S1 = 2, B_P = 3, B_OF = 4, B_O = 5, B_PER_WG = 6;
-
-__device__ __forceinline__ void init_pipeline(const TcSmem& s, int tid, int warp) {
+__device__ __forceinline__ void init_common(const TcSmem& s, int tid, int warp, float pad_row0) {
+  uint64_t* b = s.bars;
   if (tid == 0) {
-    for (int w = 0; w < 2; ++w) {
-      uint64_t* b = s.bars + w * B_PER_WG;
-      mbar_init(&b[B_X], 128); mbar_init(&b[B_S0], 1); mbar_init(&b[B_S1], 1); mbar_init(&b[B_P], 128); mbar_init(&b[B_OF], 1); mbar_init(&b[B_O], 1);
-    }
+    for (int w = 0; w < 2; ++w) { mbar_init(&b[w], 128); mbar_init(&b[2 + w], 1); mbar_init(&b[4 + w], 128); mbar_init(&b[6 + w], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < 64) s.pad[tid] = 0.f;
+  if (tid < 64) s.pad[tid] = ((tid & 31) < 4) ? pad_row0 : 0.f;    // row 0 of both 16-byte K chunks
   if (warp == 8) tmem_alloc<512>(s.tmem);
 }
-
-// nRT row tiles (2 per iteration, one per warpgroup), T column tiles each.
-// issue_in(w, j, b): first product of column tile j into IN buffer b.  issue_acc(w, j): second product of tile j.
-template <class FIn, class FAcc>
-__device__ __forceinline__ void mma_issuer(const TcSmem& s, int NIT, int nRT, int T, FIn issue_in, FAcc issue_acc) {
-  uint32_t pc[2] = {0, 0};
-  for (int it = 0; it < NIT && T > 0; ++it) {
-    for (int w = 0; w < 2; ++w) {
-      if (2 * it + w >= nRT) continue;
-      uint64_t* b = s.bars + w * B_PER_WG;
-      mbar_wait(&b[B_X], it & 1);
-      fence_after();
-      if (elect_one()) {
-        issue_in(w, 0, 0); commit(&b[B_S0]);
-        if (T > 1) { issue_in(w, 1, 1); commit(&b[B_S1]); }
-      }
-      __syncwarp();
-    }
-    for (int j = 0; j < T; ++j) {
-      for (int w = 0; w < 2; ++w) {
-        if (2 * it + w >= nRT) continue;
-        uint64_t* b = s.bars + w * B_PER_WG;
-        mbar_wait(&b[B_P], pc[w] & 1); pc[w]++;
-        fence_after();
-        if (elect_one()) {
-          issue_acc(w, j);
-          commit(j + 1 < T ? &b[B_OF] : &b[B_O]);
-          if (j + 2 < T) { issue_in(w, j + 2, j & 1); commit(&b[B_S0 + (j & 1)]); }
-        }
-        __syncwarp();
-      }
-    }
-  }
-}
-
-// warpgroup-side bookkeeping of barrier phases
-struct WgPhase {
-  uint32_t cs0, cs1, cof;
-  __device__ __forceinline__ void wait_s(uint64_t* b, int buf) {
-    if (buf) { mbar_wait(&b[B_S1], cs1 & 1); cs1++; } else { mbar_wait(&b[B_S0], cs0 & 1); cs0++; }
-    fence_after();
-  }
-  __device__ __forceinline__ void wait_out_free(uint64_t* b) { mbar_wait(&b[B_OF], cof & 1); cof++; fence_after(); }
-};
 
 // =================================================================================================
 // forward
@@ -290,9 +233,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
   float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V2 = s.arr[2]; float* V2lo = s.arr[3];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
+  uint64_t* x_ready = s.bars;       // [2] count 128 : row operands (Q) stored in TMEM
+  uint64_t* s_ready = s.bars + 2;   // [2] count 1   : tcgen05.commit after S
+  uint64_t* p_ready = s.bars + 4;   // [2] count 128 : P stored in TMEM
+  uint64_t* o_ready = s.bars + 6;   // [2] count 1   : tcgen05.commit after the last PV
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
 
-  init_pipeline(s, tid, warp);
+  init_common(s, tid, warp, 0.f);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
   stage_keys(a, s, n, h, tid, LkC, FK, Khi, Klo, nullptr, nullptr, V2, V2lo, nullptr, nullptr, dc);
   fence_async_smem();
@@ -303,13 +250,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
   const int T = (LkC + FK - 1) / FK;
   const int nQT = (a.Lq + TCQ - 1) / TCQ;
   const int NIT = (nQT + 1) / 2;
-  // per warpgroup: IN b = S (64 columns) ; OUT = P (64) ; ACC = O hi (8) | O lo (8) ; X = Q hi (8) | Q lo (8)
+  // TMEM columns: S[w] = w*128 (128) ; O[w] = 256 + w*16 (16) ; Q[w] = 288 + w*16 (hi 8 | lo 8)
 
   if (warp == 8) {
+    // ------------------------------- MMA issuer -------------------------------------------------
     const uint32_t idQK = idesc_tf32(128, FK), idPV = idesc_tf32(128, 16);
     const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV2 = smem_u32(V2);
-    auto issue_qk = [&](int w, int j, int b) {
-      const uint32_t d = tb + (uint32_t)(w * C_WG + (b ? C_IN1 : C_IN0)), q = tb + (uint32_t)(w * C_WG + C_X);
+    uint32_t pcount[2] = {0, 0};
+    auto issue_qk = [&](int w, int j) {
+      const uint32_t d = tb + (uint32_t)w * 128, q = tb + 288 + (uint32_t)w * 16;
       const uint64_t dKhi = smem_desc(aKhi + j * (FK * 32), 128, 256), dKlo = smem_desc(aKlo + j * (FK * 32), 128, 256);
       mma_ts(d, q, dKhi, idQK, 0);
       mma_ts(d, q + 8, dKhi, idQK, 1);
@@ -317,19 +266,40 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
     };
     auto issue_pv = [&](int w, int j) {
       const int nsteps = (min(FK, LkC - j * FK) + 7) >> 3;
-      const uint32_t dO = tb + (uint32_t)(w * C_WG + C_ACC), p = tb + (uint32_t)(w * C_WG + C_OUT);
+      const uint32_t dO = tb + 256 + (uint32_t)w * 16;
       for (int t = 0; t < nsteps; ++t) {
         const uint32_t v = aV2 + (uint32_t)(j * (FK / 8) + t) * 256;
-        mma_ts(dO, p + (uint32_t)t * 8, smem_desc(v, 128, TILE_F * 4), idPV, (j > 0 || t > 0) ? 1u : 0u);   // [Vhi | Vlo]
+        mma_ts(dO, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(v, 128, TILE_F * 4), idPV, (j > 0 || t > 0) ? 1u : 0u);   // [Vhi | Vlo]
       }
     };
-    mma_issuer(s, NIT, nQT, T, issue_qk, issue_pv);
+    for (int it = 0; it < NIT && T > 0; ++it) {
+      for (int w = 0; w < 2; ++w) {
+        if (2 * it + w >= nQT) continue;
+        mbar_wait(&x_ready[w], it & 1);
+        fence_after();
+        if (elect_one()) { issue_qk(w, 0); commit(&s_ready[w]); }
+        __syncwarp();
+      }
+      for (int j = 0; j < T; ++j) {
+        for (int w = 0; w < 2; ++w) {
+          if (2 * it + w >= nQT) continue;
+          mbar_wait(&p_ready[w], pcount[w] & 1); pcount[w]++;
+          fence_after();
+          if (elect_one()) {
+            issue_pv(w, j);
+            if (j + 1 < T) { issue_qk(w, j + 1); commit(&s_ready[w]); }
+            else commit(&o_ready[w]);
+          }
+          __syncwarp();
+        }
+      }
+    }
   } else {
+    // ------------------------------- softmax warpgroups ------------------------------------------
     const int wg = warp >> 2, r = tid & 127;
-    uint64_t* bars = s.bars + wg * B_PER_WG;
-    const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * C_WG);
-    const uint32_t tOUT = tw + C_OUT, tO = tw + C_ACC, tQ = tw + C_X;
-    WgPhase ph = {0, 0, 0};
+    const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tb + tlane + (uint32_t)wg * 128, tO = tb + tlane + 256 + (uint32_t)wg * 16, tQ = tb + tlane + 288 + (uint32_t)wg * 16;
+    uint32_t scount = 0;
     for (int it = 0; it < NIT; ++it) {
       const int qt = 2 * it + wg;
       if (qt >= nQT) break;
@@ -356,35 +326,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
         tmem_put8(tQ, hi); tmem_put8(tQ + 8, lo);
         tmem_wait_st();
         fence_before();
-        mbar_arrive(&bars[B_X]);
+        mbar_arrive(&x_ready[wg]);
       }
       const uint32_t rw = dc.on ? drop_row_word(dc, nh, a.Lq, valid ? i : 0) : 1u;
       float m_used = -1e30f, lsum = 0.f;
       for (int j = 0; j < T; ++j) {
-        const int b = j & 1;
-        ph.wait_s(bars, b);
-        const uint32_t tIN = tw + (b ? C_IN1 : C_IN0);
+        mbar_wait(&s_ready[wg], scount & 1); scount++;
+        fence_after();
         const int nvalid = min(FK, LkC - j * FK);
-        uint32_t sr[64];
-        tmem_ld32(tIN, sr); tmem_ld32(tIN + 32, sr + 32);
+        uint32_t sr[128];
+        tmem_ld32(tS, sr); tmem_ld32(tS + 32, sr + 32); tmem_ld32(tS + 64, sr + 64); tmem_ld32(tS + 96, sr + 96);
         tmem_wait_ld();
         float mt = -1e30f;
         if (nvalid == FK) {
 #pragma unroll
-          for (int c = 0; c < 64; ++c) mt = fmaxf(mt, __uint_as_float(sr[c]));
+          for (int c = 0; c < 128; ++c) mt = fmaxf(mt, __uint_as_float(sr[c]));
         } else {
 #pragma unroll
-          for (int c = 0; c < 64; ++c) { if (c >= nvalid) sr[c] = 0xff800000u; mt = fmaxf(mt, __uint_as_float(sr[c])); }
+          for (int c = 0; c < 128; ++c) { if (c >= nvalid) sr[c] = 0xff800000u; mt = fmaxf(mt, __uint_as_float(sr[c])); }
         }
         const float m_new = fmaxf(m_used, mt);
-        const bool resc = __any_sync(0xffffffffu, m_new > m_used + kLazy);    // warp-uniform: TMEM ld/st are warp-collective
-        float alpha = 1.f;
-        if (resc) { alpha = ex2(m_used - m_new); lsum *= alpha; m_used = m_new; }   // first tile: 2^(-1e30 - m) = 0
-        // the row sum stays in fp32 registers (it defines LSE, which the backward exponentiates); the MMA operand
-        // is P rounded to nearest tf32 (adding half an ulp before the tensor core truncates)
-        if (!dc.on) {
+        const bool need = (m_new > m_used + kLazy);
+        if (__any_sync(0xffffffffu, need)) {         // warp-uniform: TMEM ld/st are warp-collective
+          const float alpha = ex2(m_used - m_new);   // first tile: 2^(-1e30 - m) = 0, O not yet written
+          if (j > 0) {
+            uint32_t o[16];
+            tmem_ld16(tO, o); tmem_wait_ld();
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
+            for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st16(tO, o);
+          }
+          lsum *= alpha;
+          m_used = m_new;
+        }
+        if (!dc.on) {
+          // the row sum stays in fp32 registers (it defines LSE, which the backward exponentiates); the MMA
+          // operand is P rounded to nearest tf32 (adding half an ulp before the tensor core truncates)
+#pragma unroll
+          for (int c = 0; c < 128; ++c) {
             const float p = ex2(__uint_as_float(sr[c]) - m_used);
             lsum += p;
             sr[c] = __float_as_uint(p) + 0x1000u;
@@ -392,34 +371,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
         } else {
           const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * FK);
 #pragma unroll
-          for (int cc = 0; cc < 16; ++cc) {
-            const uint4 bq = bw[cc];
-            const uint32_t bb[4] = {bq.x, bq.y, bq.z, bq.w};
+          for (int cc = 0; cc < 32; ++cc) {
+            const uint4 b = bw[cc];
+            const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float p = ex2(__uint_as_float(sr[cc * 4 + e]) - m_used);
               lsum += p;
-              sr[cc * 4 + e] = (rw * bb[e] >= dc.thr) ? (__float_as_uint(p) + 0x1000u) : 0u;
+              sr[cc * 4 + e] = (rw * bb[e] >= dc.thr) ? (__float_as_uint(p) + 0x1000u) : 0u;   // RN to tf32
             }
           }
         }
-        if (j > 0) {
-          ph.wait_out_free(bars);                    // PV of tile j-1 has read OUT and written O
-          if (resc) {
-            uint32_t o[16];
-            tmem_ld16(tO, o); tmem_wait_ld();
-#pragma unroll
-            for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-            tmem_st16(tO, o);
-          }
-        }
-        tmem_st32(tOUT, sr); tmem_st32(tOUT + 32, sr + 32);
+        tmem_st32(tS, sr); tmem_st32(tS + 32, sr + 32); tmem_st32(tS + 64, sr + 64); tmem_st32(tS + 96, sr + 96);
         tmem_wait_st();
         fence_before();
-        mbar_arrive(&bars[B_P]);
+        mbar_arrive(&p_ready[wg]);
       }
       // epilogue: (O_hi + O_lo) / l
-      mbar_wait(&bars[B_O], it & 1);
+      mbar_wait(&o_ready[wg], it & 1);
       fence_after();
       uint32_t o[16];
       tmem_ld16(tO, o); tmem_wait_ld();
@@ -450,9 +419,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
   float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V1 = s.arr[2]; float* V1lo = s.arr[3]; float* K2 = s.arr[4]; float* K2lo = s.arr[5];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
+  uint64_t* x_ready = s.bars; uint64_t* s_ready = s.bars + 2; uint64_t* p_ready = s.bars + 4; uint64_t* o_ready = s.bars + 6;
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
 
-  init_pipeline(s, tid, warp);
+  init_common(s, tid, warp, 0.f);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
   stage_keys(a, s, n, h, tid, LkC, BK, Khi, Klo, V1, V1lo, nullptr, nullptr, K2, K2lo, dc);
   fence_async_smem();
@@ -463,37 +433,57 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
   const int T = (LkC + BK - 1) / BK;
   const int nQT = (a.Lq + TCQ - 1) / TCQ;
   const int NIT = (nQT + 1) / 2;
-  // per warpgroup: IN b = S (32) | T (32) ; OUT = dS (32) ; ACC = dQ hi (8) | lo (8) ; X = Qhi | Qlo | dOhi | dOlo
+  // TMEM columns: S[w] = w*128 (64) ; T[w] = w*128 + 64 (64) ; ACC[w] = 256 + w*16 ; X[w] = 288 + w*32 (Qhi | Qlo | dOhi | dOlo)
 
   if (warp == 8) {
     const uint32_t idS = idesc_tf32(128, BK), idA = idesc_tf32(128, 16);
     const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV1 = smem_u32(V1), aV1lo = smem_u32(V1lo), aK2 = smem_u32(K2);
-    auto issue_st = [&](int w, int j, int b) {
-      const uint32_t d = tb + (uint32_t)(w * C_WG + (b ? C_IN1 : C_IN0)), x = tb + (uint32_t)(w * C_WG + C_X);
+    uint32_t pcount[2] = {0, 0};
+    auto issue_st = [&](int w, int j) {
+      const uint32_t d = tb + (uint32_t)w * 128, x = tb + 288 + (uint32_t)w * 32;
       const uint64_t dKhi = smem_desc(aKhi + j * (BK * 32), 128, 256), dKlo = smem_desc(aKlo + j * (BK * 32), 128, 256);
       mma_ts(d, x, dKhi, idS, 0);
       mma_ts(d, x + 8, dKhi, idS, 1);
       mma_ts(d, x, dKlo, idS, 1);
       const uint64_t dVhi = smem_desc(aV1 + j * (BK * 32), 128, 256), dVlo = smem_desc(aV1lo + j * (BK * 32), 128, 256);
-      mma_ts(d + 32, x + 16, dVhi, idS, 0);
-      mma_ts(d + 32, x + 24, dVhi, idS, 1);
-      mma_ts(d + 32, x + 16, dVlo, idS, 1);
+      mma_ts(d + 64, x + 16, dVhi, idS, 0);
+      if (kSplitT) { mma_ts(d + 64, x + 24, dVhi, idS, 1); mma_ts(d + 64, x + 16, dVlo, idS, 1); }
     };
     auto issue_acc = [&](int w, int j) {
       const int nsteps = (min(BK, LkC - j * BK) + 7) >> 3;
-      const uint32_t dA = tb + (uint32_t)(w * C_WG + C_ACC), ds = tb + (uint32_t)(w * C_WG + C_OUT);
+      const uint32_t dA = tb + 256 + (uint32_t)w * 16;
       for (int t = 0; t < nsteps; ++t) {
         const uint32_t k2 = aK2 + (uint32_t)(j * (BK / 8) + t) * 256;
-        mma_ts(dA, ds + (uint32_t)t * 8, smem_desc(k2, 128, TILE_F * 4), idA, (j > 0 || t > 0) ? 1u : 0u);   // [Khi | Klo]
+        mma_ts(dA, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(k2, 128, TILE_F * 4), idA, (j > 0 || t > 0) ? 1u : 0u);   // [Khi | Klo]
       }
     };
-    mma_issuer(s, NIT, nQT, T, issue_st, issue_acc);
+    for (int it = 0; it < NIT && T > 0; ++it) {
+      for (int w = 0; w < 2; ++w) {
+        if (2 * it + w >= nQT) continue;
+        mbar_wait(&x_ready[w], it & 1);
+        fence_after();
+        if (elect_one()) { issue_st(w, 0); commit(&s_ready[w]); }
+        __syncwarp();
+      }
+      for (int j = 0; j < T; ++j) {
+        for (int w = 0; w < 2; ++w) {
+          if (2 * it + w >= nQT) continue;
+          mbar_wait(&p_ready[w], pcount[w] & 1); pcount[w]++;
+          fence_after();
+          if (elect_one()) {
+            issue_acc(w, j);
+            if (j + 1 < T) { issue_st(w, j + 1); commit(&s_ready[w]); }
+            else commit(&o_ready[w]);
+          }
+          __syncwarp();
+        }
+      }
+    }
   } else {
     const int wg = warp >> 2, r = tid & 127;
-    uint64_t* bars = s.bars + wg * B_PER_WG;
-    const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * C_WG);
-    const uint32_t tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
-    WgPhase ph = {0, 0, 0};
+    const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tb + tlane + (uint32_t)wg * 128, tA = tb + tlane + 256 + (uint32_t)wg * 16, tX = tb + tlane + 288 + (uint32_t)wg * 32;
+    uint32_t scount = 0;
     for (int it = 0; it < NIT; ++it) {
       const int qt = 2 * it + wg;
       if (qt >= nQT) break;
@@ -527,48 +517,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
       tmem_put8(tX + 16, hi); tmem_put8(tX + 24, lo);
       tmem_wait_st();
       fence_before();
-      mbar_arrive(&bars[B_X]);
+      mbar_arrive(&x_ready[wg]);
       const uint32_t rw = dc.on ? drop_row_word(dc, nh, a.Lq, valid ? i : 0) : 1u;
       for (int j = 0; j < T; ++j) {
-        const int b = j & 1;
-        ph.wait_s(bars, b);
-        const uint32_t tIN = tw + (b ? C_IN1 : C_IN0);
+        mbar_wait(&s_ready[wg], scount & 1); scount++;
+        fence_after();
         const int nvalid = min(BK, LkC - j * BK);
-        uint32_t sr[32], tr[32];
-        tmem_ld32(tIN, sr); tmem_ld32(tIN + 32, tr);
-        tmem_wait_ld();
-        if (!dc.on) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float p = ex2(__uint_as_float(sr[c]) - lse2);
-            sr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - delta)) + 0x1000u;
-          }
-        } else {
-          const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * BK);
+        for (int half = 0; half < 2; ++half) {
+          uint32_t sr[32], tr[32];
+          tmem_ld32(tS + half * 32, sr); tmem_ld32(tS + 64 + half * 32, tr);
+          tmem_wait_ld();
+          if (!dc.on) {
 #pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            const uint4 bq = bw[cc];
-            const uint32_t bb[4] = {bq.x, bq.y, bq.z, bq.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = cc * 4 + e;
+            for (int c = 0; c < 32; ++c) {
               const float p = ex2(__uint_as_float(sr[c]) - lse2);
-              const float dp = (rw * bb[e] >= dc.thr) ? __uint_as_float(tr[c]) * dc.scale : 0.f;
-              sr[c] = __float_as_uint(p * (dp - delta)) + 0x1000u;
+              sr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - delta)) + 0x1000u;
+            }
+          } else {
+            const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              const uint4 b = bw[cc];
+              const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = cc * 4 + e;
+                const float p = ex2(__uint_as_float(sr[c]) - lse2);
+                const float dp = (rw * bb[e] >= dc.thr) ? __uint_as_float(tr[c]) * dc.scale : 0.f;
+                sr[c] = __float_as_uint(p * (dp - delta)) + 0x1000u;
+              }
             }
           }
-        }
-        if (nvalid < BK) {      // padded key slots: exactly zero (2^(-lse) may overflow and inf * 0 would poison the row)
+          if (nvalid < BK) {      // padded key slots: exactly zero (2^(-lse) may overflow and inf * 0 would poison the row)
 #pragma unroll
-          for (int c = 0; c < 32; ++c) if (c >= nvalid) sr[c] = 0u;
+            for (int c = 0; c < 32; ++c) if (half * 32 + c >= nvalid) sr[c] = 0u;
+          }
+          tmem_st32(tS + half * 32, sr);
         }
-        if (j > 0) ph.wait_out_free(bars);
-        tmem_st32(tOUT, sr);
         tmem_wait_st();
         fence_before();
-        mbar_arrive(&bars[B_P]);
+        mbar_arrive(&p_ready[wg]);
       }
-      mbar_wait(&bars[B_O], it & 1);
+      mbar_wait(&o_ready[wg], it & 1);
       fence_after();
       uint32_t o[16];
       tmem_ld16(tA, o); tmem_wait_ld();
@@ -597,9 +588,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
   float* Qhi = s.arr[0]; float* Qlo = s.arr[1]; float* G1 = s.arr[2]; float* G1lo = s.arr[3]; float* Q2 = s.arr[4]; float* G2 = s.arr[5];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
+  uint64_t* x_ready = s.bars; uint64_t* s_ready = s.bars + 2; uint64_t* p_ready = s.bars + 4; uint64_t* o_ready = s.bars + 6;
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
 
-  init_pipeline(s, tid, warp);
+  init_common(s, tid, warp, 0.f);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
   // slot -> key index, zero gradients of the masked keys
   for (int j = tid; j < a.Lk; j += NTHREADS) {
@@ -611,7 +603,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
     st8g(a.dk + ((long long)n * a.Lk + j) * a.lddk + h * 8, z);
     st8g(a.dv + ((long long)n * a.Lk + j) * a.lddv + h * 8, z);
   }
-  // stage the query side: Q (scaled; L1 hi/lo + L2), dO (L1 hi/lo + L2), lse2, delta, dropout row words
+  // stage the query side: Q (scaled; L1 hi/lo + L2), dO (L1 + L2), lse2, delta, dropout row words
   const int NQ = (a.Lq + BK - 1) / BK;
   for (int i = tid; i < NQ * BK; i += NTHREADS) {
     float q[8], g[8], hi[8], lo[8];
@@ -640,40 +632,60 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
   const uint32_t tb = *s.tmem;
   const int nKT = (LkC + TCQ - 1) / TCQ;
   const int NIT = (nKT + 1) / 2;
-  // per warpgroup: IN b = S^T (32) | T^T (32) ; OUT = P^T (32) | dS^T (32) ; ACC = dK (16) | dV (16) ; X = Khi | Klo | Vhi | Vlo
+  // TMEM columns: S[w] = w*128 (64) ; T[w] = w*128 + 64 (64) ; dK[w] = 256 + w*32 ; dV[w] = 272 + w*32 ; X[w] = 320 + w*32 (Khi | Klo | Vhi | Vlo)
 
   if (warp == 8) {
     const uint32_t idS = idesc_tf32(128, BK), idA = idesc_tf32(128, 16);
     const uint32_t aQhi = smem_u32(Qhi), aQlo = smem_u32(Qlo), aG1 = smem_u32(G1), aG1lo = smem_u32(G1lo), aQ2 = smem_u32(Q2), aG2 = smem_u32(G2), aPad = smem_u32(s.pad);
-    auto issue_st = [&](int w, int j, int b) {
-      const uint32_t d = tb + (uint32_t)(w * C_WG + (b ? C_IN1 : C_IN0)), x = tb + (uint32_t)(w * C_WG + C_X);
+    uint32_t pcount[2] = {0, 0};
+    auto issue_st = [&](int w, int j) {
+      const uint32_t d = tb + (uint32_t)w * 128, x = tb + 320 + (uint32_t)w * 32;
       const uint64_t dQhi = smem_desc(aQhi + j * (BK * 32), 128, 256), dQlo = smem_desc(aQlo + j * (BK * 32), 128, 256);
       mma_ts(d, x, dQhi, idS, 0);
       mma_ts(d, x + 8, dQhi, idS, 1);
       mma_ts(d, x, dQlo, idS, 1);
       const uint64_t dGhi = smem_desc(aG1 + j * (BK * 32), 128, 256), dGlo = smem_desc(aG1lo + j * (BK * 32), 128, 256);
-      mma_ts(d + 32, x + 16, dGhi, idS, 0);
-      mma_ts(d + 32, x + 24, dGhi, idS, 1);
-      mma_ts(d + 32, x + 16, dGlo, idS, 1);
+      mma_ts(d + 64, x + 16, dGhi, idS, 0);
+      if (kSplitT) { mma_ts(d + 64, x + 24, dGhi, idS, 1); mma_ts(d + 64, x + 16, dGlo, idS, 1); }
     };
     auto issue_acc = [&](int w, int j) {
       const int nsteps = (min(BK, a.Lq - j * BK) + 7) >> 3;
-      const uint32_t dK = tb + (uint32_t)(w * C_WG + C_ACC), dV = dK + 16, o = tb + (uint32_t)(w * C_WG + C_OUT);
+      const uint32_t dK = tb + 256 + (uint32_t)w * 32, dV = dK + 16;
       for (int t = 0; t < nsteps; ++t) {
         const uint32_t off = (uint32_t)(j * (BK / 8) + t) * 256;
         const uint32_t g2 = aG2 + off, q2 = aQ2 + off;
         const uint32_t acc = (j > 0 || t > 0) ? 1u : 0u;
-        mma_ts(dV, o + (uint32_t)t * 8, smem_desc(g2, 128, aPad - g2), idA, acc);
-        mma_ts(dK, o + 32 + (uint32_t)t * 8, smem_desc(q2, 128, aPad - q2), idA, acc);
+        mma_ts(dV, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(g2, 128, aPad - g2), idA, acc);
+        mma_ts(dK, tb + (uint32_t)w * 128 + 64 + (uint32_t)t * 8, smem_desc(q2, 128, aPad - q2), idA, acc);
       }
     };
-    mma_issuer(s, NIT, nKT, NQ, issue_st, issue_acc);
+    for (int it = 0; it < NIT; ++it) {
+      for (int w = 0; w < 2; ++w) {
+        if (2 * it + w >= nKT) continue;
+        mbar_wait(&x_ready[w], it & 1);
+        fence_after();
+        if (elect_one()) { issue_st(w, 0); commit(&s_ready[w]); }
+        __syncwarp();
+      }
+      for (int j = 0; j < NQ; ++j) {
+        for (int w = 0; w < 2; ++w) {
+          if (2 * it + w >= nKT) continue;
+          mbar_wait(&p_ready[w], pcount[w] & 1); pcount[w]++;
+          fence_after();
+          if (elect_one()) {
+            issue_acc(w, j);
+            if (j + 1 < NQ) { issue_st(w, j + 1); commit(&s_ready[w]); }
+            else commit(&o_ready[w]);
+          }
+          __syncwarp();
+        }
+      }
+    }
   } else {
     const int wg = warp >> 2, r = tid & 127;
-    uint64_t* bars = s.bars + wg * B_PER_WG;
-    const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * C_WG);
-    const uint32_t tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
-    WgPhase ph = {0, 0, 0};
+    const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tb + tlane + (uint32_t)wg * 128, tA = tb + tlane + 256 + (uint32_t)wg * 32, tX = tb + tlane + 320 + (uint32_t)wg * 32;
+    uint32_t scount = 0;
     for (int it = 0; it < NIT; ++it) {
       const int kt = 2 * it + wg;
       if (kt >= nKT) break;
@@ -693,50 +705,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       tmem_put8(tX + 16, hi); tmem_put8(tX + 24, lo);
       tmem_wait_st();
       fence_before();
-      mbar_arrive(&bars[B_X]);
+      mbar_arrive(&x_ready[wg]);
       const uint32_t cw = dc.on ? drop_col_word(dc, nh, cs) : 1u;
       for (int j = 0; j < NQ; ++j) {
-        const int b = j & 1;
-        ph.wait_s(bars, b);
-        const uint32_t tIN = tw + (b ? C_IN1 : C_IN0);
-        uint32_t sr[32], tr[32];
-        tmem_ld32(tIN, sr); tmem_ld32(tIN + 32, tr);
-        tmem_wait_ld();
-        const float4* l4 = reinterpret_cast<const float4*>(s.f0 + j * BK);
-        const float4* d4 = reinterpret_cast<const float4*>(s.f1 + j * BK);
-        const uint4* w4 = reinterpret_cast<const uint4*>(s.w0 + j * BK);
+        mbar_wait(&s_ready[wg], scount & 1); scount++;
+        fence_after();
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {
-          const float4 lv = l4[cc], dv = d4[cc];
-          const float ll[4] = {lv.x, lv.y, lv.z, lv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
-          if (!dc.on) {
+        for (int half = 0; half < 2; ++half) {
+          uint32_t sr[32], tr[32];
+          tmem_ld32(tS + half * 32, sr); tmem_ld32(tS + 64 + half * 32, tr);
+          tmem_wait_ld();
+          const float4* l4 = reinterpret_cast<const float4*>(s.f0 + j * BK + half * 32);
+          const float4* d4 = reinterpret_cast<const float4*>(s.f1 + j * BK + half * 32);
+          const uint4* w4 = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = cc * 4 + e;
-              const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
-              sr[c] = __float_as_uint(p) + 0x1000u;
-              tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - dd[e])) + 0x1000u;
-            }
-          } else {
-            const uint4 wv = w4[cc];
-            const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+          for (int cc = 0; cc < 8; ++cc) {
+            const float4 lv = l4[cc], dv = d4[cc];
+            const float ll[4] = {lv.x, lv.y, lv.z, lv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+            if (!dc.on) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int c = cc * 4 + e;
-              const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
-              const float dm = (ww[e] * cw >= dc.thr) ? dc.scale : 0.f;
-              sr[c] = __float_as_uint(p * dm) + 0x1000u;
-              tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) * dm - dd[e])) + 0x1000u;
+              for (int e = 0; e < 4; ++e) {
+                const int c = cc * 4 + e;
+                const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
+                sr[c] = __float_as_uint(p) + 0x1000u;
+                tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - dd[e])) + 0x1000u;
+              }
+            } else {
+              const uint4 wv = w4[cc];
+              const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = cc * 4 + e;
+                const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
+                const float dm = (ww[e] * cw >= dc.thr) ? dc.scale : 0.f;
+                sr[c] = __float_as_uint(p * dm) + 0x1000u;
+                tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) * dm - dd[e])) + 0x1000u;
+              }
             }
           }
+          tmem_st32(tS + half * 32, sr); tmem_st32(tS + 64 + half * 32, tr);
         }
-        if (j > 0) ph.wait_out_free(bars);
-        tmem_st32(tOUT, sr); tmem_st32(tOUT + 32, tr);
         tmem_wait_st();
         fence_before();
-        mbar_arrive(&bars[B_P]);
+        mbar_arrive(&p_ready[wg]);
       }
-      mbar_wait(&bars[B_O], it & 1);
+      mbar_wait(&o_ready[wg], it & 1);
       fence_after();
       uint32_t o[32];
       tmem_ld32(tA, o); tmem_wait_ld();

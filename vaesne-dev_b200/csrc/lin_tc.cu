@@ -25,6 +25,7 @@
 #include "lin_args.cuh"
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <stdio.h>
 
 namespace vaesne {
 using namespace tc;
@@ -113,11 +114,11 @@ template <int NCH>
 __host__ __device__ constexpr size_t lin_tc_fwd_smem() { return 128 + sizeof(float) * (2 * NCH * 1024 + 96 + 64 + 2 * TILE) + 32; }
 
 template <int NCH, bool LN>
-__global__ void __launch_bounds__(LT, 2) lin_tc_fwd_kernel(LinFwd a) {
+__global__ void __launch_bounds__(LT, 3) lin_tc_fwd_kernel(LinFwd a) {
   constexpr int N = NCH * 32;
   constexpr int COLS = (64 + N) <= 128 ? 128 : 256;
-  extern __shared__ unsigned char lin_tc_raw[];
-  float* Whi = reinterpret_cast<float*>(((uintptr_t)lin_tc_raw + 127) & ~(uintptr_t)127);
+  extern __shared__ __align__(1024) unsigned char lin_tc_raw[];      // plain pointer arithmetic from here on: keeps LDS/STS
+  float* Whi = reinterpret_cast<float*>(lin_tc_raw);
   float* Wlo = Whi + NCH * 1024;
   float* sB = Wlo + NCH * 1024;      // [96]
   float* sG = sB + 96;               // [32]
@@ -265,8 +266,8 @@ template <int NCH, bool LN>
 __global__ void __launch_bounds__(LT, 2) lin_tc_bwd_kernel(LinBwd a) {
   constexpr int N = NCH * 32;
   constexpr int COLS = 256;            // A hi|lo 64 + dX 32 + dW 64*NCH  (NCH <= 2)
-  extern __shared__ unsigned char lin_tc_raw[];
-  float* dZT = reinterpret_cast<float*>(((uintptr_t)lin_tc_raw + 127) & ~(uintptr_t)127);   // first: the M=128 MMA reads 16 row groups from here
+  extern __shared__ __align__(1024) unsigned char lin_tc_raw[];
+  float* dZT = reinterpret_cast<float*>(lin_tc_raw);   // first: the M=128 MMA reads 16 row groups from here
   float* B1 = dZT + TILE;
   float* XT = B1 + TILE;
   float* B2 = XT + TILE;
@@ -507,33 +508,60 @@ bool lin_tc_bwd_eligible(const LinBwd& a) {
   return al16(a.dY, a.lddy) && al16(a.S, 32) && al16(a.dR, a.lddr) && al16(a.A, a.lda) && al16(a.X, a.ldx) && al16(a.dX, a.lddx);
 }
 
-static int tc_grid(int T, int ctas_per_sm) {
-  const int ntiles = (T + LT - 1) / LT;
-  return ntiles < 148 * ctas_per_sm ? ntiles : 148 * ctas_per_sm;
+// Persistent grid: exactly as many CTAs as can be co-resident (a partial second wave would double the run time),
+// never more than there are tiles.  The occupancy of each kernel instantiation is queried once.
+struct TcKernelInfo { const void* fn; int ctas_per_sm; int sms; };
+template <typename K>
+static int tc_prepare(K k, size_t smem, const char* what, TcKernelInfo& out) {
+  static thread_local TcKernelInfo cache[16] = {};
+  for (auto& e : cache) if (e.fn == (const void*)k) { out = e; return V_OK; }
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("%s: cannot reserve %zu B of shared memory: %s", what, smem, cudaGetErrorString(e)); return V_ECUDA; }
+  // ask for the full shared-memory carve-out, otherwise the occupancy (and residency) is computed for a small default
+  (void)cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  // Residency from the kernel's own resources.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for
+  // kernels that allocate tensor memory, whatever they allocate; the block scheduler itself only looks at
+  // registers / shared memory / threads, and tcgen05.alloc waits for free columns.)
+  int dev = 0, sms = 148, smem_sm = 233472, regs_sm = 65536;
+  cudaFuncAttributes fa;
+  e = cudaFuncGetAttributes(&fa, k);
+  if (e != cudaSuccess) { set_error("%s: cudaFuncGetAttributes failed: %s", what, cudaGetErrorString(e)); return V_ECUDA; }
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+  }
+  const int regs_cta = ((fa.numRegs + 7) / 8) * 8 * LT;
+  const int by_regs = regs_sm / (regs_cta > 0 ? regs_cta : 1);
+  const int by_smem = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + 1024));
+  int occ = by_regs < by_smem ? by_regs : by_smem;
+  if (occ < 1) occ = 1;
+  out = TcKernelInfo{(const void*)k, occ, sms};
+  if (getenv("VAESNE_DEBUG")) fprintf(stderr, "[vaesne] %s: %d CTAs/SM by occupancy, %d SMs, %zu B smem\n", what, occ, sms, smem);
+  for (auto& c : cache) if (!c.fn) { c = out; break; }
+  return V_OK;
 }
 template <typename K, typename A>
-static int tc_launch(K k, size_t smem, int grid, cudaStream_t st, const char* what, const A& args) {
-  static thread_local const void* configured[16] = {};
-  bool done = false;
-  for (auto p : configured) if (p == (const void*)k) done = true;
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("%s: cannot reserve %zu B of shared memory: %s", what, smem, cudaGetErrorString(e)); return V_ECUDA; }
-    for (auto& p : configured) if (!p) { p = (const void*)k; break; }
-  }
+static int tc_launch(K k, size_t smem, int tmem_ctas, cudaStream_t st, const char* what, const A& args) {
+  TcKernelInfo ki;
+  int rc = tc_prepare(k, smem, what, ki); if (rc) return rc;
+  const int per_sm = ki.ctas_per_sm < tmem_ctas ? ki.ctas_per_sm : tmem_ctas;      // TMEM: 512 columns per SM
+  const int ntiles = (args.T + LT - 1) / LT;
+  const int cap = ki.sms * per_sm;
+  const int grid = ntiles < cap ? ntiles : cap;
   k<<<grid, LT, smem, st>>>(args);
   return check_launch(what);
 }
 
 int lin_tc_fwd(const LinFwd& a, cudaStream_t st) {
-  const int g = tc_grid(a.T, a.N <= 64 ? 4 : 2);     // TMEM: 128 columns per CTA up to N = 64, else 256
+  const int g = a.N <= 64 ? 4 : 2;     // TMEM: 128 columns per CTA up to N = 64, else 256
   if (a.R) return tc_launch(lin_tc_fwd_kernel<1, true>, lin_tc_fwd_smem<1>(), g, st, "lin_tc_fwd_ln", a);
   if (a.N == 32) return tc_launch(lin_tc_fwd_kernel<1, false>, lin_tc_fwd_smem<1>(), g, st, "lin_tc_fwd", a);
   if (a.N == 64) return tc_launch(lin_tc_fwd_kernel<2, false>, lin_tc_fwd_smem<2>(), g, st, "lin_tc_fwd", a);
   return tc_launch(lin_tc_fwd_kernel<3, false>, lin_tc_fwd_smem<3>(), g, st, "lin_tc_fwd", a);
 }
 static int lin_tc_bwd_one(const LinBwd& a, cudaStream_t st) {
-  const int g = tc_grid(a.T, 2);                     // ~100 KB of shared memory per CTA
+  const int g = 2;                                   // TMEM: 256 columns per CTA
   if (a.S) return tc_launch(lin_tc_bwd_kernel<1, true>, lin_tc_bwd_smem<1>(), g, st, "lin_tc_bwd_ln", a);
   if (a.N == 32) return tc_launch(lin_tc_bwd_kernel<1, false>, lin_tc_bwd_smem<1>(), g, st, "lin_tc_bwd", a);
   return tc_launch(lin_tc_bwd_kernel<2, false>, lin_tc_bwd_smem<2>(), g, st, "lin_tc_bwd", a);

@@ -32,6 +32,9 @@ for scale in (() if os.environ.get('ONLY_TIME') else (1.0, 3.0)):
             msg += f" dq {rel_err(dq.cpu(), dq_ref):.2e} dk {rel_err(dk.cpu(), dk_ref):.2e} dv {rel_err(dv.cpu(), dv_ref):.2e}"
         print(msg, flush=True)
 
+import ctypes
+if os.environ.get('TC_DBG'):
+    ctypes.CDLL(os.path.join(ROOT, 'vaesne-dev_b200', 'lib', 'libvaesne_b200.so')).vaesne_debug_tc(int(os.environ['TC_DBG']))
 # timing at the bench shape: N = 2*K*B = 1024 rows (B=64)
 g = torch.Generator().manual_seed(0)
 N = int(os.environ.get("TIME_N", "1024"))
@@ -61,3 +64,12 @@ for p in [float(x) for x in os.environ.get('PS', '0.0,0.1').split(',')]:
         b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 3
         print(f"bwd p={p}: {ms:.3f} ms  ({10 * 8 * el / ms / 1e9:.1f} TFLOP/s algorithmic)", flush=True)
+
+if os.environ.get('TC_PROF'):
+    lib = ctypes.CDLL(os.path.join(ROOT, 'vaesne-dev_b200', 'lib', 'libvaesne_b200.so'))
+    buf = (ctypes.c_longlong * 16)()
+    torch.cuda.synchronize(); lib.vaesne_debug_tc_prof(buf)
+    names = ["warp0 wait s_ready", "warp0 ld+compute+st", "warp0 wait::st", "warp0 wait o_ready", "warp0 total", "", "", "",
+             "issuer wait x_ready", "issuer wait p_ready[0]", "issuer wait p_ready[1]", "issuer issue+commit"]
+    for n_, v in zip(names, buf):
+        if n_: print(f"  dkv CTA(0,0) {n_:28s} {v:10d} clk")

@@ -32,6 +32,7 @@
 #include "attn_args.cuh"
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <cuda_fp16.h>
 
 namespace vaesne {
 using namespace tc;
@@ -50,6 +51,9 @@ constexpr float kLazy = 8.f;        // rescale O only when the row max grows by 
 constexpr bool kSplitT = VAESNE_TC_SPLIT_T != 0;   // dP = dO V^T with hi/lo-split operands (3 MMAs) or rounded operands (1 MMA)
 constexpr int TILE_F = MAXL * 8;    // floats of one staged operand array (32 KB)
 
+__device__ long long g_tc_prof[16];   // probe: per-phase clocks of CTA (0,0): warp 0 and the issuer
+#define TPROF(slot, expr) do { long long _t0 = clock64(); expr; prof[slot] += clock64() - _t0; } while (0)
+__constant__ int g_tc_dbg = 0;      // timing experiments only (tests/probe): 1 = no second-product MMAs, 2 = no exponentials
 struct TcDrop { uint32_t s0, s1, stream, thr; float scale; bool on; };
 __device__ __forceinline__ TcDrop make_tcdrop(float p, const uint64_t* seed, uint32_t stream) {
   TcDrop d; d.on = (p > 0.f) && seed != nullptr; d.s0 = d.s1 = 0; d.stream = stream; d.thr = 0; d.scale = 1.f;
@@ -104,6 +108,28 @@ __device__ __forceinline__ void put_l2(float* dst, int row, const float* x) {
   float* p = dst + (row >> 3) * 64 + ((row & 7) >> 2) * 32 + (row & 3);
 #pragma unroll
   for (int d = 0; d < 8; ++d) p[d * 4] = x[d];
+}
+// layout L2h (second product, kind::f16): for every 16 consecutive rows one [8 features x 16 rows] K-major fp16 operand
+// (two 8x8 core matrices 128 B apart); the lo parts live 16 KB (HALF_ARR halfs) after the hi parts and form the second
+// 8-row group of the N=16 operand, so accumulator columns 8..15 collect the lo-part product for free.
+constexpr int HALF_ARR = (MAXL / 16) * 128;     // halfs per hi (or lo) array = 16 KB
+__device__ __forceinline__ void put_l2h(__half* dst, int row, const float* x) {
+  __half* p = dst + (row >> 4) * 128 + ((row >> 3) & 1) * 64 + (row & 7);
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    const __half hi = __float2half_rn(x[d]);
+    p[d * 8] = hi;
+    p[HALF_ARR + d * 8] = __float2half_rn(x[d] - __half2float(hi));
+  }
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// power of two that brings |x| into [1, 2)  (1 for zero / subnormal / non-finite x): exact fp16 range management
+__device__ __forceinline__ float pow2_normaliser(float amax) {
+  const uint32_t e = (__float_as_uint(amax) >> 23) & 255u;
+  return (e == 0u || e >= 254u) ? 1.f : __uint_as_float((254u - e) << 23);
 }
 __device__ __forceinline__ void split8(const float* x, float* hi, float* lo) {
 #pragma unroll
@@ -183,8 +209,8 @@ __device__ __forceinline__ int key_slot(const TcSmem& s, int j) {     // -1 if m
 // V2hi/V2lo, K2hi/K2lo: L2 of V / K (the lo array sits one TILE_F after the hi array: it is the second 8-row
 // group of the N=16 operand, so the accumulator's columns 8..15 collect the lo-part product for free).
 __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, int n, int h, int tid, int LkC, int tile,
-                                           float* Khi, float* Klo, float* V1hi, float* V1lo, float* V2hi, float* V2lo,
-                                           float* K2hi, float* K2lo, const TcDrop& dc) {
+                                           float* Khi, float* Klo, float* V1hi, float* V1lo, __half* V2h, __half* K2h,
+                                           const TcDrop& dc) {
   const int Lpad = ((LkC + tile - 1) / tile) * tile;
   float z[8];
 #pragma unroll
@@ -192,8 +218,8 @@ __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, i
   for (int c = LkC + tid; c < Lpad; c += NTHREADS) {
     put_l1(Khi, c, z); put_l1(Klo, c, z);
     if (V1hi) { put_l1(V1hi, c, z); put_l1(V1lo, c, z); }
-    if (V2hi) { put_l2(V2hi, c, z); put_l2(V2lo, c, z); }
-    if (K2hi) { put_l2(K2hi, c, z); put_l2(K2lo, c, z); }
+    if (V2h) put_l2h(V2h, c, z);
+    if (K2h) put_l2h(K2h, c, z);
   }
   const int nh = n * kH + h;
   if (dc.on) for (int c = tid; c < Lpad; c += NTHREADS) s.w0[c] = drop_col_word(dc, nh, c);
@@ -205,10 +231,10 @@ __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, i
     ld8g(vv, a.v + ((long long)n * a.Lk + j) * a.ldv + h * 8);
     split8(kk, hi, lo);
     put_l1(Khi, c, hi); put_l1(Klo, c, lo);
-    if (K2hi) { put_l2(K2hi, c, hi); put_l2(K2lo, c, lo); }
+    if (K2h) put_l2h(K2h, c, kk);
     split8(vv, hi, lo);
     if (V1hi) { put_l1(V1hi, c, hi); put_l1(V1lo, c, lo); }
-    if (V2hi) { put_l2(V2hi, c, hi); put_l2(V2lo, c, lo); }
+    if (V2h) put_l2h(V2h, c, vv);
   }
 }
 
@@ -225,12 +251,12 @@ __device__ __forceinline__ void init_common(const TcSmem& s, int tid, int warp, 
 // =================================================================================================
 // forward
 // =================================================================================================
-constexpr size_t FWD_SMEM = tc_smem_bytes(4, false);
+constexpr size_t FWD_SMEM = tc_smem_bytes(3, false);
 
 __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-  const TcSmem s = carve(tc_smem_raw, 4, false);
-  float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V2 = s.arr[2]; float* V2lo = s.arr[3];
+  const TcSmem s = carve(tc_smem_raw, 3, false);
+  float* Khi = s.arr[0]; float* Klo = s.arr[1]; __half* V2h = reinterpret_cast<__half*>(s.arr[2]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   uint64_t* x_ready = s.bars;       // [2] count 128 : row operands (Q) stored in TMEM
@@ -241,7 +267,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
 
   init_common(s, tid, warp, 0.f);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
-  stage_keys(a, s, n, h, tid, LkC, FK, Khi, Klo, nullptr, nullptr, V2, V2lo, nullptr, nullptr, dc);
+  stage_keys(a, s, n, h, tid, LkC, FK, Khi, Klo, nullptr, nullptr, V2h, nullptr, dc);
   fence_async_smem();
   fence_before();
   __syncthreads();
@@ -254,8 +280,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
 
   if (warp == 8) {
     // ------------------------------- MMA issuer -------------------------------------------------
-    const uint32_t idQK = idesc_tf32(128, FK), idPV = idesc_tf32(128, 16);
-    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV2 = smem_u32(V2);
+    const uint32_t idQK = idesc_tf32(128, FK), idPV = idesc_f16(128, 16);
+    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV2 = smem_u32(V2h);
     uint32_t pcount[2] = {0, 0};
     auto issue_qk = [&](int w, int j) {
       const uint32_t d = tb + (uint32_t)w * 128, q = tb + 288 + (uint32_t)w * 16;
@@ -265,11 +291,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
       mma_ts(d, q, dKlo, idQK, 1);
     };
     auto issue_pv = [&](int w, int j) {
-      const int nsteps = (min(FK, LkC - j * FK) + 7) >> 3;
+      const int nsteps = (min(FK, LkC - j * FK) + 15) >> 4;      // 16 keys per kind::f16 MMA
       const uint32_t dO = tb + 256 + (uint32_t)w * 16;
       for (int t = 0; t < nsteps; ++t) {
-        const uint32_t v = aV2 + (uint32_t)(j * (FK / 8) + t) * 256;
-        mma_ts(dO, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(v, 128, TILE_F * 4), idPV, (j > 0 || t > 0) ? 1u : 0u);   // [Vhi | Vlo]
+        const uint32_t v = aV2 + (uint32_t)(j * (FK / 16) + t) * 256;
+        mma_ts_f16(dO, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(v, 128, HALF_ARR * 2), idPV, (j > 0 || t > 0) ? 1u : 0u);   // [Vhi | Vlo]
       }
     };
     for (int it = 0; it < NIT && T > 0; ++it) {
@@ -361,12 +387,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
         }
         if (!dc.on) {
           // the row sum stays in fp32 registers (it defines LSE, which the backward exponentiates); the MMA
-          // operand is P rounded to nearest tf32 (adding half an ulp before the tensor core truncates)
+          // operand is P rounded to nearest fp16 (11 significant bits, like tf32)
 #pragma unroll
           for (int c = 0; c < 128; ++c) {
             const float p = ex2(__uint_as_float(sr[c]) - m_used);
             lsum += p;
-            sr[c] = __float_as_uint(p) + 0x1000u;
+            sr[c] = __float_as_uint(p);
           }
         } else {
           const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * FK);
@@ -378,11 +404,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
             for (int e = 0; e < 4; ++e) {
               const float p = ex2(__uint_as_float(sr[cc * 4 + e]) - m_used);
               lsum += p;
-              sr[cc * 4 + e] = (rw * bb[e] >= dc.thr) ? (__float_as_uint(p) + 0x1000u) : 0u;   // RN to tf32
+              sr[cc * 4 + e] = (rw * bb[e] >= dc.thr) ? __float_as_uint(p) : 0u;
             }
           }
         }
-        tmem_st32(tS, sr); tmem_st32(tS + 32, sr + 32); tmem_st32(tS + 64, sr + 64); tmem_st32(tS + 96, sr + 96);
+        // P (<= 2^8 by the lazy rescale) leaves as fp16 pairs: 64 TMEM columns, 8 MMAs of K = 16 per tile
+#pragma unroll
+        for (int c = 0; c < 64; ++c) sr[c] = pack_h2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1]));
+        tmem_st32(tS, sr); tmem_st32(tS + 32, sr + 32);
         tmem_wait_st();
         fence_before();
         mbar_arrive(&p_ready[wg]);
@@ -411,12 +440,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
 // =================================================================================================
 // backward, pass 1: rows = queries.  delta = dO.O ; dQ = scale * sum_j dS_ij K_j
 // =================================================================================================
-constexpr size_t DQ_SMEM = tc_smem_bytes(6, false);
+constexpr size_t DQ_SMEM = tc_smem_bytes(5, false);
 
 __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-  const TcSmem s = carve(tc_smem_raw, 6, false);
-  float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V1 = s.arr[2]; float* V1lo = s.arr[3]; float* K2 = s.arr[4]; float* K2lo = s.arr[5];
+  const TcSmem s = carve(tc_smem_raw, 5, false);
+  float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V1 = s.arr[2]; float* V1lo = s.arr[3]; __half* K2h = reinterpret_cast<__half*>(s.arr[4]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   uint64_t* x_ready = s.bars; uint64_t* s_ready = s.bars + 2; uint64_t* p_ready = s.bars + 4; uint64_t* o_ready = s.bars + 6;
@@ -424,7 +453,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
 
   init_common(s, tid, warp, 0.f);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
-  stage_keys(a, s, n, h, tid, LkC, BK, Khi, Klo, V1, V1lo, nullptr, nullptr, K2, K2lo, dc);
+  stage_keys(a, s, n, h, tid, LkC, BK, Khi, Klo, V1, V1lo, nullptr, K2h, dc);
   fence_async_smem();
   fence_before();
   __syncthreads();
@@ -436,8 +465,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
   // TMEM columns: S[w] = w*128 (64) ; T[w] = w*128 + 64 (64) ; ACC[w] = 256 + w*16 ; X[w] = 288 + w*32 (Qhi | Qlo | dOhi | dOlo)
 
   if (warp == 8) {
-    const uint32_t idS = idesc_tf32(128, BK), idA = idesc_tf32(128, 16);
-    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV1 = smem_u32(V1), aV1lo = smem_u32(V1lo), aK2 = smem_u32(K2);
+    const uint32_t idS = idesc_tf32(128, BK), idA = idesc_f16(128, 16);
+    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV1 = smem_u32(V1), aV1lo = smem_u32(V1lo), aK2 = smem_u32(K2h);
     uint32_t pcount[2] = {0, 0};
     auto issue_st = [&](int w, int j) {
       const uint32_t d = tb + (uint32_t)w * 128, x = tb + 288 + (uint32_t)w * 32;
@@ -450,11 +479,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
       if (kSplitT) { mma_ts(d + 64, x + 24, dVhi, idS, 1); mma_ts(d + 64, x + 16, dVlo, idS, 1); }
     };
     auto issue_acc = [&](int w, int j) {
-      const int nsteps = (min(BK, LkC - j * BK) + 7) >> 3;
+      const int nsteps = (min(BK, LkC - j * BK) + 15) >> 4;
       const uint32_t dA = tb + 256 + (uint32_t)w * 16;
       for (int t = 0; t < nsteps; ++t) {
-        const uint32_t k2 = aK2 + (uint32_t)(j * (BK / 8) + t) * 256;
-        mma_ts(dA, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(k2, 128, TILE_F * 4), idA, (j > 0 || t > 0) ? 1u : 0u);   // [Khi | Klo]
+        const uint32_t k2 = aK2 + (uint32_t)(j * (BK / 16) + t) * 256;
+        mma_ts_f16(dA, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(k2, 128, HALF_ARR * 2), idA, (j > 0 || t > 0) ? 1u : 0u);   // [Khi | Klo]
       }
     };
     for (int it = 0; it < NIT && T > 0; ++it) {
@@ -503,6 +532,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
         lse2 = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
         a.delta[(long long)nh * a.Lq + i] = delta;
       }
+      // dS leaves as fp16: this row's dO (hence dP, delta, dS, dQ: all linear in it) is scaled by a power of two into [1, 2)
+      float gmax = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) gmax = fmaxf(gmax, fabsf(g[c]));
+      const float rs = pow2_normaliser(gmax);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) g[c] *= rs;
+      delta *= rs;
       if (T == 0) {       // every key masked: the reference's gradients are NaN
         if (valid) {
 #pragma unroll
@@ -532,7 +569,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float p = ex2(__uint_as_float(sr[c]) - lse2);
-              sr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - delta)) + 0x1000u;
+              sr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - delta));
             }
           } else {
             const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
@@ -545,7 +582,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
                 const int c = cc * 4 + e;
                 const float p = ex2(__uint_as_float(sr[c]) - lse2);
                 const float dp = (rw * bb[e] >= dc.thr) ? __uint_as_float(tr[c]) * dc.scale : 0.f;
-                sr[c] = __float_as_uint(p * (dp - delta)) + 0x1000u;
+                sr[c] = __float_as_uint(p * (dp - delta));
               }
             }
           }
@@ -553,7 +590,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
 #pragma unroll
             for (int c = 0; c < 32; ++c) if (half * 32 + c >= nvalid) sr[c] = 0u;
           }
-          tmem_st32(tS + half * 32, sr);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) sr[c] = pack_h2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1]));
+          tmem_st16(tS + half * 16, sr);
         }
         tmem_wait_st();
         fence_before();
@@ -566,7 +605,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
       if (valid) {
         float out[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) out[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * kScale;
+        for (int c = 0; c < 8; ++c) out[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * (kScale / rs);
         st8g(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, out);
       }
       fence_before();
@@ -585,7 +624,8 @@ constexpr size_t DKV_SMEM = tc_smem_bytes(6, true);
 __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   const TcSmem s = carve(tc_smem_raw, 6, true);
-  float* Qhi = s.arr[0]; float* Qlo = s.arr[1]; float* G1 = s.arr[2]; float* G1lo = s.arr[3]; float* Q2 = s.arr[4]; float* G2 = s.arr[5];
+  float* Qhi = s.arr[0]; float* Qlo = s.arr[1]; float* G1 = s.arr[2]; float* G1lo = s.arr[3];
+  __half* Q2h = reinterpret_cast<__half*>(s.arr[4]); __half* G2h = reinterpret_cast<__half*>(s.arr[5]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   uint64_t* x_ready = s.bars; uint64_t* s_ready = s.bars + 2; uint64_t* p_ready = s.bars + 4; uint64_t* o_ready = s.bars + 6;
@@ -603,7 +643,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
     st8g(a.dk + ((long long)n * a.Lk + j) * a.lddk + h * 8, z);
     st8g(a.dv + ((long long)n * a.Lk + j) * a.lddv + h * 8, z);
   }
-  // stage the query side: Q (scaled; L1 hi/lo + L2), dO (L1 + L2), lse2, delta, dropout row words
+  // P^T and dS^T leave as fp16: dO of this (row, head) is scaled by ONE power of two that brings its largest entry into
+  // [1, 2) (dP, delta, dS, dK, dV are linear in it; entries 2^14 below the largest one lose relative accuracy only)
+  {
+    float gm = 0.f;
+    for (int i = tid; i < a.Lq; i += NTHREADS) {
+      float g[8];
+      ld8g(g, a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) gm = fmaxf(gm, fabsf(g[c]));
+    }
+    gm = isfinite(gm) ? gm : 0.f;
+    if (tid == 0) s.pre[33] = 0u;
+    __syncthreads();
+    atomicMax(&s.pre[33], __float_as_uint(gm));      // non-negative floats order like their bit patterns
+    __syncthreads();
+  }
+  const float cs_scale = pow2_normaliser(__uint_as_float(s.pre[33]));
+  // stage the query side: Q (scaled; L1 hi/lo + L2h), dO (L1 hi/lo + L2h), lse2, delta, dropout row words
   const int NQ = (a.Lq + BK - 1) / BK;
   for (int i = tid; i < NQ * BK; i += NTHREADS) {
     float q[8], g[8], hi[8], lo[8];
@@ -614,14 +671,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       ld8g(q, a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
       ld8g(g, a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) q[c] *= kQScale;
+      for (int c = 0; c < 8; ++c) { q[c] *= kQScale; g[c] *= cs_scale; }
       lse2 = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
-      delta = a.delta[(long long)nh * a.Lq + i];
+      delta = a.delta[(long long)nh * a.Lq + i] * cs_scale;
     }
     split8(q, hi, lo);
-    put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l2(Q2, i, hi);
+    put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l2h(Q2h, i, q);
     split8(g, hi, lo);
-    put_l1(G1, i, hi); put_l1(G1lo, i, lo); put_l2(G2, i, hi);
+    put_l1(G1, i, hi); put_l1(G1lo, i, lo); put_l2h(G2h, i, g);
     s.f0[i] = lse2; s.f1[i] = delta;
     s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
   }
@@ -635,9 +692,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
   // TMEM columns: S[w] = w*128 (64) ; T[w] = w*128 + 64 (64) ; dK[w] = 256 + w*32 ; dV[w] = 272 + w*32 ; X[w] = 320 + w*32 (Khi | Klo | Vhi | Vlo)
 
   if (warp == 8) {
-    const uint32_t idS = idesc_tf32(128, BK), idA = idesc_tf32(128, 16);
-    const uint32_t aQhi = smem_u32(Qhi), aQlo = smem_u32(Qlo), aG1 = smem_u32(G1), aG1lo = smem_u32(G1lo), aQ2 = smem_u32(Q2), aG2 = smem_u32(G2), aPad = smem_u32(s.pad);
+    const uint32_t idS = idesc_tf32(128, BK), idA = idesc_f16(128, 16);
+    const uint32_t aQhi = smem_u32(Qhi), aQlo = smem_u32(Qlo), aG1 = smem_u32(G1), aG1lo = smem_u32(G1lo), aQ2 = smem_u32(Q2h), aG2 = smem_u32(G2h);
     uint32_t pcount[2] = {0, 0};
+    long long prof[16] = {0};
     auto issue_st = [&](int w, int j) {
       const uint32_t d = tb + (uint32_t)w * 128, x = tb + 320 + (uint32_t)w * 32;
       const uint64_t dQhi = smem_desc(aQhi + j * (BK * 32), 128, 256), dQlo = smem_desc(aQlo + j * (BK * 32), 128, 256);
@@ -649,20 +707,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       if (kSplitT) { mma_ts(d + 64, x + 24, dGhi, idS, 1); mma_ts(d + 64, x + 16, dGlo, idS, 1); }
     };
     auto issue_acc = [&](int w, int j) {
-      const int nsteps = (min(BK, a.Lq - j * BK) + 7) >> 3;
+      if (g_tc_dbg & 1) return;
+      const int nsteps = (min(BK, a.Lq - j * BK) + 15) >> 4;
       const uint32_t dK = tb + 256 + (uint32_t)w * 32, dV = dK + 16;
       for (int t = 0; t < nsteps; ++t) {
-        const uint32_t off = (uint32_t)(j * (BK / 8) + t) * 256;
+        const uint32_t off = (uint32_t)(j * (BK / 16) + t) * 256;
         const uint32_t g2 = aG2 + off, q2 = aQ2 + off;
         const uint32_t acc = (j > 0 || t > 0) ? 1u : 0u;
-        mma_ts(dV, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(g2, 128, aPad - g2), idA, acc);
-        mma_ts(dK, tb + (uint32_t)w * 128 + 64 + (uint32_t)t * 8, smem_desc(q2, 128, aPad - q2), idA, acc);
+        mma_ts_f16(dV, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(g2, 128, HALF_ARR * 2), idA, acc);       // P^T [dOhi | dOlo]
+        mma_ts_f16(dK, tb + (uint32_t)w * 128 + 64 + (uint32_t)t * 8, smem_desc(q2, 128, HALF_ARR * 2), idA, acc);  // dS^T [Qhi | Qlo]
       }
     };
     for (int it = 0; it < NIT; ++it) {
       for (int w = 0; w < 2; ++w) {
         if (2 * it + w >= nKT) continue;
-        mbar_wait(&x_ready[w], it & 1);
+        TPROF(8, mbar_wait(&x_ready[w], it & 1));
         fence_after();
         if (elect_one()) { issue_st(w, 0); commit(&s_ready[w]); }
         __syncwarp();
@@ -670,21 +729,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       for (int j = 0; j < NQ; ++j) {
         for (int w = 0; w < 2; ++w) {
           if (2 * it + w >= nKT) continue;
-          mbar_wait(&p_ready[w], pcount[w] & 1); pcount[w]++;
+          TPROF(9 + w, mbar_wait(&p_ready[w], pcount[w] & 1)); pcount[w]++;
           fence_after();
-          if (elect_one()) {
+          TPROF(11, if (elect_one()) {
             issue_acc(w, j);
             if (j + 1 < NQ) { issue_st(w, j + 1); commit(&s_ready[w]); }
             else commit(&o_ready[w]);
           }
-          __syncwarp();
+          __syncwarp());
         }
       }
     }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) for (int q = 8; q < 12; ++q) g_tc_prof[q] = prof[q];
   } else {
     const int wg = warp >> 2, r = tid & 127;
     const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tb + tlane + (uint32_t)wg * 128, tA = tb + tlane + 256 + (uint32_t)wg * 32, tX = tb + tlane + 320 + (uint32_t)wg * 32;
+    long long prof[16] = {0}; const long long tstart = clock64();
     uint32_t scount = 0;
     for (int it = 0; it < NIT; ++it) {
       const int kt = 2 * it + wg;
@@ -708,8 +769,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       mbar_arrive(&x_ready[wg]);
       const uint32_t cw = dc.on ? drop_col_word(dc, nh, cs) : 1u;
       for (int j = 0; j < NQ; ++j) {
-        mbar_wait(&s_ready[wg], scount & 1); scount++;
+        TPROF(0, mbar_wait(&s_ready[wg], scount & 1)); scount++;
         fence_after();
+        const long long tc0 = clock64();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t sr[32], tr[32];
@@ -719,6 +781,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
           const float4* d4 = reinterpret_cast<const float4*>(s.f1 + j * BK + half * 32);
           const uint4* w4 = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
 #pragma unroll
+          if (!(g_tc_dbg & 2))
           for (int cc = 0; cc < 8; ++cc) {
             const float4 lv = l4[cc], dv = d4[cc];
             const float ll[4] = {lv.x, lv.y, lv.z, lv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
@@ -727,8 +790,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
               for (int e = 0; e < 4; ++e) {
                 const int c = cc * 4 + e;
                 const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
-                sr[c] = __float_as_uint(p) + 0x1000u;
-                tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - dd[e])) + 0x1000u;
+                sr[c] = __float_as_uint(p);
+                tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - dd[e]));
               }
             } else {
               const uint4 wv = w4[cc];
@@ -738,30 +801,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
                 const int c = cc * 4 + e;
                 const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
                 const float dm = (ww[e] * cw >= dc.thr) ? dc.scale : 0.f;
-                sr[c] = __float_as_uint(p * dm) + 0x1000u;
-                tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) * dm - dd[e])) + 0x1000u;
+                sr[c] = __float_as_uint(p * dm);
+                tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) * dm - dd[e]));
               }
             }
           }
-          tmem_st32(tS + half * 32, sr); tmem_st32(tS + 64 + half * 32, tr);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            sr[c] = pack_h2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1]));
+            tr[c] = pack_h2(__uint_as_float(tr[2 * c]), __uint_as_float(tr[2 * c + 1]));
+          }
+          tmem_st16(tS + half * 16, sr); tmem_st16(tS + 64 + half * 16, tr);
         }
-        tmem_wait_st();
+        prof[1] += clock64() - tc0;
+        TPROF(2, tmem_wait_st());
         fence_before();
         mbar_arrive(&p_ready[wg]);
       }
-      mbar_wait(&o_ready[wg], it & 1);
+      TPROF(3, mbar_wait(&o_ready[wg], it & 1));
       fence_after();
       uint32_t o[32];
       tmem_ld32(tA, o); tmem_wait_ld();
       if (valid) {
         float dk[8], dv[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) { dk[c] = __uint_as_float(o[c]) * kLn2; dv[c] = __uint_as_float(o[16 + c]); }   // Q carried log2(e)
+        const float inv = 1.f / cs_scale;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {      // hi + lo parts; Q carried log2(e)
+          dk[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * (kLn2 * inv);
+          dv[c] = (__uint_as_float(o[16 + c]) + __uint_as_float(o[24 + c])) * inv;
+        }
         st8g(a.dk + ((long long)n * a.Lk + jk) * a.lddk + h * 8, dk);
         st8g(a.dv + ((long long)n * a.Lk + jk) * a.lddv + h * 8, dv);
       }
       fence_before();
     }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { prof[4] = clock64() - tstart; for (int q = 0; q < 5; ++q) g_tc_prof[q] = prof[q]; }
   }
   fence_before();
   __syncthreads();
@@ -805,3 +880,6 @@ int attn_tc_bwd(const AttnArgs& a, cudaStream_t st) {
 }
 
 }  // namespace vaesne
+extern "C" int vaesne_debug_tc_prof(long long* out16) { return (int)cudaMemcpyFromSymbol(out16, vaesne::g_tc_prof, 16 * sizeof(long long)); }
+extern "C" int vaesne_debug_tc(int flags) { return (int)cudaMemcpyToSymbol(vaesne::g_tc_dbg, &flags, sizeof(int)); }
+

@@ -69,7 +69,6 @@ if os.environ.get('TC_PROF'):
     lib = ctypes.CDLL(os.path.join(ROOT, 'vaesne-dev_b200', 'lib', 'libvaesne_b200.so'))
     buf = (ctypes.c_longlong * 16)()
     torch.cuda.synchronize(); lib.vaesne_debug_tc_prof(buf)
-    names = ["warp0 wait s_ready", "warp0 ld+compute+st", "warp0 wait::st", "warp0 wait o_ready", "warp0 total", "", "", "",
-             "issuer wait x_ready", "issuer wait p_ready[0]", "issuer wait p_ready[1]", "issuer issue+commit"]
+    names = ["warp0 wait s_ready", "warp0 ld+compute (incl. in_free signal)", "warp0 wait::st", "warp0 wait o_ready", "warp0 total", "warp0 wait out_free"]
     for n_, v in zip(names, buf):
         if n_: print(f"  dkv CTA(0,0) {n_:28s} {v:10d} clk")

@@ -41,7 +41,7 @@ constexpr int TCQ = 128;            // rows per tile (= TMEM lanes)
 constexpr int FK = 128;             // fwd: keys per tile
 constexpr int BK = 64;              // bwd: columns per tile
 constexpr int MAXL = 1024;          // staged column-side length
-constexpr int NTHREADS = 288;       // 8 softmax warps + 1 MMA warp
+constexpr int NTHREADS = 320;       // 8 softmax warps (2 warpgroups) + 1 MMA-issuing warp per warpgroup
 constexpr float kScale = 0.35355339059327373f;             // sqrt(1/8)
 constexpr float kQScale = kScale * 1.4426950408889634f;    // ... * log2(e)
 constexpr float kLazy = 8.f;        // rescale O only when the row max grows by more than 2^8
@@ -158,7 +158,7 @@ struct TcSmem {
   uint32_t* ballot; uint32_t* pre; uint64_t* bars; uint32_t* tmem;
 };
 __host__ __device__ constexpr size_t tc_smem_bytes(int narr, bool cols) {
-  return 128 + (size_t)narr * TILE_F * 4 + 256 + (cols ? 2 * MAXL * 4 : 0) + MAXL * 4 + MAXL * 2 + 32 * 4 + 36 * 4 + 8 * 8 + 16;
+  return 128 + (size_t)narr * TILE_F * 4 + 256 + (cols ? 2 * MAXL * 4 : 0) + MAXL * 4 + MAXL * 2 + 32 * 4 + 36 * 4 + 16 * 8 + 16;
 }
 // (the dynamic shared window is declared __align__(1024); deriving every pointer from it by plain pointer
 // arithmetic keeps the shared address space visible to ptxas: LDS/STS instead of generic LD/ST)
@@ -174,7 +174,7 @@ __device__ __forceinline__ TcSmem carve(unsigned char* raw, int narr, bool cols)
   s.idx = (uint16_t*)f; f += MAXL / 2;
   s.ballot = (uint32_t*)f; s.pre = s.ballot + 32;    // pre[0..31] exclusive prefix, pre[32] total
   s.bars = (uint64_t*)(s.pre + 36);
-  s.tmem = (uint32_t*)(s.bars + 8);
+  s.tmem = (uint32_t*)(s.bars + 16);
   return s;
 }
 
@@ -238,15 +238,67 @@ __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, i
   }
 }
 
-__device__ __forceinline__ void init_common(const TcSmem& s, int tid, int warp, float pad_row0) {
-  uint64_t* b = s.bars;
+// =================================================================================================
+// pipeline skeleton shared by the three kernels
+// =================================================================================================
+// TMEM, per warpgroup w (256 columns at w*256):
+//   IN  [0,128)  : score tiles written by the first product (fwd: S 128 ; bwd: S 64 | T 64)
+//   OUT [128,192): what the warpgroup writes back as fp16 pairs (fwd: P ; bwd: P^T 32 | dS 32) = A operand of the second product
+//   ACC [192,224): accumulators of the second product           X [224,256): this warpgroup's row operands
+// mbarriers, per warpgroup: x_ready (128 arrivals: row operands stored), s_ready (commit: first product done),
+//   in_free (128: the warpgroup holds the score tile in registers), p_ready (128: OUT stored),
+//   out_free (commit: second product has consumed OUT), o_ready (commit: accumulators final).
+// Because OUT is separate from IN, the issuer runs the first product of tile j+1 while the warpgroup is still
+// exponentiating tile j, and the second product of tile j while it works on tile j+1: the warpgroups compute back to
+// back and the exponential unit (MUFU, 16/clk/SM) is the only resource that saturates.  One issuer warp per warpgroup.
+constexpr int C_IN = 0, C_OUT = 128, C_ACC = 192, C_X = 224, C_WG = 256;
+constexpr int B_X = 0, B_S = 1, B_F = 2, B_P = 3, B_OF = 4, B_O = 5, B_PER_WG = 6;
+
+__device__ __forceinline__ void init_pipeline(const TcSmem& s, int tid, int warp) {
   if (tid == 0) {
-    for (int w = 0; w < 2; ++w) { mbar_init(&b[w], 128); mbar_init(&b[2 + w], 1); mbar_init(&b[4 + w], 128); mbar_init(&b[6 + w], 1); }
+    for (int w = 0; w < 2; ++w) {
+      uint64_t* b = s.bars + w * B_PER_WG;
+      mbar_init(&b[B_X], 128); mbar_init(&b[B_S], 1); mbar_init(&b[B_F], 128); mbar_init(&b[B_P], 128); mbar_init(&b[B_OF], 1); mbar_init(&b[B_O], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (tid < 64) s.pad[tid] = ((tid & 31) < 4) ? pad_row0 : 0.f;    // row 0 of both 16-byte K chunks
   if (warp == 8) tmem_alloc<512>(s.tmem);
 }
+
+// Issuer of warpgroup w: row tiles w, w+2, ... ; T column tiles each.
+// issue_in(j): first product of column tile j into IN.   issue_acc(j): second product of tile j from OUT into ACC.
+template <class FIn, class FAcc>
+__device__ __forceinline__ void mma_issuer(uint64_t* b, int w, int nRT, int T, FIn issue_in, FAcc issue_acc) {
+  if (T <= 0) return;
+  uint32_t cF = 0, cP = 0;
+  int it = 0;
+  for (int rt = w; rt < nRT; rt += 2, ++it) {
+    mbar_wait(&b[B_X], it & 1);
+    fence_after();
+    if (elect_one()) { issue_in(0); commit(&b[B_S]); }
+    __syncwarp();
+    for (int j = 0; j < T; ++j) {
+      if (j + 1 < T) {
+        mbar_wait(&b[B_F], cF & 1); cF++;
+        fence_after();
+        if (elect_one()) { issue_in(j + 1); commit(&b[B_S]); }
+        __syncwarp();
+      }
+      mbar_wait(&b[B_P], cP & 1); cP++;
+      fence_after();
+      if (elect_one()) { issue_acc(j); commit(j + 1 < T ? &b[B_OF] : &b[B_O]); }
+      __syncwarp();
+    }
+  }
+}
+
+// warpgroup-side bookkeeping of barrier phases
+struct WgPhase {
+  uint32_t cs, cof;
+  __device__ __forceinline__ void wait_s(uint64_t* b) { mbar_wait(&b[B_S], cs & 1); cs++; fence_after(); }
+  __device__ __forceinline__ void wait_out_free(uint64_t* b) { mbar_wait(&b[B_OF], cof & 1); cof++; fence_after(); }
+};
+__device__ __forceinline__ void signal_in_free(uint64_t* b) { fence_before(); mbar_arrive(&b[B_F]); }
 
 // =================================================================================================
 // forward
@@ -259,13 +311,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
   float* Khi = s.arr[0]; float* Klo = s.arr[1]; __half* V2h = reinterpret_cast<__half*>(s.arr[2]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
-  uint64_t* x_ready = s.bars;       // [2] count 128 : row operands (Q) stored in TMEM
-  uint64_t* s_ready = s.bars + 2;   // [2] count 1   : tcgen05.commit after S
-  uint64_t* p_ready = s.bars + 4;   // [2] count 128 : P stored in TMEM
-  uint64_t* o_ready = s.bars + 6;   // [2] count 1   : tcgen05.commit after the last PV
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
 
-  init_common(s, tid, warp, 0.f);
+  init_pipeline(s, tid, warp);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
   stage_keys(a, s, n, h, tid, LkC, FK, Khi, Klo, nullptr, nullptr, V2h, nullptr, dc);
   fence_async_smem();
@@ -275,60 +323,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
   const uint32_t tb = *s.tmem;
   const int T = (LkC + FK - 1) / FK;
   const int nQT = (a.Lq + TCQ - 1) / TCQ;
-  const int NIT = (nQT + 1) / 2;
-  // TMEM columns: S[w] = w*128 (128) ; O[w] = 256 + w*16 (16) ; Q[w] = 288 + w*16 (hi 8 | lo 8)
+  // per warpgroup: IN = S (128 columns) ; OUT = P as fp16 pairs (64) ; ACC = O hi (8) | O lo (8) ; X = Q hi (8) | Q lo (8)
 
-  if (warp == 8) {
-    // ------------------------------- MMA issuer -------------------------------------------------
+  if (warp >= 8) {
+    const int w = warp - 8;
     const uint32_t idQK = idesc_tf32(128, FK), idPV = idesc_f16(128, 16);
     const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV2 = smem_u32(V2h);
-    uint32_t pcount[2] = {0, 0};
-    auto issue_qk = [&](int w, int j) {
-      const uint32_t d = tb + (uint32_t)w * 128, q = tb + 288 + (uint32_t)w * 16;
+    const uint32_t tw = tb + (uint32_t)(w * C_WG);
+    auto issue_qk = [&](int j) {
+      const uint32_t d = tw + C_IN, q = tw + C_X;
       const uint64_t dKhi = smem_desc(aKhi + j * (FK * 32), 128, 256), dKlo = smem_desc(aKlo + j * (FK * 32), 128, 256);
       mma_ts(d, q, dKhi, idQK, 0);
       mma_ts(d, q + 8, dKhi, idQK, 1);
       mma_ts(d, q, dKlo, idQK, 1);
     };
-    auto issue_pv = [&](int w, int j) {
+    auto issue_pv = [&](int j) {
       const int nsteps = (min(FK, LkC - j * FK) + 15) >> 4;      // 16 keys per kind::f16 MMA
-      const uint32_t dO = tb + 256 + (uint32_t)w * 16;
       for (int t = 0; t < nsteps; ++t) {
         const uint32_t v = aV2 + (uint32_t)(j * (FK / 16) + t) * 256;
-        mma_ts_f16(dO, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(v, 128, HALF_ARR * 2), idPV, (j > 0 || t > 0) ? 1u : 0u);   // [Vhi | Vlo]
+        mma_ts_f16(tw + C_ACC, tw + C_OUT + (uint32_t)t * 8, smem_desc(v, 128, HALF_ARR * 2), idPV, (j > 0 || t > 0) ? 1u : 0u);   // [Vhi | Vlo]
       }
     };
-    for (int it = 0; it < NIT && T > 0; ++it) {
-      for (int w = 0; w < 2; ++w) {
-        if (2 * it + w >= nQT) continue;
-        mbar_wait(&x_ready[w], it & 1);
-        fence_after();
-        if (elect_one()) { issue_qk(w, 0); commit(&s_ready[w]); }
-        __syncwarp();
-      }
-      for (int j = 0; j < T; ++j) {
-        for (int w = 0; w < 2; ++w) {
-          if (2 * it + w >= nQT) continue;
-          mbar_wait(&p_ready[w], pcount[w] & 1); pcount[w]++;
-          fence_after();
-          if (elect_one()) {
-            issue_pv(w, j);
-            if (j + 1 < T) { issue_qk(w, j + 1); commit(&s_ready[w]); }
-            else commit(&o_ready[w]);
-          }
-          __syncwarp();
-        }
-      }
-    }
+    mma_issuer(s.bars + w * B_PER_WG, w, nQT, T, issue_qk, issue_pv);
   } else {
-    // ------------------------------- softmax warpgroups ------------------------------------------
     const int wg = warp >> 2, r = tid & 127;
-    const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tS = tb + tlane + (uint32_t)wg * 128, tO = tb + tlane + 256 + (uint32_t)wg * 16, tQ = tb + tlane + 288 + (uint32_t)wg * 16;
-    uint32_t scount = 0;
-    for (int it = 0; it < NIT; ++it) {
-      const int qt = 2 * it + wg;
-      if (qt >= nQT) break;
+    uint64_t* bars = s.bars + wg * B_PER_WG;
+    const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * C_WG);
+    const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tO = tw + C_ACC, tQ = tw + C_X;
+    WgPhase ph = {0, 0};
+    int it = 0;
+    for (int qt = wg; qt < nQT; qt += 2, ++it) {
       const int i = qt * TCQ + r;
       const bool valid = i < a.Lq;
       if (T == 0) {       // every key masked: softmax of an empty set (the reference yields NaN)
@@ -352,17 +376,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
         tmem_put8(tQ, hi); tmem_put8(tQ + 8, lo);
         tmem_wait_st();
         fence_before();
-        mbar_arrive(&x_ready[wg]);
+        mbar_arrive(&bars[B_X]);
       }
       const uint32_t rw = dc.on ? drop_row_word(dc, nh, a.Lq, valid ? i : 0) : 1u;
       float m_used = -1e30f, lsum = 0.f;
       for (int j = 0; j < T; ++j) {
-        mbar_wait(&s_ready[wg], scount & 1); scount++;
-        fence_after();
+        ph.wait_s(bars);
         const int nvalid = min(FK, LkC - j * FK);
         uint32_t sr[128];
-        tmem_ld32(tS, sr); tmem_ld32(tS + 32, sr + 32); tmem_ld32(tS + 64, sr + 64); tmem_ld32(tS + 96, sr + 96);
+        tmem_ld32(tIN, sr); tmem_ld32(tIN + 32, sr + 32); tmem_ld32(tIN + 64, sr + 64); tmem_ld32(tIN + 96, sr + 96);
         tmem_wait_ld();
+        if (j + 1 < T) signal_in_free(bars);          // QK^T of the next tile runs under this tile's softmax
         float mt = -1e30f;
         if (nvalid == FK) {
 #pragma unroll
@@ -372,52 +396,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
           for (int c = 0; c < 128; ++c) { if (c >= nvalid) sr[c] = 0xff800000u; mt = fmaxf(mt, __uint_as_float(sr[c])); }
         }
         const float m_new = fmaxf(m_used, mt);
-        const bool need = (m_new > m_used + kLazy);
-        if (__any_sync(0xffffffffu, need)) {         // warp-uniform: TMEM ld/st are warp-collective
-          const float alpha = ex2(m_used - m_new);   // first tile: 2^(-1e30 - m) = 0, O not yet written
-          if (j > 0) {
+        const bool resc = __any_sync(0xffffffffu, m_new > m_used + kLazy);    // warp-uniform: TMEM ld/st are warp-collective
+        float alpha = 1.f;
+        if (resc) { alpha = ex2(m_used - m_new); lsum *= alpha; m_used = m_new; }   // first tile: 2^(-1e30 - m) = 0
+        // the row sum stays in fp32 registers (it defines LSE, which the backward exponentiates); the MMA operand is P
+        // rounded to nearest fp16 (11 significant bits, like tf32; P <= 2^8 by the lazy rescale): 64 TMEM columns
+        uint32_t pk[64];
+        if (!dc.on) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const float p0 = ex2(__uint_as_float(sr[2 * c]) - m_used), p1 = ex2(__uint_as_float(sr[2 * c + 1]) - m_used);
+            lsum += p0 + p1;
+            pk[c] = pack_h2(p0, p1);
+          }
+        } else {
+          const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * FK);
+#pragma unroll
+          for (int cc = 0; cc < 32; ++cc) {
+            const uint4 bq = bw[cc];
+            const uint32_t bb[4] = {bq.x, bq.y, bq.z, bq.w};
+            float pp[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float p = ex2(__uint_as_float(sr[cc * 4 + e]) - m_used);
+              lsum += p;
+              pp[e] = (rw * bb[e] >= dc.thr) ? p : 0.f;
+            }
+            pk[cc * 2] = pack_h2(pp[0], pp[1]); pk[cc * 2 + 1] = pack_h2(pp[2], pp[3]);
+          }
+        }
+        if (j > 0) {
+          ph.wait_out_free(bars);                    // PV of tile j-1 has consumed OUT and updated O
+          if (resc) {
             uint32_t o[16];
             tmem_ld16(tO, o); tmem_wait_ld();
 #pragma unroll
             for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
             tmem_st16(tO, o);
           }
-          lsum *= alpha;
-          m_used = m_new;
         }
-        if (!dc.on) {
-          // the row sum stays in fp32 registers (it defines LSE, which the backward exponentiates); the MMA
-          // operand is P rounded to nearest fp16 (11 significant bits, like tf32)
-#pragma unroll
-          for (int c = 0; c < 128; ++c) {
-            const float p = ex2(__uint_as_float(sr[c]) - m_used);
-            lsum += p;
-            sr[c] = __float_as_uint(p);
-          }
-        } else {
-          const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * FK);
-#pragma unroll
-          for (int cc = 0; cc < 32; ++cc) {
-            const uint4 b = bw[cc];
-            const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float p = ex2(__uint_as_float(sr[cc * 4 + e]) - m_used);
-              lsum += p;
-              sr[cc * 4 + e] = (rw * bb[e] >= dc.thr) ? __float_as_uint(p) : 0u;
-            }
-          }
-        }
-        // P (<= 2^8 by the lazy rescale) leaves as fp16 pairs: 64 TMEM columns, 8 MMAs of K = 16 per tile
-#pragma unroll
-        for (int c = 0; c < 64; ++c) sr[c] = pack_h2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1]));
-        tmem_st32(tS, sr); tmem_st32(tS + 32, sr + 32);
+        tmem_st32(tOUT, pk); tmem_st32(tOUT + 32, pk + 32);
         tmem_wait_st();
         fence_before();
-        mbar_arrive(&p_ready[wg]);
+        mbar_arrive(&bars[B_P]);
       }
       // epilogue: (O_hi + O_lo) / l
-      mbar_wait(&o_ready[wg], it & 1);
+      mbar_wait(&bars[B_O], it & 1);
       fence_after();
       uint32_t o[16];
       tmem_ld16(tO, o); tmem_wait_ld();
@@ -448,10 +472,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
   float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V1 = s.arr[2]; float* V1lo = s.arr[3]; __half* K2h = reinterpret_cast<__half*>(s.arr[4]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
-  uint64_t* x_ready = s.bars; uint64_t* s_ready = s.bars + 2; uint64_t* p_ready = s.bars + 4; uint64_t* o_ready = s.bars + 6;
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
 
-  init_common(s, tid, warp, 0.f);
+  init_pipeline(s, tid, warp);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
   stage_keys(a, s, n, h, tid, LkC, BK, Khi, Klo, V1, V1lo, nullptr, K2h, dc);
   fence_async_smem();
@@ -461,15 +484,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
   const uint32_t tb = *s.tmem;
   const int T = (LkC + BK - 1) / BK;
   const int nQT = (a.Lq + TCQ - 1) / TCQ;
-  const int NIT = (nQT + 1) / 2;
-  // TMEM columns: S[w] = w*128 (64) ; T[w] = w*128 + 64 (64) ; ACC[w] = 256 + w*16 ; X[w] = 288 + w*32 (Qhi | Qlo | dOhi | dOlo)
+  // per warpgroup: IN = S (64) | T (64) ; OUT = dS as fp16 pairs (32) ; ACC = dQ hi (8) | lo (8) ; X = Qhi | Qlo | dOhi | dOlo
 
-  if (warp == 8) {
+  if (warp >= 8) {
+    const int w = warp - 8;
     const uint32_t idS = idesc_tf32(128, BK), idA = idesc_f16(128, 16);
     const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV1 = smem_u32(V1), aV1lo = smem_u32(V1lo), aK2 = smem_u32(K2h);
-    uint32_t pcount[2] = {0, 0};
-    auto issue_st = [&](int w, int j) {
-      const uint32_t d = tb + (uint32_t)w * 128, x = tb + 288 + (uint32_t)w * 32;
+    const uint32_t tw = tb + (uint32_t)(w * C_WG);
+    auto issue_st = [&](int j) {
+      const uint32_t d = tw + C_IN, x = tw + C_X;
       const uint64_t dKhi = smem_desc(aKhi + j * (BK * 32), 128, 256), dKlo = smem_desc(aKlo + j * (BK * 32), 128, 256);
       mma_ts(d, x, dKhi, idS, 0);
       mma_ts(d, x + 8, dKhi, idS, 1);
@@ -478,44 +501,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
       mma_ts(d + 64, x + 16, dVhi, idS, 0);
       if (kSplitT) { mma_ts(d + 64, x + 24, dVhi, idS, 1); mma_ts(d + 64, x + 16, dVlo, idS, 1); }
     };
-    auto issue_acc = [&](int w, int j) {
+    auto issue_acc = [&](int j) {
       const int nsteps = (min(BK, LkC - j * BK) + 15) >> 4;
-      const uint32_t dA = tb + 256 + (uint32_t)w * 16;
       for (int t = 0; t < nsteps; ++t) {
         const uint32_t k2 = aK2 + (uint32_t)(j * (BK / 16) + t) * 256;
-        mma_ts_f16(dA, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(k2, 128, HALF_ARR * 2), idA, (j > 0 || t > 0) ? 1u : 0u);   // [Khi | Klo]
+        mma_ts_f16(tw + C_ACC, tw + C_OUT + (uint32_t)t * 8, smem_desc(k2, 128, HALF_ARR * 2), idA, (j > 0 || t > 0) ? 1u : 0u);   // [Khi | Klo]
       }
     };
-    for (int it = 0; it < NIT && T > 0; ++it) {
-      for (int w = 0; w < 2; ++w) {
-        if (2 * it + w >= nQT) continue;
-        mbar_wait(&x_ready[w], it & 1);
-        fence_after();
-        if (elect_one()) { issue_st(w, 0); commit(&s_ready[w]); }
-        __syncwarp();
-      }
-      for (int j = 0; j < T; ++j) {
-        for (int w = 0; w < 2; ++w) {
-          if (2 * it + w >= nQT) continue;
-          mbar_wait(&p_ready[w], pcount[w] & 1); pcount[w]++;
-          fence_after();
-          if (elect_one()) {
-            issue_acc(w, j);
-            if (j + 1 < T) { issue_st(w, j + 1); commit(&s_ready[w]); }
-            else commit(&o_ready[w]);
-          }
-          __syncwarp();
-        }
-      }
-    }
+    mma_issuer(s.bars + w * B_PER_WG, w, nQT, T, issue_st, issue_acc);
   } else {
     const int wg = warp >> 2, r = tid & 127;
-    const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tS = tb + tlane + (uint32_t)wg * 128, tA = tb + tlane + 256 + (uint32_t)wg * 16, tX = tb + tlane + 288 + (uint32_t)wg * 32;
-    uint32_t scount = 0;
-    for (int it = 0; it < NIT; ++it) {
-      const int qt = 2 * it + wg;
-      if (qt >= nQT) break;
+    uint64_t* bars = s.bars + wg * B_PER_WG;
+    const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * C_WG);
+    const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
+    WgPhase ph = {0, 0};
+    int it = 0;
+    for (int qt = wg; qt < nQT; qt += 2, ++it) {
       const int i = qt * TCQ + r;
       const bool valid = i < a.Lq;
       float q[8], g[8], hi[8], lo[8];
@@ -532,14 +533,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
         lse2 = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
         a.delta[(long long)nh * a.Lq + i] = delta;
       }
-      // dS leaves as fp16: this row's dO (hence dP, delta, dS, dQ: all linear in it) is scaled by a power of two into [1, 2)
-      float gmax = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) gmax = fmaxf(gmax, fabsf(g[c]));
-      const float rs = pow2_normaliser(gmax);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) g[c] *= rs;
-      delta *= rs;
       if (T == 0) {       // every key masked: the reference's gradients are NaN
         if (valid) {
 #pragma unroll
@@ -548,57 +541,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
         }
         continue;
       }
+      // dS leaves as fp16: this row's dO (hence dP, delta, dS, dQ: all linear in it) is scaled by a power of two into [1, 2)
+      float gmax = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) gmax = fmaxf(gmax, fabsf(g[c]));
+      const float rs = pow2_normaliser(gmax);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) g[c] *= rs;
+      delta *= rs;
       split8(q, hi, lo);
       tmem_put8(tX, hi); tmem_put8(tX + 8, lo);
       split8(g, hi, lo);
       tmem_put8(tX + 16, hi); tmem_put8(tX + 24, lo);
       tmem_wait_st();
       fence_before();
-      mbar_arrive(&x_ready[wg]);
+      mbar_arrive(&bars[B_X]);
       const uint32_t rw = dc.on ? drop_row_word(dc, nh, a.Lq, valid ? i : 0) : 1u;
       for (int j = 0; j < T; ++j) {
-        mbar_wait(&s_ready[wg], scount & 1); scount++;
-        fence_after();
+        ph.wait_s(bars);
         const int nvalid = min(BK, LkC - j * BK);
+        uint32_t pk[32];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t sr[32], tr[32];
-          tmem_ld32(tS + half * 32, sr); tmem_ld32(tS + 64 + half * 32, tr);
+          tmem_ld32(tIN + half * 32, sr); tmem_ld32(tIN + 64 + half * 32, tr);
           tmem_wait_ld();
+          if (half == 1 && j + 1 < T) signal_in_free(bars);       // the next tile's first product runs under this one's exponentials
+          float ds[32];
           if (!dc.on) {
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float p = ex2(__uint_as_float(sr[c]) - lse2);
-              sr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - delta));
+              ds[c] = p * (__uint_as_float(tr[c]) - delta);
             }
           } else {
             const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
 #pragma unroll
             for (int cc = 0; cc < 8; ++cc) {
-              const uint4 b = bw[cc];
-              const uint32_t bb[4] = {b.x, b.y, b.z, b.w};
+              const uint4 bq = bw[cc];
+              const uint32_t bb[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int c = cc * 4 + e;
                 const float p = ex2(__uint_as_float(sr[c]) - lse2);
                 const float dp = (rw * bb[e] >= dc.thr) ? __uint_as_float(tr[c]) * dc.scale : 0.f;
-                sr[c] = __float_as_uint(p * (dp - delta));
+                ds[c] = p * (dp - delta);
               }
             }
           }
           if (nvalid < BK) {      // padded key slots: exactly zero (2^(-lse) may overflow and inf * 0 would poison the row)
 #pragma unroll
-            for (int c = 0; c < 32; ++c) if (half * 32 + c >= nvalid) sr[c] = 0u;
+            for (int c = 0; c < 32; ++c) if (half * 32 + c >= nvalid) ds[c] = 0.f;
           }
 #pragma unroll
-          for (int c = 0; c < 16; ++c) sr[c] = pack_h2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1]));
-          tmem_st16(tS + half * 16, sr);
+          for (int c = 0; c < 16; ++c) pk[half * 16 + c] = pack_h2(ds[2 * c], ds[2 * c + 1]);
         }
+        if (j > 0) ph.wait_out_free(bars);
+        tmem_st32(tOUT, pk);
         tmem_wait_st();
         fence_before();
-        mbar_arrive(&p_ready[wg]);
+        mbar_arrive(&bars[B_P]);
       }
-      mbar_wait(&o_ready[wg], it & 1);
+      mbar_wait(&bars[B_O], it & 1);
       fence_after();
       uint32_t o[16];
       tmem_ld16(tA, o); tmem_wait_ld();
@@ -628,10 +632,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
   __half* Q2h = reinterpret_cast<__half*>(s.arr[4]); __half* G2h = reinterpret_cast<__half*>(s.arr[5]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
-  uint64_t* x_ready = s.bars; uint64_t* s_ready = s.bars + 2; uint64_t* p_ready = s.bars + 4; uint64_t* o_ready = s.bars + 6;
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
 
-  init_common(s, tid, warp, 0.f);
+  init_pipeline(s, tid, warp);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
   // slot -> key index, zero gradients of the masked keys
   for (int j = tid; j < a.Lk; j += NTHREADS) {
@@ -688,16 +691,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
   fence_after();
   const uint32_t tb = *s.tmem;
   const int nKT = (LkC + TCQ - 1) / TCQ;
-  const int NIT = (nKT + 1) / 2;
-  // TMEM columns: S[w] = w*128 (64) ; T[w] = w*128 + 64 (64) ; dK[w] = 256 + w*32 ; dV[w] = 272 + w*32 ; X[w] = 320 + w*32 (Khi | Klo | Vhi | Vlo)
+  // per warpgroup: IN = S^T (64) | T^T (64) ; OUT = P^T (32) | dS^T (32) as fp16 pairs ; ACC = dK hi|lo (16) | dV hi|lo (16) ; X = Khi | Klo | Vhi | Vlo
 
-  if (warp == 8) {
+  if (warp >= 8) {
+    const int w = warp - 8;
     const uint32_t idS = idesc_tf32(128, BK), idA = idesc_f16(128, 16);
     const uint32_t aQhi = smem_u32(Qhi), aQlo = smem_u32(Qlo), aG1 = smem_u32(G1), aG1lo = smem_u32(G1lo), aQ2 = smem_u32(Q2h), aG2 = smem_u32(G2h);
-    uint32_t pcount[2] = {0, 0};
-    long long prof[16] = {0};
-    auto issue_st = [&](int w, int j) {
-      const uint32_t d = tb + (uint32_t)w * 128, x = tb + 320 + (uint32_t)w * 32;
+    const uint32_t tw = tb + (uint32_t)(w * C_WG);
+    auto issue_st = [&](int j) {
+      const uint32_t d = tw + C_IN, x = tw + C_X;
       const uint64_t dQhi = smem_desc(aQhi + j * (BK * 32), 128, 256), dQlo = smem_desc(aQlo + j * (BK * 32), 128, 256);
       mma_ts(d, x, dQhi, idS, 0);
       mma_ts(d, x + 8, dQhi, idS, 1);
@@ -706,50 +708,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       mma_ts(d + 64, x + 16, dGhi, idS, 0);
       if (kSplitT) { mma_ts(d + 64, x + 24, dGhi, idS, 1); mma_ts(d + 64, x + 16, dGlo, idS, 1); }
     };
-    auto issue_acc = [&](int w, int j) {
+    auto issue_acc = [&](int j) {
       if (g_tc_dbg & 1) return;
       const int nsteps = (min(BK, a.Lq - j * BK) + 15) >> 4;
-      const uint32_t dK = tb + 256 + (uint32_t)w * 32, dV = dK + 16;
+      const uint32_t dK = tw + C_ACC, dV = dK + 16;
       for (int t = 0; t < nsteps; ++t) {
         const uint32_t off = (uint32_t)(j * (BK / 16) + t) * 256;
-        const uint32_t g2 = aG2 + off, q2 = aQ2 + off;
         const uint32_t acc = (j > 0 || t > 0) ? 1u : 0u;
-        mma_ts_f16(dV, tb + (uint32_t)w * 128 + (uint32_t)t * 8, smem_desc(g2, 128, HALF_ARR * 2), idA, acc);       // P^T [dOhi | dOlo]
-        mma_ts_f16(dK, tb + (uint32_t)w * 128 + 64 + (uint32_t)t * 8, smem_desc(q2, 128, HALF_ARR * 2), idA, acc);  // dS^T [Qhi | Qlo]
+        mma_ts_f16(dV, tw + C_OUT + (uint32_t)t * 8, smem_desc(aG2 + off, 128, HALF_ARR * 2), idA, acc);        // P^T [dOhi | dOlo]
+        mma_ts_f16(dK, tw + C_OUT + 32 + (uint32_t)t * 8, smem_desc(aQ2 + off, 128, HALF_ARR * 2), idA, acc);   // dS^T [Qhi | Qlo]
       }
     };
-    for (int it = 0; it < NIT; ++it) {
-      for (int w = 0; w < 2; ++w) {
-        if (2 * it + w >= nKT) continue;
-        TPROF(8, mbar_wait(&x_ready[w], it & 1));
-        fence_after();
-        if (elect_one()) { issue_st(w, 0); commit(&s_ready[w]); }
-        __syncwarp();
-      }
-      for (int j = 0; j < NQ; ++j) {
-        for (int w = 0; w < 2; ++w) {
-          if (2 * it + w >= nKT) continue;
-          TPROF(9 + w, mbar_wait(&p_ready[w], pcount[w] & 1)); pcount[w]++;
-          fence_after();
-          TPROF(11, if (elect_one()) {
-            issue_acc(w, j);
-            if (j + 1 < NQ) { issue_st(w, j + 1); commit(&s_ready[w]); }
-            else commit(&o_ready[w]);
-          }
-          __syncwarp());
-        }
-      }
-    }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) for (int q = 8; q < 12; ++q) g_tc_prof[q] = prof[q];
+    mma_issuer(s.bars + w * B_PER_WG, w, nKT, NQ, issue_st, issue_acc);
   } else {
     const int wg = warp >> 2, r = tid & 127;
-    const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tS = tb + tlane + (uint32_t)wg * 128, tA = tb + tlane + 256 + (uint32_t)wg * 32, tX = tb + tlane + 320 + (uint32_t)wg * 32;
+    uint64_t* bars = s.bars + wg * B_PER_WG;
+    const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * C_WG);
+    const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
     long long prof[16] = {0}; const long long tstart = clock64();
-    uint32_t scount = 0;
-    for (int it = 0; it < NIT; ++it) {
-      const int kt = 2 * it + wg;
-      if (kt >= nKT) break;
+    WgPhase ph = {0, 0};
+    int it = 0;
+    for (int kt = wg; kt < nKT; kt += 2, ++it) {
       const int cs = kt * TCQ + r;
       const bool valid = cs < LkC;
       const int jk = valid ? (int)s.idx[cs] : 0;
@@ -766,32 +745,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       tmem_put8(tX + 16, hi); tmem_put8(tX + 24, lo);
       tmem_wait_st();
       fence_before();
-      mbar_arrive(&x_ready[wg]);
+      mbar_arrive(&bars[B_X]);
       const uint32_t cw = dc.on ? drop_col_word(dc, nh, cs) : 1u;
       for (int j = 0; j < NQ; ++j) {
-        TPROF(0, mbar_wait(&s_ready[wg], scount & 1)); scount++;
-        fence_after();
+        TPROF(0, ph.wait_s(bars));
         const long long tc0 = clock64();
+        uint32_t pk[32], dk2[32];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t sr[32], tr[32];
-          tmem_ld32(tS + half * 32, sr); tmem_ld32(tS + 64 + half * 32, tr);
+          tmem_ld32(tIN + half * 32, sr); tmem_ld32(tIN + 64 + half * 32, tr);
           tmem_wait_ld();
+          if (half == 1 && j + 1 < NQ) signal_in_free(bars);      // the next tile's first product runs under this one's exponentials
           const float4* l4 = reinterpret_cast<const float4*>(s.f0 + j * BK + half * 32);
           const float4* d4 = reinterpret_cast<const float4*>(s.f1 + j * BK + half * 32);
           const uint4* w4 = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
-#pragma unroll
           if (!(g_tc_dbg & 2))
+#pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
             const float4 lv = l4[cc], dv = d4[cc];
             const float ll[4] = {lv.x, lv.y, lv.z, lv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+            float pp[4], ss[4];
             if (!dc.on) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int c = cc * 4 + e;
-                const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
-                sr[c] = __float_as_uint(p);
-                tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) - dd[e]));
+                pp[e] = ex2(__uint_as_float(sr[c]) - ll[e]);
+                ss[e] = pp[e] * (__uint_as_float(tr[c]) - dd[e]);
               }
             } else {
               const uint4 wv = w4[cc];
@@ -801,30 +781,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
                 const int c = cc * 4 + e;
                 const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
                 const float dm = (ww[e] * cw >= dc.thr) ? dc.scale : 0.f;
-                sr[c] = __float_as_uint(p * dm);
-                tr[c] = __float_as_uint(p * (__uint_as_float(tr[c]) * dm - dd[e]));
+                pp[e] = p * dm;
+                ss[e] = p * (__uint_as_float(tr[c]) * dm - dd[e]);
               }
             }
+            pk[half * 16 + cc * 2] = pack_h2(pp[0], pp[1]); pk[half * 16 + cc * 2 + 1] = pack_h2(pp[2], pp[3]);
+            dk2[half * 16 + cc * 2] = pack_h2(ss[0], ss[1]); dk2[half * 16 + cc * 2 + 1] = pack_h2(ss[2], ss[3]);
           }
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            sr[c] = pack_h2(__uint_as_float(sr[2 * c]), __uint_as_float(sr[2 * c + 1]));
-            tr[c] = pack_h2(__uint_as_float(tr[2 * c]), __uint_as_float(tr[2 * c + 1]));
-          }
-          tmem_st16(tS + half * 16, sr); tmem_st16(tS + 64 + half * 16, tr);
         }
         prof[1] += clock64() - tc0;
+        if (j > 0) TPROF(5, ph.wait_out_free(bars));
+        tmem_st32(tOUT, pk); tmem_st32(tOUT + 32, dk2);
         TPROF(2, tmem_wait_st());
         fence_before();
-        mbar_arrive(&p_ready[wg]);
+        mbar_arrive(&bars[B_P]);
       }
-      TPROF(3, mbar_wait(&o_ready[wg], it & 1));
+      TPROF(3, mbar_wait(&bars[B_O], it & 1));
       fence_after();
       uint32_t o[32];
       tmem_ld32(tA, o); tmem_wait_ld();
       if (valid) {
         float dk[8], dv[8];
-#pragma unroll
         const float inv = 1.f / cs_scale;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {      // hi + lo parts; Q carried log2(e)
@@ -836,7 +813,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       }
       fence_before();
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { prof[4] = clock64() - tstart; for (int q = 0; q < 5; ++q) g_tc_prof[q] = prof[q]; }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { prof[4] = clock64() - tstart; for (int q = 0; q < 6; ++q) g_tc_prof[q] = prof[q]; }
   }
   fence_before();
   __syncthreads();

@@ -49,6 +49,7 @@ constexpr float kLazy = 8.f;        // rescale O only when the row max grows by 
 #define VAESNE_TC_SPLIT_T 1
 #endif
 constexpr bool kSplitT = VAESNE_TC_SPLIT_T != 0;   // dP = dO V^T with hi/lo-split operands (3 MMAs) or rounded operands (1 MMA)
+constexpr int RPT = (MAXL + NTHREADS - 1) / NTHREADS;   // staged rows per thread
 constexpr int TILE_F = MAXL * 8;    // floats of one staged operand array (32 KB)
 
 __device__ long long g_tc_prof[16];   // probe: per-phase clocks of CTA (0,0): warp 0 and the issuer
@@ -223,18 +224,30 @@ __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, i
   }
   const int nh = n * kH + h;
   if (dc.on) for (int c = tid; c < Lpad; c += NTHREADS) s.w0[c] = drop_col_word(dc, nh, c);
-  for (int j = tid; j < a.Lk; j += NTHREADS) {
-    const int c = key_slot(s, j);
+  // every thread owns up to RPT rows; all their global loads are issued before the first one is consumed
+  // (the prologue is latency-bound: one round trip instead of RPT)
+  float kk[RPT][8], vv[RPT][8];
+  int cc[RPT];
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    const int j = tid + u * NTHREADS;
+    cc[u] = j < a.Lk ? key_slot(s, j) : -1;
+    if (cc[u] >= 0) {
+      ld8g(kk[u], a.k + ((long long)n * a.Lk + j) * a.ldk + h * 8);
+      ld8g(vv[u], a.v + ((long long)n * a.Lk + j) * a.ldv + h * 8);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    const int c = cc[u];
     if (c < 0) continue;
-    float kk[8], vv[8], hi[8], lo[8];
-    ld8g(kk, a.k + ((long long)n * a.Lk + j) * a.ldk + h * 8);
-    ld8g(vv, a.v + ((long long)n * a.Lk + j) * a.ldv + h * 8);
-    split8(kk, hi, lo);
+    float hi[8], lo[8];
+    split8(kk[u], hi, lo);
     put_l1(Khi, c, hi); put_l1(Klo, c, lo);
-    if (K2h) put_l2h(K2h, c, kk);
-    split8(vv, hi, lo);
+    if (K2h) put_l2h(K2h, c, kk[u]);
+    split8(vv[u], hi, lo);
     if (V1hi) { put_l1(V1hi, c, hi); put_l1(V1lo, c, lo); }
-    if (V2h) put_l2h(V2h, c, vv);
+    if (V2h) put_l2h(V2h, c, vv[u]);
   }
 }
 
@@ -633,6 +646,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
+  const long long tk0 = clock64();
 
   init_pipeline(s, tid, warp);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
@@ -647,44 +661,53 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
     st8g(a.dv + ((long long)n * a.Lk + j) * a.lddv + h * 8, z);
   }
   // P^T and dS^T leave as fp16: dO of this (row, head) is scaled by ONE power of two that brings its largest entry into
-  // [1, 2) (dP, delta, dS, dK, dV are linear in it; entries 2^14 below the largest one lose relative accuracy only)
+  // [1, 2) (dP, delta, dS, dK, dV are linear in it; entries 2^14 below the largest one lose relative accuracy only).
+  // Query side: every thread owns up to RPT queries; all their loads are issued up front (one latency round trip),
+  // the block-wide max|dO| is reduced, then Q (scaled; L1 hi/lo + L2h), dO (L1 hi/lo + L2h), lse2, delta and the
+  // dropout row words are staged from registers.
+  const int NQ = (a.Lq + BK - 1) / BK;
   {
+    float q[RPT][8], g[RPT][8], lse2[RPT], delta[RPT];
     float gm = 0.f;
-    for (int i = tid; i < a.Lq; i += NTHREADS) {
-      float g[8];
-      ld8g(g, a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) gm = fmaxf(gm, fabsf(g[c]));
+    for (int u = 0; u < RPT; ++u) {
+      const int i = tid + u * NTHREADS;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { q[u][c] = 0.f; g[u][c] = 0.f; }
+      lse2[u] = INFINITY; delta[u] = 0.f;
+      if (i < a.Lq) {
+        ld8g(q[u], a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
+        ld8g(g[u], a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
+        lse2[u] = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
+        delta[u] = a.delta[(long long)nh * a.Lq + i];
+      }
     }
+#pragma unroll
+    for (int u = 0; u < RPT; ++u)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) gm = fmaxf(gm, fabsf(g[u][c]));
     gm = isfinite(gm) ? gm : 0.f;
     if (tid == 0) s.pre[33] = 0u;
     __syncthreads();
     atomicMax(&s.pre[33], __float_as_uint(gm));      // non-negative floats order like their bit patterns
     __syncthreads();
+    const float sc = pow2_normaliser(__uint_as_float(s.pre[33]));
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+      const int i = tid + u * NTHREADS;
+      if (i >= NQ * BK) continue;
+      float hi[8], lo[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { q[u][c] *= kQScale; g[u][c] *= sc; }
+      split8(q[u], hi, lo);
+      put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l2h(Q2h, i, q[u]);
+      split8(g[u], hi, lo);
+      put_l1(G1, i, hi); put_l1(G1lo, i, lo); put_l2h(G2h, i, g[u]);
+      s.f0[i] = lse2[u]; s.f1[i] = delta[u] * sc;
+      s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
+    }
   }
   const float cs_scale = pow2_normaliser(__uint_as_float(s.pre[33]));
-  // stage the query side: Q (scaled; L1 hi/lo + L2h), dO (L1 hi/lo + L2h), lse2, delta, dropout row words
-  const int NQ = (a.Lq + BK - 1) / BK;
-  for (int i = tid; i < NQ * BK; i += NTHREADS) {
-    float q[8], g[8], hi[8], lo[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) { q[c] = 0.f; g[c] = 0.f; }
-    float lse2 = INFINITY, delta = 0.f;
-    if (i < a.Lq) {
-      ld8g(q, a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
-      ld8g(g, a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { q[c] *= kQScale; g[c] *= cs_scale; }
-      lse2 = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
-      delta = a.delta[(long long)nh * a.Lq + i] * cs_scale;
-    }
-    split8(q, hi, lo);
-    put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l2h(Q2h, i, q);
-    split8(g, hi, lo);
-    put_l1(G1, i, hi); put_l1(G1lo, i, lo); put_l2h(G2h, i, g);
-    s.f0[i] = lse2; s.f1[i] = delta;
-    s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
-  }
   fence_async_smem();
   fence_before();
   __syncthreads();
@@ -725,7 +748,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
     uint64_t* bars = s.bars + wg * B_PER_WG;
     const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * C_WG);
     const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
-    long long prof[16] = {0}; const long long tstart = clock64();
+    long long prof[16] = {0}; const long long tstart = clock64(); prof[6] = tstart - tk0;
     WgPhase ph = {0, 0};
     int it = 0;
     for (int kt = wg; kt < nKT; kt += 2, ++it) {
@@ -813,7 +836,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       }
       fence_before();
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { prof[4] = clock64() - tstart; for (int q = 0; q < 6; ++q) g_tc_prof[q] = prof[q]; }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { prof[4] = clock64() - tstart; for (int q = 0; q < 7; ++q) g_tc_prof[q] = prof[q]; }
   }
   fence_before();
   __syncthreads();

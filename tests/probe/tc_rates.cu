@@ -79,6 +79,27 @@ __global__ void __launch_bounds__(NT, 1) rates(long long* out, float* sink, int 
     }
     sync(); t1 = clock64(); rec(t1 - t0);
   }
+  // cvt.rn.f16x2.f32 (F2FP) throughput, 8 warps: 64 packs per rep per thread
+  {
+    sync(); t0 = clock64();
+    if (warp < 8) {
+      float x[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) x[c] = 0.001f * (float)(c + lane);
+      uint32_t accu = 0;
+      for (int r = 0; r < reps; ++r) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            uint32_t h; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x[c + 1]), "f"(x[c]));
+            accu ^= h; x[c] += 1.0f;
+          }
+      }
+      acc += (float)accu;
+    }
+    sync(); t1 = clock64(); rec(t1 - t0);
+  }
   // 6..: MMA issue + completion. one thread issues `reps` MMAs then commits; records issue-only and total clocks
   const uint64_t dA = smem_desc(smem_u32(tiles), 128, 256), dB = smem_desc(smem_u32(tiles) + 8192, 128, 256);
   const int shapes[5] = {128, 64, 32, 16, 8};
@@ -170,6 +191,7 @@ int main() {
   for (int nw = 8; nw >= 4; nw -= 4, ++i) printf("tcgen05.ld %d warps: %lld clk  -> %.1f B/clk/SM\n", nw, h[i], (double)reps * nw * 32 * 128 * 4 / h[i]);
   for (int nw = 8; nw >= 4; nw -= 4, ++i) printf("tcgen05.st %d warps: %lld clk  -> %.1f B/clk/SM\n", nw, h[i], (double)reps * nw * 32 * 128 * 4 / h[i]);
   for (int nw = 8; nw >= 4; nw -= 4, ++i) printf("ex2+fadd   %d warps: %lld clk  -> %.2f ex2/clk/SM\n", nw, h[i], (double)reps * nw * 32 * 128 / h[i]);
+  printf("cvt.rn.f16x2.f32 (+xor+fadd) 8 warps: %lld clk -> %.2f packs/clk/SM\n", h[i], (double)reps * 8 * 32 * 64 / h[i]); ++i;
   const int shapes[5] = {128, 64, 32, 16, 8};
   for (int ts = 0; ts < 2; ++ts) for (int si = 0; si < 4; ++si, i += 2)
     printf("mma.%s M128 N%-3d K8 x%d: issue %.1f clk/mma, issue+complete %.1f clk/mma\n", ts ? "ts" : "ss", shapes[si], reps, (double)h[i] / reps, (double)h[i + 1] / reps);

@@ -73,6 +73,14 @@ __device__ __forceinline__ uint32_t drop_col_word(const TcDrop& d, int nh, int c
   return hash_ctr(d.s1, d.s0, d.stream ^ 0x5bd1e995u, ((uint64_t)nh << 32) | (uint64_t)c);
 }
 
+// packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2): two lanes per issue slot — the exponentiation loops are bound by
+// instruction issue next to the 16/clk MUFU, not by FP32 throughput
+typedef uint64_t f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rn_tf32(float x) { uint32_t h; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x)); return __uint_as_float(h); }
 __device__ __forceinline__ bool elect_one() {
@@ -560,7 +568,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
       for (int c = 0; c < 8; ++c) gmax = fmaxf(gmax, fabsf(g[c]));
       const float rs = pow2_normaliser(gmax);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) g[c] *= rs;
+      for (int c = 0; c < 8; ++c) g[c] *= rs * dc.scale;      // dropout scale folded in: dP = (dO * scale) . V
       delta *= rs;
       split8(q, hi, lo);
       tmem_put8(tX, hi); tmem_put8(tX + 8, lo);
@@ -581,26 +589,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
           tmem_wait_ld();
           if (half == 1 && j + 1 < T) signal_in_free(bars);       // the next tile's first product runs under this one's exponentials
           float ds[32];
-          if (!dc.on) {
+          const f32x2 nl = pk2(-lse2, -lse2), nd = pk2(-delta, -delta);
+          const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float p = ex2(__uint_as_float(sr[c]) - lse2);
-              ds[c] = p * (__uint_as_float(tr[c]) - delta);
-            }
-          } else {
-            const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
+          for (int cc = 0; cc < 8; ++cc) {
+            const int c = cc * 4;
+            float x0, x1, x2, x3;
+            upk2(add2(pk2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), nl), x0, x1);
+            upk2(add2(pk2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])), nl), x2, x3);
+            const f32x2 pa = pk2(ex2(x0), ex2(x1)), pb = pk2(ex2(x2), ex2(x3));
+            float t0 = __uint_as_float(tr[c]), t1 = __uint_as_float(tr[c + 1]), t2 = __uint_as_float(tr[c + 2]), t3 = __uint_as_float(tr[c + 3]);
+            if (dc.on) {        // the dropout scale is folded into the dO row operand: dP arrives scaled
               const uint4 bq = bw[cc];
-              const uint32_t bb[4] = {bq.x, bq.y, bq.z, bq.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = cc * 4 + e;
-                const float p = ex2(__uint_as_float(sr[c]) - lse2);
-                const float dp = (rw * bb[e] >= dc.thr) ? __uint_as_float(tr[c]) * dc.scale : 0.f;
-                ds[c] = p * (dp - delta);
-              }
+              t0 = (rw * bq.x >= dc.thr) ? t0 : 0.f; t1 = (rw * bq.y >= dc.thr) ? t1 : 0.f;
+              t2 = (rw * bq.z >= dc.thr) ? t2 : 0.f; t3 = (rw * bq.w >= dc.thr) ? t3 : 0.f;
             }
+            upk2(mul2(pa, add2(pk2(t0, t1), nd)), ds[c], ds[c + 1]);
+            upk2(mul2(pb, add2(pk2(t2, t3), nd)), ds[c + 2], ds[c + 3]);
           }
           if (nvalid < BK) {      // padded key slots: exactly zero (2^(-lse) may overflow and inf * 0 would poison the row)
 #pragma unroll
@@ -703,7 +708,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l2h(Q2h, i, q[u]);
       split8(g[u], hi, lo);
       put_l1(G1, i, hi); put_l1(G1lo, i, lo); put_l2h(G2h, i, g[u]);
-      s.f0[i] = lse2[u]; s.f1[i] = delta[u] * sc;
+      s.f0[i] = -lse2[u]; s.f1[i] = -delta[u] * sc;          // negated: the loop adds
       s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
     }
   }
@@ -786,27 +791,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
           if (!(g_tc_dbg & 2))
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
-            const float4 lv = l4[cc], dv = d4[cc];
-            const float ll[4] = {lv.x, lv.y, lv.z, lv.w}, dd[4] = {dv.x, dv.y, dv.z, dv.w};
+            const float4 lv = l4[cc], dv = d4[cc];          // -lse2, -delta of 4 queries
             float pp[4], ss[4];
+            const int c = cc * 4;
+            // x = s - lse2 (2 lanes per FADD2), p = 2^x
+            float x0, x1, x2, x3;
+            upk2(add2(pk2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), pk2(lv.x, lv.y)), x0, x1);
+            upk2(add2(pk2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])), pk2(lv.z, lv.w)), x2, x3);
+            const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);
+            const f32x2 pa = pk2(p0, p1), pb = pk2(p2, p3);
+            const f32x2 ta = pk2(__uint_as_float(tr[c]), __uint_as_float(tr[c + 1])), tb2 = pk2(__uint_as_float(tr[c + 2]), __uint_as_float(tr[c + 3]));
             if (!dc.on) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = cc * 4 + e;
-                pp[e] = ex2(__uint_as_float(sr[c]) - ll[e]);
-                ss[e] = pp[e] * (__uint_as_float(tr[c]) - dd[e]);
-              }
+              pp[0] = p0; pp[1] = p1; pp[2] = p2; pp[3] = p3;
+              upk2(mul2(pa, add2(ta, pk2(dv.x, dv.y))), ss[0], ss[1]);
+              upk2(mul2(pb, add2(tb2, pk2(dv.z, dv.w))), ss[2], ss[3]);
             } else {
               const uint4 wv = w4[cc];
-              const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int c = cc * 4 + e;
-                const float p = ex2(__uint_as_float(sr[c]) - ll[e]);
-                const float dm = (ww[e] * cw >= dc.thr) ? dc.scale : 0.f;
-                pp[e] = p * dm;
-                ss[e] = p * (__uint_as_float(tr[c]) * dm - dd[e]);
-              }
+              const float m0 = (wv.x * cw >= dc.thr) ? dc.scale : 0.f, m1 = (wv.y * cw >= dc.thr) ? dc.scale : 0.f;
+              const float m2 = (wv.z * cw >= dc.thr) ? dc.scale : 0.f, m3 = (wv.w * cw >= dc.thr) ? dc.scale : 0.f;
+              const f32x2 ma = pk2(m0, m1), mb = pk2(m2, m3);
+              upk2(mul2(pa, ma), pp[0], pp[1]);
+              upk2(mul2(pb, mb), pp[2], pp[3]);
+              upk2(mul2(pa, fma2(ta, ma, pk2(dv.x, dv.y))), ss[0], ss[1]);
+              upk2(mul2(pb, fma2(tb2, mb, pk2(dv.z, dv.w))), ss[2], ss[3]);
             }
             pk[half * 16 + cc * 2] = pack_h2(pp[0], pp[1]); pk[half * 16 + cc * 2 + 1] = pack_h2(pp[2], pp[3]);
             dk2[half * 16 + cc * 2] = pack_h2(ss[0], ss[1]); dk2[half * 16 + cc * 2 + 1] = pack_h2(ss[2], ss[3]);

@@ -396,6 +396,11 @@ __global__ void __launch_bounds__(LT, 2) lin_tc_bwd_kernel(LinBwd a) {
         // X row -> X^T hi / lo.  XT_lo aliases the X tile: every thread must have read its row first.
         float x[32];
         lds_row(x, my2);
+        if (a.Xadd && active) {               // rare (the MLP heads): the second addend comes straight from global memory
+          const float4* xa = reinterpret_cast<const float4*>(a.Xadd + t * a.ldxa);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float4 v4 = xa[j]; x[4 * j] += v4.x; x[4 * j + 1] += v4.y; x[4 * j + 2] += v4.z; x[4 * j + 3] += v4.w; }
+        }
         __syncthreads();                      // also: every thread has read its B1 row (dZT_lo aliases B1)
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -501,11 +506,11 @@ bool lin_tc_fwd_eligible(const LinFwd& a) {
   return al16(a.X, a.ldx) && al16(a.Xadd, a.ldxa) && al16(a.H, a.ldh) && al16(a.R, a.ldr) && al16(a.S, 32) && al16(a.Y, a.ldy);
 }
 bool lin_tc_bwd_eligible(const LinBwd& a) {
-  if (tc_off() || a.K != 32 || !(a.N == 32 || a.N == 64 || a.N == 96) || a.Xadd) return false;
+  if (tc_off() || a.K != 32 || !(a.N == 32 || a.N == 64 || a.N == 96)) return false;
   if (a.S && (a.N != 32 || a.act != 0)) return false;
   if (a.N != 32 && a.act != 0) return false;
   if (!a.dX && !a.dW) return false;
-  return al16(a.dY, a.lddy) && al16(a.S, 32) && al16(a.dR, a.lddr) && al16(a.A, a.lda) && al16(a.X, a.ldx) && al16(a.dX, a.lddx);
+  return al16(a.dY, a.lddy) && al16(a.S, 32) && al16(a.dR, a.lddr) && al16(a.A, a.lda) && al16(a.X, a.ldx) && al16(a.Xadd, a.ldxa) && al16(a.dX, a.lddx);
 }
 
 // Persistent grid: exactly as many CTAs as can be co-resident (a partial second wave would double the run time),

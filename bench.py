@@ -317,7 +317,8 @@ def main():
             ex2_floor_ms = elems * (1 if name == "attn_fwd" else 2) / ex2_rate * 1e3
             roof = {"kernel": f"{name}[N={Nb},Lq={Lq},Lk={Lk}] (attn_tc_* kernels: tcgen05 kind::tf32 + kind::f16)", "bound": "tensor",
                     "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tf_sust"], "traffic": traffic_tab.get("|".join(map(str, key))),
+                    "frac": ach / pk["tf_sust"],
+                    "traffic": (lambda t: None if t is None else int(t * Nb))(traffic_tab.get("per_row", {}).get(f"{name}|{Lq}|{Lk}")),
                     "peak_source": pk["src"] + " bf16 sustained (kernel timed inside the step)",
                     "share_of_step": top["total_ms"] / tot, "avg_ms": top["avg_ms"],
                     "binding_unit": {"name": "MUFU.EX2 (32 tensor FLOP per exponential at head_dim 8)", "floor_ms": ex2_floor_ms,

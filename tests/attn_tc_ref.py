@@ -70,3 +70,16 @@ def attn_reference_drop(q, k, v, mask_full, dO, keep, drop_scale):
     o = (p @ vh).transpose(1, 2).reshape(N, Lq, 32)
     o.backward(dO.double())
     return o.detach(), lse.detach(), q.grad, k.grad, v.grad
+
+
+def keep_mask_general(seed, stream, p, N, H, Lq, Lk):
+    """Dropout mask of the general / few-key kernels (csrc/common.cuh drop_mult; csrc/attn.cu, attn_small.cu):
+    element index ((n*H + h)*Lq + i)*Lk + j, one 32-bit hash per two consecutive elements, 16-bit thresholds."""
+    s0, s1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    t = float(np.float32(p)) * 65536.0 + 0.5
+    thresh = 65535 if t > 65535.0 else int(t)
+    scale = float(np.float32(1.0 / (1.0 - np.float32(thresh) * np.float32(1.0 / 65536.0))))
+    idx = np.arange(N * H * Lq * Lk, dtype=np.uint64)
+    r = hash_ctr(s0, s1, stream, idx >> np.uint64(1))
+    r16 = np.where((idx & np.uint64(1)) == 1, r >> np.uint64(16), r & np.uint64(0xFFFF))
+    return (r16 >= np.uint64(thresh)).reshape(N, H, Lq, Lk), scale

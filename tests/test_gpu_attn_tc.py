@@ -73,3 +73,25 @@ def test_tc_masked_keys_get_exact_zero_gradients():
     mf = mask_full.to("cuda")
     assert torch.equal(dk[mf], torch.zeros_like(dk[mf])) and torch.equal(dv[mf], torch.zeros_like(dv[mf]))
     assert torch.isfinite(dq).all() and torch.isfinite(dk).all() and torch.isfinite(dv).all()
+
+
+@pytest.mark.parametrize("case", [c for c in OC.ATTN_CASES_FULL if c["id"] in ("cross_982x5", "cross_60x4", "self_60x60_mask_rowmod")], ids=lambda c: c["id"])
+def test_general_and_few_key_kernels_dropout_mask_is_the_restated_one(case):
+    """attn.cu / attn_small.cu: the counter-hash dropout mask restated in numpy, forward and backward."""
+    from VAESNe import _ops as P
+    dev = "cuda"
+    (q, k, v, mask, mask_full, dO), (qd, kd, vd) = OC.make_attn_inputs(case, dev)
+    seed_val, sid, p = 0x0BADC0DE12345678, 41, 0.1
+    seed = torch.tensor([seed_val], dtype=torch.int64, device=dev)
+    drop = P.Drop(p, seed, sid)
+    N, Lq, Lk = case["N"], case["Lq"], case["Lk"]
+    keep, dscale = R.keep_mask_general(seed_val, sid, p, N, 4, Lq, Lk)
+    o_ref, lse_ref, dq_ref, dk_ref, dv_ref = R.attn_reference_drop(q, k, v, mask_full, dO, torch.from_numpy(keep), dscale)
+    md = mask.to(dev) if mask is not None else None
+    O, LSE = P.attn_fwd(qd, kd, vd, md, drop)
+    assert rel_err(O.cpu(), o_ref) < OC.TOL, ("O", rel_err(O.cpu(), o_ref))
+    assert rel_err(LSE.cpu(), lse_ref) < OC.TOL
+    dq, dk, dv = _grads(case, dev)
+    P.attn_bwd(qd, kd, vd, md, O, LSE, dO.to(dev), dq, dk, dv, drop)
+    for name, got, ref in (("dq", dq, dq_ref), ("dk", dk, dk_ref), ("dv", dv, dv_ref)):
+        assert rel_err(got.cpu(), ref) < OC.TOL, (name, rel_err(got.cpu(), ref))

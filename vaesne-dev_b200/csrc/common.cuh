@@ -77,6 +77,15 @@ __device__ __forceinline__ float drop_mult(const DropCfg& d, uint64_t idx) {
   return r16 < d.thresh ? 0.f : d.scale;
 }
 
+// Row-wise variant for the 32 features of one token (LayerNorm-input dropout): one counter hash per token, then one
+// mix32 per feature pair — 4x fewer integer instructions than drop_mult per element.
+__device__ __forceinline__ uint32_t drop_row_hash(const DropCfg& d, uint64_t row) { return hash_ctr(d.s0, d.s1, d.stream, row); }
+__device__ __forceinline__ float drop_mult_row(const DropCfg& d, uint32_t rh, int j) {
+  const uint32_t r = mix32(rh + (uint32_t)(j >> 1) * 0x9E3779B1U);
+  const uint32_t r16 = (j & 1) ? (r >> 16) : (r & 0xffffu);
+  return r16 < d.thresh ? 0.f : d.scale;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));

@@ -103,10 +103,11 @@ __global__ void __launch_bounds__(TT) lin_fwd_kernel(LinFwd a) {
           float s[NC];
           ld_row<NC>(s, a.R + t * a.ldr, vec);
           float mean = 0.f;
+          const uint32_t rh = dc.on ? drop_row_hash(dc, (uint64_t)t) : 0u;
 #pragma unroll
           for (int j = 0; j < NC; ++j) {
             float v = acc[j];
-            if (dc.on) v *= drop_mult(dc, (uint64_t)t * 32 + j);
+            if (dc.on) v *= drop_mult_row(dc, rh, j);
             s[j] += v;
             mean += s[j];
           }
@@ -236,8 +237,9 @@ __global__ void __launch_bounds__(TT) lin_bwd_kernel(LinBwd a) {
           }
         }
         if (dc.on) {
+          const uint32_t rh = drop_row_hash(dc, (uint64_t)t);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dz[j] *= drop_mult(dc, (uint64_t)t * 32 + j);
+          for (int j = 0; j < 32; ++j) dz[j] *= drop_mult_row(dc, rh, j);
         }
       }
       __syncthreads();

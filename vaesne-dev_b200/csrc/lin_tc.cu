@@ -199,10 +199,11 @@ __global__ void __launch_bounds__(LT, 3) lin_tc_fwd_kernel(LinFwd a) {
       float s[32];
       lds_row(s, myR);
       float mean = 0.f;
+      const uint32_t rh = dc.on ? drop_row_hash(dc, (uint64_t)t) : 0u;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float v = __uint_as_float(d[j]) + sB[j];
-        if (dc.on) v *= drop_mult(dc, (uint64_t)t * 32 + j);
+        if (dc.on) v *= drop_mult_row(dc, rh, j);
         s[j] += v;
         mean += s[j];
       }
@@ -306,6 +307,9 @@ __global__ void __launch_bounds__(LT, 2) lin_tc_bwd_kernel(LinBwd a) {
   uint32_t ph = 0;
   bool pending = false;          // an MMA batch has been committed and not yet waited for
   bool first_tile = true;
+  float accg[LN ? 32 : 1], accb[LN ? 32 : 1];
+#pragma unroll
+  for (int j = 0; j < (LN ? 32 : 1); ++j) { accg[j] = 0.f; accb[j] = 0.f; }
 
   const int ntiles = (a.T + LT - 1) / LT;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -349,26 +353,17 @@ __global__ void __launch_bounds__(LT, 2) lin_tc_bwd_kernel(LinBwd a) {
           m1 += g[j]; m2 = fmaf(g[j], s[j], m2);
         }
         m1 *= (1.f / 32); m2 *= (1.f / 32);
-        if (a.dgamma) {
-          float r1[32];
+        if (active) {        // dgamma / dbeta: accumulated per thread over all tiles of the CTA, reduced once at the end
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r1[j] = active ? dz[j] * s[j] : 0.f;
-          const float cs = warp_colsum32(r1, lane);
-          atomicAdd(&sDg[lane], cs);
-        }
-        if (a.dbeta) {
-          float r2[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r2[j] = active ? dz[j] : 0.f;
-          const float cs = warp_colsum32(r2, lane);
-          atomicAdd(&sDbe[lane], cs);
+          for (int j = 0; j < 32; ++j) { accg[j] = fmaf(dz[j], s[j], accg[j]); accb[j] += dz[j]; }
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) dz[j] = rstd * (g[j] - m1 - s[j] * m2);     // dS = dR
         if (a.dR) sts_row(my0, dz);           // own row of B0: already consumed by this thread
         if (dc.on) {
+          const uint32_t rh = drop_row_hash(dc, (uint64_t)t);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dz[j] *= drop_mult(dc, (uint64_t)t * 32 + j);
+          for (int j = 0; j < 32; ++j) dz[j] *= drop_mult_row(dc, rh, j);
         }
       } else if (a.act != 0) {
         float av[32];
@@ -484,6 +479,10 @@ __global__ void __launch_bounds__(LT, 2) lin_tc_bwd_kernel(LinBwd a) {
       for (int k = 0; k < 32; ++k)
         atomicAdd(&a.dW[(c * 32 + lane) * 32 + k], __uint_as_float(d[k]) + (warp == 0 ? __uint_as_float(e[k]) : 0.f));
     }
+  }
+  if (LN) {
+    const float cg = warp_colsum32(accg, lane), cb = warp_colsum32(accb, lane);
+    atomicAdd(&sDg[lane], cg); atomicAdd(&sDbe[lane], cb);
   }
   __syncthreads();
   if (wgrad && a.db && tid < N) atomicAdd(&a.db[tid], sDb[tid]);

@@ -26,6 +26,7 @@
 #include "tc_common.cuh"
 #include <stdlib.h>
 #include <stdio.h>
+#include <cuda.h>          // CUtensorMap (the encoder itself is fetched through the runtime: no libcuda link)
 
 namespace vaesne {
 using namespace tc;
@@ -33,6 +34,7 @@ using namespace tc;
 constexpr int LT = 128;              // tokens per tile == threads per CTA == TMEM lanes
 constexpr int PITCH = 36;            // floats per padded shared-memory row (144 B)
 constexpr int TILE = LT * PITCH;     // floats per staged tile (18 KB)
+constexpr int TSW = LT * 32;         // floats per 128-byte-swizzled tile (16 KB, TMA destination)
 
 __device__ __forceinline__ bool lelect_one() {
   uint32_t pred;
@@ -64,6 +66,38 @@ __device__ __forceinline__ void store_tile(float* dst, long long ld, const float
       if (ACC) { const float4 o = *g; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
       *g = v;
     }
+  }
+}
+// TMA: one 128-token x 32-float tile (16 KB) per bulk tensor copy, 128-byte swizzle: the 16-byte chunk c of row r lands at
+// chunk position c ^ (r & 7), which makes the row-per-thread 16-byte reads below conflict-free without padding.
+__device__ __forceinline__ void tma_load_tile(float* dst, const CUtensorMap* tm, int row0, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(smem_u32(dst)), "l"(tm), "r"(0), "r"(row0), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void lds_row_sw(float* v, const float* tile, int r) {
+  const float* row = tile + r * 32;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(row + ((j ^ (r & 7)) << 2));
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void sts_row_sw(float* tile, int r, const float* v) {
+  float* row = tile + r * 32;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(row + ((j ^ (r & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+// swizzled [128][32] staging tile -> global rows (coalesced: 8 lanes per 128-byte row)
+__device__ __forceinline__ void store_tile_sw(float* dst, long long ld, const float* src, long long t0, int rows, int tid) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int id = it * LT + tid, r = id >> 3, c = id & 7;
+    if (r < rows)
+      *reinterpret_cast<float4*>(dst + (t0 + r) * ld + c * 4) = *reinterpret_cast<const float4*>(src + r * 32 + ((c ^ (r & 7)) << 2));
   }
 }
 __device__ __forceinline__ void lds_row(float* v, const float* row) {
@@ -111,22 +145,25 @@ __device__ __forceinline__ int tcanon(int row, int t) { return (row >> 3) * 1152
 // forward
 // =================================================================================================
 template <int NCH>
-__host__ __device__ constexpr size_t lin_tc_fwd_smem() { return 128 + sizeof(float) * (2 * NCH * 1024 + 96 + 64 + 2 * TILE) + 32; }
+__host__ __device__ constexpr size_t lin_tc_fwd_smem() { return 128 + sizeof(float) * (2 * NCH * 1024 + 96 + 64 + 4 * TSW) + 64; }
 
 template <int NCH, bool LN>
-__global__ void __launch_bounds__(LT, 3) lin_tc_fwd_kernel(LinFwd a) {
+__global__ void __launch_bounds__(LT, 3) lin_tc_fwd_kernel(LinFwd a, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR) {
   constexpr int N = NCH * 32;
   constexpr int COLS = (64 + N) <= 128 ? 128 : 256;
   extern __shared__ __align__(1024) unsigned char lin_tc_raw[];      // plain pointer arithmetic from here on: keeps LDS/STS
-  float* Whi = reinterpret_cast<float*>(lin_tc_raw);
+  // two input sets {X tile, R | Xadd tile} (TMA destinations, 128-byte-swizzled [128][32] = 16 KB each); the set of the
+  // tile being processed doubles as output staging (same swizzle) once its rows are in registers, while the TMA unit
+  // fills the other set with the next tile
+  float* IN = reinterpret_cast<float*>(lin_tc_raw);
+  float* Whi = IN + 4 * TSW;
   float* Wlo = Whi + NCH * 1024;
   float* sB = Wlo + NCH * 1024;      // [96]
   float* sG = sB + 96;               // [32]
   float* sBe = sG + 32;              // [32]
-  float* bufX = sBe + 32;            // X tile, later output staging
-  float* bufR = bufX + TILE;         // R (LN) or Xadd tile, later output staging
-  uint64_t* bar = reinterpret_cast<uint64_t*>(bufR + TILE);
-  uint32_t* tmem_s = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sBe + 32);
+  uint64_t* tbar = bar + 1;          // [2] TMA transaction barriers, one per input set
+  uint32_t* tmem_s = reinterpret_cast<uint32_t*>(tbar + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
 
   for (int i = tid; i < N * 32; i += LT) {
@@ -137,7 +174,7 @@ __global__ void __launch_bounds__(LT, 3) lin_tc_fwd_kernel(LinFwd a) {
   }
   for (int i = tid; i < N; i += LT) sB[i] = a.b ? a.b[i] : 0.f;
   if (LN && tid < 32) { sG[tid] = a.gamma[tid]; sBe[tid] = a.beta[tid]; }
-  if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(&tbar[0], 1); mbar_init(&tbar[1], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   if (warp == 0) tmem_alloc<COLS>(tmem_s);
   fence_async_smem();
   fence_before();
@@ -145,28 +182,37 @@ __global__ void __launch_bounds__(LT, 3) lin_tc_fwd_kernel(LinFwd a) {
   fence_after();
   const uint32_t tb = *tmem_s;
   const uint32_t tl = tb + ((uint32_t)(warp * 32) << 16);      // this thread's lane
+  const bool second = LN || (a.Xadd != nullptr);
+  auto tma_issue = [&](int tile, int set) {      // one thread; rows beyond T are zero-filled by the TMA unit
+    mbar_expect_tx(&tbar[set], second ? 2u * LT * 128u : LT * 128u);
+    tma_load_tile(IN + set * 2 * TSW, &tmX, tile * LT, &tbar[set]);
+    if (second) tma_load_tile(IN + set * 2 * TSW + TSW, &tmR, tile * LT, &tbar[set]);
+  };
   const uint32_t idesc = idesc_tf32(128, N);
   const uint32_t aWhi = smem_u32(Whi), aWlo = smem_u32(Wlo);
   const DropCfg dc = make_drop(LN ? a.p_drop : 0.f, a.seed, a.stream_id);
-  float* myX = bufX + tid * PITCH; float* myR = bufR + tid * PITCH;
   uint32_t ph = 0;
 
   const int ntiles = (a.T + LT - 1) / LT;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  if (tid == 0 && (int)blockIdx.x < ntiles) tma_issue(blockIdx.x, 0);
+  int kiter = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++kiter) {
+    const int set = kiter & 1;
+    float* bufX = IN + set * 2 * TSW; float* bufR = bufX + TSW;
     const long long t0 = (long long)tile * LT;
     const int rows = min(LT, a.T - (int)t0);
     const long long t = t0 + tid;
-    load_tile(bufX, a.X, a.ldx, t0, rows, tid);
-    if (LN) load_tile(bufR, a.R, a.ldr, t0, rows, tid);
-    else if (a.Xadd) load_tile(bufR, a.Xadd, a.ldxa, t0, rows, tid);
-    cp_async_wait_all();
-    __syncthreads();
+    // the other set was released by the barrier that ended the previous iteration: prefetch the next tile into it
+    if (tid == 0 && tile + (int)gridDim.x < ntiles) tma_issue(tile + gridDim.x, set ^ 1);
+    mbar_wait(&tbar[set], (uint32_t)((kiter >> 1) & 1));
+    float res[LN ? 32 : 1];          // the residual row is read now, before the tiles turn into staging buffers
+    if (LN) lds_row_sw(res, bufR, tid);
     {
       float x[32], hi[32], lo[32];
-      lds_row(x, myX);
+      lds_row_sw(x, bufX, tid);
       if (!LN && a.Xadd) {
         float xa[32];
-        lds_row(xa, myR);
+        lds_row_sw(xa, bufR, tid);
 #pragma unroll
         for (int j = 0; j < 32; ++j) x[j] += xa[j];
       }
@@ -197,7 +243,8 @@ __global__ void __launch_bounds__(LT, 3) lin_tc_fwd_kernel(LinFwd a) {
       uint32_t d[32];
       tmem_ld32(tl + 64, d); tmem_wait_ld();
       float s[32];
-      lds_row(s, myR);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s[j] = res[LN ? j : 0];
       float mean = 0.f;
       const uint32_t rh = dc.on ? drop_row_hash(dc, (uint64_t)t) : 0u;
 #pragma unroll
@@ -212,13 +259,13 @@ __global__ void __launch_bounds__(LT, 3) lin_tc_fwd_kernel(LinFwd a) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) { const float dd = s[j] - mean; var = fmaf(dd, dd, var); }
       const float rstd = 1.f / sqrtf(var * (1.f / 32) + a.eps);
-      if (a.S) sts_row(myX, s);
+      if (a.S) sts_row_sw(bufX, tid, s);
 #pragma unroll
       for (int j = 0; j < 32; ++j) s[j] = (s[j] - mean) * rstd * sG[j] + sBe[j];
-      sts_row(myR, s);
+      sts_row_sw(bufR, tid, s);
       __syncthreads();
-      if (a.S) store_tile<false>(a.S, 32, bufX, t0, rows, tid);
-      store_tile<false>(a.Y, a.ldy, bufR, t0, rows, tid);
+      if (a.S) store_tile_sw(a.S, 32, bufX, t0, rows, tid);
+      store_tile_sw(a.Y, a.ldy, bufR, t0, rows, tid);
     } else {
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
@@ -228,7 +275,7 @@ __global__ void __launch_bounds__(LT, 3) lin_tc_fwd_kernel(LinFwd a) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(d[j]) + sB[c * 32 + j];
         if (c > 0) __syncthreads();                 // previous chunk's coalesced stores have read the staging tiles
-        if (a.H) sts_row(myR, v);
+        if (a.H) sts_row_sw(bufR, tid, v);
         if (a.act == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -236,12 +283,13 @@ __global__ void __launch_bounds__(LT, 3) lin_tc_fwd_kernel(LinFwd a) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
         }
-        sts_row(myX, v);
+        sts_row_sw(bufX, tid, v);
         __syncthreads();
-        if (a.H) store_tile<false>(a.H + c * 32, a.ldh, bufR, t0, rows, tid);
-        store_tile<false>(a.Y + c * 32, a.ldy, bufX, t0, rows, tid);
+        if (a.H) store_tile_sw(a.H + c * 32, a.ldh, bufR, t0, rows, tid);
+        store_tile_sw(a.Y + c * 32, a.ldy, bufX, t0, rows, tid);
       }
     }
+    fence_async_smem();     // generic-proxy accesses of the staging tiles are ordered before the next TMA (async proxy) write
     fence_before();
     __syncthreads();        // staging tiles are free again; D has been read by every thread
     fence_after();
@@ -557,12 +605,53 @@ static int tc_launch(K k, size_t smem, int tmem_ctas, cudaStream_t st, const cha
   return check_launch(what);
 }
 
+// ---- TMA descriptors: [T, 32] fp32 view with row stride ld, 128-row boxes, 128-byte swizzle, zero fill out of bounds ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tma_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+static int make_tile_map(CUtensorMap* tm, const float* base, long long ld, int T, const char* what) {
+  EncodeTiledFn enc = tma_encoder();
+  if (!enc) { set_error("%s: cuTensorMapEncodeTiled is not available from this driver", what); return V_ECUDA; }
+  const cuuint64_t dims[2] = {32, (cuuint64_t)T};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)LT}, estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled failed (%d) for base %p ld %lld T %d", what, (int)r, (const void*)base, ld, T); return V_ECUDA; }
+  return V_OK;
+}
+
+template <typename K>
+static int lin_tc_fwd_launch(K k, size_t smem, int tmem_ctas, cudaStream_t st, const char* what, const LinFwd& a) {
+  TcKernelInfo ki;
+  int rc = tc_prepare(k, smem, what, ki); if (rc) return rc;
+  CUtensorMap tmX, tmR;
+  rc = make_tile_map(&tmX, a.X, a.ldx, a.T, what); if (rc) return rc;
+  const float* second = a.R ? a.R : a.Xadd;
+  rc = make_tile_map(&tmR, second ? second : a.X, second ? (a.R ? a.ldr : a.ldxa) : a.ldx, a.T, what); if (rc) return rc;
+  const int per_sm = ki.ctas_per_sm < tmem_ctas ? ki.ctas_per_sm : tmem_ctas;      // TMEM: 512 columns per SM
+  const int ntiles = (a.T + LT - 1) / LT;
+  const int cap = ki.sms * per_sm;
+  k<<<ntiles < cap ? ntiles : cap, LT, smem, st>>>(a, tmX, tmR);
+  return check_launch(what);
+}
+
 int lin_tc_fwd(const LinFwd& a, cudaStream_t st) {
   const int g = a.N <= 64 ? 4 : 2;     // TMEM: 128 columns per CTA up to N = 64, else 256
-  if (a.R) return tc_launch(lin_tc_fwd_kernel<1, true>, lin_tc_fwd_smem<1>(), g, st, "lin_tc_fwd_ln", a);
-  if (a.N == 32) return tc_launch(lin_tc_fwd_kernel<1, false>, lin_tc_fwd_smem<1>(), g, st, "lin_tc_fwd", a);
-  if (a.N == 64) return tc_launch(lin_tc_fwd_kernel<2, false>, lin_tc_fwd_smem<2>(), g, st, "lin_tc_fwd", a);
-  return tc_launch(lin_tc_fwd_kernel<3, false>, lin_tc_fwd_smem<3>(), g, st, "lin_tc_fwd", a);
+  if (a.R) return lin_tc_fwd_launch(lin_tc_fwd_kernel<1, true>, lin_tc_fwd_smem<1>(), g, st, "lin_tc_fwd_ln", a);
+  if (a.N == 32) return lin_tc_fwd_launch(lin_tc_fwd_kernel<1, false>, lin_tc_fwd_smem<1>(), g, st, "lin_tc_fwd", a);
+  if (a.N == 64) return lin_tc_fwd_launch(lin_tc_fwd_kernel<2, false>, lin_tc_fwd_smem<2>(), g, st, "lin_tc_fwd", a);
+  return lin_tc_fwd_launch(lin_tc_fwd_kernel<3, false>, lin_tc_fwd_smem<3>(), g, st, "lin_tc_fwd", a);
 }
 static int lin_tc_bwd_one(const LinBwd& a, cudaStream_t st) {
   const int g = 2;                                   // TMEM: 256 columns per CTA

@@ -31,6 +31,8 @@ cases = [
     ("bwd 32   (dY,X -> dX)        384 B/tok", 384, lambda: P.lin_bwd(dY, X, W32, dW=dW32, db=db32, dX=dX)),
     ("bwd gelu (dY,H,X -> dX)      512 B/tok", 512, lambda: P.lin_bwd(dY, X, W32, act=P.ACT_GELU, A=H, dW=dW32, db=db32, dX=dX)),
     ("bwd 96   (dY96,X -> dX)      640 B/tok", 640, lambda: P.lin_bwd(dY96, X, W96, dW=dW96, db=db96, dX=dX)),
+    ("bwd 32 dX only (dY -> dX)    256 B/tok", 256, lambda: P.lin_bwd(dY, None, W32, dX=dX)),
+    ("bwd 32 dW only (dY,X -> )    256 B/tok", 256, lambda: P.lin_bwd(dY, X, W32, dW=dW32, db=db32)),
 ]
 for name, bpt, fn in cases:
     for _ in range(3): fn()

@@ -159,6 +159,26 @@ __global__ void __launch_bounds__(NT, 1) rates(long long* out, float* sink, int 
     }
     sync(); t1 = clock64(); rec(t1 - t0);
   }
+  // dW-style SS MMAs (lin_tc bwd): M=128, N=64, K=8, transposed operands with 144-byte chunk stride (LBO) / 4608-byte groups
+  {
+    sync();
+    if (warp == 8 && elect_one()) {
+      const uint32_t id = idesc_tf32(128, 64);
+      const long long m0 = clock64();
+      for (int r = 0; r < reps; ++r)
+        mma_ss(tb + 256, smem_desc(smem_u32(tiles) + (r & 15) * 288, 144, 4608), smem_desc(smem_u32(tiles) + 18432 + (r & 15) * 288, 144, 4608), id, 1);
+      commit(&bar[3]);
+      mbar_wait(&bar[3], 0);
+      out[50] = clock64() - m0;
+      const long long m1 = clock64();
+      for (int r = 0; r < reps; ++r)
+        mma_ss(tb + 256, smem_desc(smem_u32(tiles) + (r & 15) * 256, 128, 4096), smem_desc(smem_u32(tiles) + 16384 + (r & 15) * 256, 128, 4096), id, 1);
+      commit(&bar[3]);
+      mbar_wait(&bar[3], 1);
+      out[51] = clock64() - m1;
+    }
+    __syncwarp();
+  }
   // commit -> wait round trip with a single tiny MMA
   sync();
   if (warp == 8 && elect_one()) {
@@ -180,9 +200,9 @@ int main() {
   long long* d; float* s;
   cudaMalloc(&d, 64 * 8); cudaMalloc(&s, NT * 4); cudaMemset(d, 0, 64 * 8);
   const int reps = 64;
-  cudaFuncSetAttribute(rates, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  cudaFuncSetAttribute(rates, cudaFuncAttributeMaxDynamicSharedMemorySize, 131072);
   for (int pass = 0; pass < 2; ++pass) {
-    rates<<<1, NT, 65536>>>(d, s, reps);
+    rates<<<1, NT, 131072>>>(d, s, reps);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("launch: %s\n", cudaGetErrorString(e)); return 1; }
   }
@@ -199,6 +219,7 @@ int main() {
   for (int l = 0; l < 4; ++l, ++i)
     printf("key-pass tile chain (6 x N32 + 8 x N16 MMAs + commit) with %-22s: issuer %.1f clk/tile ; streaming warps %.1f clk per 64-col ld/st round\n",
            lname[l], (double)h[40 + l] / reps, (double)h[44 + l] / (2 * reps));
+  printf("dW-style mma.ss M128 N64 K8, LBO 144 / SBO 4608: %.1f clk/mma ; LBO 128 / SBO 4096: %.1f clk/mma\n", (double)h[50] / reps, (double)h[51] / reps);
   printf("single mma + commit + wait round trip: %lld clk\n", h[i]);
   return 0;
 }

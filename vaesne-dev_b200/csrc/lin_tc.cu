@@ -302,17 +302,75 @@ __global__ void __launch_bounds__(LT, 3) lin_tc_fwd_kernel(LinFwd a, const __gri
 // =================================================================================================
 // backward
 // =================================================================================================
+// 256 threads per CTA: TWO threads per token row (thread = (row r, column half hf)); warps 0-3 own columns 0..15, warps
+// 4-7 columns 16..31 of TMEM lanes / rows 0..127.  Halving the per-thread work and doubling the warps is what hides
+// the latency of the ~1000-instruction per-row arithmetic (LayerNorm backward, dropout, hi/lo splits, transposes).
 // shared memory (tiles of 18 KB):  dZT_hi | B1 = dZT_lo | XT_hi | B2 = XT_lo | B0   then W^T hi/lo and the small tables.
 //   B0: dY chunk (cp.async) -> dR staging.   B1: S / activation input (cp.async), then, once every thread has read
 //   its row, the lo half of dZ^T.   B2: X tile (cp.async), then the lo half of X^T, then (after the MMAs) dX staging.
 // dW for one 32-row chunk of W: ONE MMA per 8-token K step with A = [dZ^T_hi ; dZ^T_lo] stacked along M (rows 0-31 /
 // 32-63) and B = [X^T_hi ; X^T_lo] stacked along N (64 columns): D[n][k] + D[n][32+k] + D[32+n][k] is the fp32-level
 // product (hi*hi + hi*lo + lo*hi), accumulated in TMEM across all tiles of the CTA.
+constexpr int BT = 256;              // threads of the backward CTA
 template <int NCH>
-__host__ __device__ constexpr size_t lin_tc_bwd_smem() { return 128 + sizeof(float) * (2 * NCH * 1024 + 5 * TILE + 32 * 3 + 64) + 32; }
+__host__ __device__ constexpr size_t lin_tc_bwd_smem() { return 128 + sizeof(float) * (2 * NCH * 1024 + 5 * TILE + 32 * 3 + 64 + 128 * 8) + 32; }
+
+__device__ __forceinline__ void load_tile256(float* dst, const float* src, long long ld, long long t0, int rows, int tid) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int id = it * BT + tid, r = id >> 3, c = id & 7;
+    if (r < rows) cp_async16(dst + r * PITCH + c * 4, src + (t0 + r) * ld + c * 4);
+  }
+}
+template <bool ACC>
+__device__ __forceinline__ void store_tile256(float* dst, long long ld, const float* src, long long t0, int rows, int tid) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int id = it * BT + tid, r = id >> 3, c = id & 7;
+    if (r < rows) {
+      float4 v = *reinterpret_cast<const float4*>(src + r * PITCH + c * 4);
+      float4* g = reinterpret_cast<float4*>(dst + (t0 + r) * ld + c * 4);
+      if (ACC) { const float4 o = *g; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+      *g = v;
+    }
+  }
+}
+__device__ __forceinline__ void lds_half(float* v, const float* p) {          // 16 floats
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = reinterpret_cast<const float4*>(p)[j];
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void sts_half(float* p, const float* v) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void tmem_put16(uint32_t taddr, const float* x) {
+  uint32_t u[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) u[c] = __float_as_uint(x[c]);
+  tmem_st16(taddr, u);
+}
+// lane l (< 16) <- sum over the warp of v[l]   (v is destroyed; lanes >= 16 hold partial garbage)
+__device__ __forceinline__ float warp_colsum16(float* v, int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 16);
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
 
 template <int NCH, bool LN>
-__global__ void __launch_bounds__(LT, 2) lin_tc_bwd_kernel(LinBwd a) {
+__global__ void __launch_bounds__(BT, 2) lin_tc_bwd_kernel(LinBwd a) {
   constexpr int N = NCH * 32;
   constexpr int COLS = 256;            // A hi|lo 64 + dX 32 + dW 64*NCH  (NCH <= 2)
   extern __shared__ __align__(1024) unsigned char lin_tc_raw[];
@@ -326,12 +384,14 @@ __global__ void __launch_bounds__(LT, 2) lin_tc_bwd_kernel(LinBwd a) {
   float* sG = WTlo + NCH * 1024;      // [32]
   float* sDg = sG + 32; float* sDbe = sDg + 32;   // [32] each
   float* sDb = sDbe + 32;             // [64]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sDb + 64);
+  float* red = sDb + 64;              // [128 rows][2 halves][4]: row-reduction exchange between the two threads of a row
+  uint64_t* bar = reinterpret_cast<uint64_t*>(red + 128 * 8);
   uint32_t* tmem_s = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r = tid & 127, hf = tid >> 7, c0 = hf * 16;       // row of the tile, column half, first column
   const bool wgrad = a.dW != nullptr;
 
-  for (int i = tid; i < N * 32; i += LT) {
+  for (int i = tid; i < N * 32; i += BT) {
     const int n = i >> 5, k = i & 31;
     float hi, lo;
     split_tf32(a.W[i], hi, lo);
@@ -347,121 +407,123 @@ __global__ void __launch_bounds__(LT, 2) lin_tc_bwd_kernel(LinBwd a) {
   __syncthreads();
   fence_after();
   const uint32_t tb = *tmem_s;
-  const uint32_t tl = tb + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t idX = idesc_tf32(128, 32), idW = idesc_tf32(128, 64);
   const uint32_t aWThi = smem_u32(WThi), aWTlo = smem_u32(WTlo), aZT = smem_u32(dZT), aXT = smem_u32(XT);
   const DropCfg dc = make_drop(LN ? a.p_drop : 0.f, a.seed, a.stream_id);
-  float* my0 = B0 + tid * PITCH; float* my1 = B1 + tid * PITCH; float* my2 = B2 + tid * PITCH;
+  float* my0 = B0 + r * PITCH + c0; float* my1 = B1 + r * PITCH + c0; float* my2 = B2 + r * PITCH + c0;
   uint32_t ph = 0;
   bool pending = false;          // an MMA batch has been committed and not yet waited for
   bool first_tile = true;
-  float accg[LN ? 32 : 1], accb[LN ? 32 : 1];
+  float accg[LN ? 16 : 1], accb[LN ? 16 : 1], accd[NCH][16];     // dgamma / dbeta / db partials of this thread's rows
 #pragma unroll
-  for (int j = 0; j < (LN ? 32 : 1); ++j) { accg[j] = 0.f; accb[j] = 0.f; }
+  for (int j = 0; j < (LN ? 16 : 1); ++j) { accg[j] = 0.f; accb[j] = 0.f; }
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) accd[c][j] = 0.f;
 
   const int ntiles = (a.T + LT - 1) / LT;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long t0 = (long long)tile * LT;
     const int rows = min(LT, a.T - (int)t0);
-    const long long t = t0 + tid;
-    const bool active = tid < rows;
+    const long long t = t0 + r;
+    const bool active = r < rows;
     // the previous tile's MMAs read dZT (incl. B1) and XT (incl. B2): they must be done before the loads land
     if (pending) { mbar_wait(bar, ph); ph ^= 1u; pending = false; fence_after(); }
     __syncthreads();
-    if (wgrad) load_tile(B2, a.X, a.ldx, t0, rows, tid);
+    if (wgrad) load_tile256(B2, a.X, a.ldx, t0, rows, tid);
 #pragma unroll
     for (int c = 0; c < NCH; ++c) {
       if (c > 0) {               // chunk c-1's MMAs read B1 (= dZT_lo); B0 was consumed before its barrier
         if (pending) { mbar_wait(bar, ph); ph ^= 1u; pending = false; fence_after(); }
         __syncthreads();
       }
-      load_tile(B0, a.dY + c * 32, a.lddy, t0, rows, tid);
-      if (LN) load_tile(B1, a.S, 32, t0, rows, tid);
-      else if (a.act != 0) load_tile(B1, a.A + c * 32, a.lda, t0, rows, tid);
+      load_tile256(B0, a.dY + c * 32, a.lddy, t0, rows, tid);
+      if (LN) load_tile256(B1, a.S, 32, t0, rows, tid);
+      else if (a.act != 0) load_tile256(B1, a.A + c * 32, a.lda, t0, rows, tid);
       cp_async_wait_all();
       __syncthreads();
-      float dz[32];
-      lds_row(dz, my0);
+      float dz[16];
+      lds_half(dz, my0);
       if (LN) {
-        float s[32], g[32];
-        lds_row(s, my1);
-        float mean = 0.f;
+        float sv[16], g[16];
+        lds_half(sv, my1);
+        float ps = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mean += s[j];
-        mean *= (1.f / 32);
-        float var = 0.f;
+        for (int j = 0; j < 16; ++j) ps += sv[j];
+        red[(r * 2 + hf) * 4] = ps;
+        __syncthreads();
+        const float mean = (red[(r * 2) * 4] + red[(r * 2 + 1) * 4]) * (1.f / 32);
+        float pv = 0.f, pg = 0.f, pgd = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) { s[j] -= mean; var = fmaf(s[j], s[j], var); }
-        const float rstd = 1.f / sqrtf(var * (1.f / 32) + a.eps);
-        float m1 = 0.f, m2 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          s[j] *= rstd;                       // xhat
-          g[j] = dz[j] * sG[j];
-          m1 += g[j]; m2 = fmaf(g[j], s[j], m2);
+        for (int j = 0; j < 16; ++j) {
+          sv[j] -= mean; pv = fmaf(sv[j], sv[j], pv);
+          g[j] = dz[j] * sG[c0 + j];
+          pg += g[j]; pgd = fmaf(g[j], sv[j], pgd);
         }
-        m1 *= (1.f / 32); m2 *= (1.f / 32);
-        if (active) {        // dgamma / dbeta: accumulated per thread over all tiles of the CTA, reduced once at the end
+        red[(r * 2 + hf) * 4 + 1] = pv; red[(r * 2 + hf) * 4 + 2] = pg; red[(r * 2 + hf) * 4 + 3] = pgd;
+        __syncthreads();
+        const float var = (red[(r * 2) * 4 + 1] + red[(r * 2 + 1) * 4 + 1]) * (1.f / 32);
+        const float rstd = 1.f / sqrtf(var + a.eps);
+        const float m1 = (red[(r * 2) * 4 + 2] + red[(r * 2 + 1) * 4 + 2]) * (1.f / 32);
+        const float m2 = (red[(r * 2) * 4 + 3] + red[(r * 2 + 1) * 4 + 3]) * (1.f / 32) * rstd;
+        if (active) {            // dgamma / dbeta: accumulated per thread over all tiles of the CTA, reduced once at the end
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { accg[j] = fmaf(dz[j], s[j], accg[j]); accb[j] += dz[j]; }
+          for (int j = 0; j < 16; ++j) { accg[j] = fmaf(dz[j] * rstd, sv[j], accg[j]); accb[j] += dz[j]; }
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dz[j] = rstd * (g[j] - m1 - s[j] * m2);     // dS = dR
-        if (a.dR) sts_row(my0, dz);           // own row of B0: already consumed by this thread
+        for (int j = 0; j < 16; ++j) dz[j] = rstd * (g[j] - m1 - sv[j] * rstd * m2);     // dS = dR
+        if (a.dR) sts_half(my0, dz);          // own half row of B0: already consumed by this thread
         if (dc.on) {
           const uint32_t rh = drop_row_hash(dc, (uint64_t)t);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dz[j] *= drop_mult_row(dc, rh, j);
+          for (int j = 0; j < 16; ++j) dz[j] *= drop_mult_row(dc, rh, c0 + j);
         }
       } else if (a.act != 0) {
-        float av[32];
-        lds_row(av, my1);
+        float av[16];
+        lds_half(av, my1);
         if (a.act == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dz[j] = av[j] > 0.f ? dz[j] : 0.f;
+          for (int j = 0; j < 16; ++j) dz[j] = av[j] > 0.f ? dz[j] : 0.f;
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dz[j] *= gelu_erf_grad(av[j]);
+          for (int j = 0; j < 16; ++j) dz[j] *= gelu_erf_grad(av[j]);
         }
       }
       if (!active) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dz[j] = 0.f;
+        for (int j = 0; j < 16; ++j) dz[j] = 0.f;
       }
-      if (wgrad && a.db) {
-        float r3[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r3[j] = dz[j];
-        const float cs = warp_colsum32(r3, lane);
-        atomicAdd(&sDb[c * 32 + lane], cs);
-      }
+      for (int j = 0; j < 16; ++j) accd[c][j] += dz[j];
       if (c == 0 && wgrad) {
-        // X row -> X^T hi / lo.  XT_lo aliases the X tile: every thread must have read its row first.
-        float x[32];
-        lds_row(x, my2);
+        // X half row -> X^T hi / lo.  XT_lo aliases the X tile: every thread must have read its row first.
+        float x[16];
+        lds_half(x, my2);
         if (a.Xadd && active) {               // rare (the MLP heads): the second addend comes straight from global memory
-          const float4* xa = reinterpret_cast<const float4*>(a.Xadd + t * a.ldxa);
+          const float4* xa = reinterpret_cast<const float4*>(a.Xadd + t * a.ldxa + c0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { const float4 v4 = xa[j]; x[4 * j] += v4.x; x[4 * j + 1] += v4.y; x[4 * j + 2] += v4.z; x[4 * j + 3] += v4.w; }
+          for (int j = 0; j < 4; ++j) { const float4 v4 = xa[j]; x[4 * j] += v4.x; x[4 * j + 1] += v4.y; x[4 * j + 2] += v4.z; x[4 * j + 3] += v4.w; }
         }
         __syncthreads();                      // also: every thread has read its B1 row (dZT_lo aliases B1)
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 16; ++j) {
           float hi, lo;
           split_tf32(active ? x[j] : 0.f, hi, lo);
-          XT[tcanon(j, tid)] = hi; B2[tcanon(j, tid)] = lo;
+          XT[tcanon(c0 + j, r)] = hi; B2[tcanon(c0 + j, r)] = lo;
         }
       } else {
         __syncthreads();                      // every thread has read its B1 row (dZT_lo aliases B1)
       }
       {
-        float hi[32], lo[32];
+        float hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) split_tf32(dz[j], hi[j], lo[j]);
-        if (a.dX) { tmem_put32(tl, hi); tmem_put32(tl + 32, lo); }
+        for (int j = 0; j < 16; ++j) split_tf32(dz[j], hi[j], lo[j]);
+        if (a.dX) { tmem_put16(tl + c0, hi); tmem_put16(tl + 32 + c0, lo); }
         if (wgrad) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { dZT[tcanon(j, tid)] = hi[j]; B1[tcanon(j, tid)] = lo[j]; }
+          for (int j = 0; j < 16; ++j) { dZT[tcanon(c0 + j, r)] = hi[j]; B1[tcanon(c0 + j, r)] = lo[j]; }
         }
         tmem_wait_st();
       }
@@ -473,19 +535,19 @@ __global__ void __launch_bounds__(LT, 2) lin_tc_bwd_kernel(LinBwd a) {
         if (lelect_one()) {
           if (a.dX) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-              const uint32_t off = (uint32_t)(8 * c + 2 * s) * 128;
+            for (int s2 = 0; s2 < 4; ++s2) {
+              const uint32_t off = (uint32_t)(8 * c + 2 * s2) * 128;
               const uint64_t bhi = smem_desc(aWThi + off, 128, N * 32), blo = smem_desc(aWTlo + off, 128, N * 32);
-              mma_ts(tb + 64, tb + s * 8, bhi, idX, (c > 0 || s > 0) ? 1u : 0u);
-              mma_ts(tb + 64, tb + 32 + s * 8, bhi, idX, 1u);
-              mma_ts(tb + 64, tb + s * 8, blo, idX, 1u);
+              mma_ts(tb + 64, tb + s2 * 8, bhi, idX, (c > 0 || s2 > 0) ? 1u : 0u);
+              mma_ts(tb + 64, tb + 32 + s2 * 8, bhi, idX, 1u);
+              mma_ts(tb + 64, tb + s2 * 8, blo, idX, 1u);
             }
           }
           if (wgrad) {
 #pragma unroll
-            for (int s = 0; s < 16; ++s)
-              mma_ss(tb + 96 + c * 64, smem_desc(aZT + s * 288, 144, 4608), smem_desc(aXT + s * 288, 144, 4608), idW,
-                     (!first_tile || s > 0) ? 1u : 0u);
+            for (int s2 = 0; s2 < 16; ++s2)
+              mma_ss(tb + 96 + c * 64, smem_desc(aZT + s2 * 288, 144, 4608), smem_desc(aXT + s2 * 288, 144, 4608), idW,
+                     (!first_tile || s2 > 0) ? 1u : 0u);
           }
           commit(bar);
         }
@@ -493,24 +555,24 @@ __global__ void __launch_bounds__(LT, 2) lin_tc_bwd_kernel(LinBwd a) {
       }
       pending = true;
       if (LN && a.dR) {        // B0 holds dR rows (written before the barriers above)
-        if (a.dR_acc) store_tile<true>(a.dR, a.lddr, B0, t0, rows, tid);
-        else store_tile<false>(a.dR, a.lddr, B0, t0, rows, tid);
+        if (a.dR_acc) store_tile256<true>(a.dR, a.lddr, B0, t0, rows, tid);
+        else store_tile256<false>(a.dR, a.lddr, B0, t0, rows, tid);
       }
     }
     first_tile = false;
     if (a.dX) {
       mbar_wait(bar, ph); ph ^= 1u; pending = false;
       fence_after();
-      uint32_t d[32];
-      tmem_ld32(tl + 64, d); tmem_wait_ld();
-      float v[32];
+      uint32_t d[16];
+      tmem_ld16(tl + 64 + c0, d); tmem_wait_ld();
+      float v[16];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(d[j]);
-      sts_row(my2, v);           // XT_lo (aliased) has been consumed: the MMAs are complete
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(d[j]);
+      sts_half(my2, v);          // XT_lo (aliased) has been consumed: the MMAs are complete
       fence_before();
       __syncthreads();
-      if (a.dX_acc) store_tile<true>(a.dX, a.lddx, B2, t0, rows, tid);
-      else store_tile<false>(a.dX, a.lddx, B2, t0, rows, tid);
+      if (a.dX_acc) store_tile256<true>(a.dX, a.lddx, B2, t0, rows, tid);
+      else store_tile256<false>(a.dX, a.lddx, B2, t0, rows, tid);
     }
   }
   if (pending) { mbar_wait(bar, ph); ph ^= 1u; pending = false; }
@@ -528,9 +590,17 @@ __global__ void __launch_bounds__(LT, 2) lin_tc_bwd_kernel(LinBwd a) {
         atomicAdd(&a.dW[(c * 32 + lane) * 32 + k], __uint_as_float(d[k]) + (warp == 0 ? __uint_as_float(e[k]) : 0.f));
     }
   }
+  // column sums of this thread's rows -> shared accumulators (lane l < 16 holds column c0 + l)
+  if (wgrad && a.db) {
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const float cs = warp_colsum16(accd[c], lane);
+      if (lane < 16) atomicAdd(&sDb[c * 32 + c0 + lane], cs);
+    }
+  }
   if (LN) {
-    const float cg = warp_colsum32(accg, lane), cb = warp_colsum32(accb, lane);
-    atomicAdd(&sDg[lane], cg); atomicAdd(&sDbe[lane], cb);
+    const float cg = warp_colsum16(accg, lane), cb = warp_colsum16(accb, lane);
+    if (lane < 16) { atomicAdd(&sDg[c0 + lane], cg); atomicAdd(&sDbe[c0 + lane], cb); }
   }
   __syncthreads();
   if (wgrad && a.db && tid < N) atomicAdd(&a.db[tid], sDb[tid]);
@@ -564,7 +634,7 @@ bool lin_tc_bwd_eligible(const LinBwd& a) {
 // never more than there are tiles.  The occupancy of each kernel instantiation is queried once.
 struct TcKernelInfo { const void* fn; int ctas_per_sm; int sms; };
 template <typename K>
-static int tc_prepare(K k, size_t smem, const char* what, TcKernelInfo& out) {
+static int tc_prepare(K k, size_t smem, const char* what, TcKernelInfo& out, int threads = LT) {
   static thread_local TcKernelInfo cache[16] = {};
   for (auto& e : cache) if (e.fn == (const void*)k) { out = e; return V_OK; }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -583,7 +653,7 @@ static int tc_prepare(K k, size_t smem, const char* what, TcKernelInfo& out) {
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
   }
-  const int regs_cta = ((fa.numRegs + 7) / 8) * 8 * LT;
+  const int regs_cta = ((fa.numRegs + 7) / 8) * 8 * threads;
   const int by_regs = regs_sm / (regs_cta > 0 ? regs_cta : 1);
   const int by_smem = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + 1024));
   int occ = by_regs < by_smem ? by_regs : by_smem;
@@ -594,14 +664,14 @@ static int tc_prepare(K k, size_t smem, const char* what, TcKernelInfo& out) {
   return V_OK;
 }
 template <typename K, typename A>
-static int tc_launch(K k, size_t smem, int tmem_ctas, cudaStream_t st, const char* what, const A& args) {
+static int tc_launch(K k, size_t smem, int tmem_ctas, cudaStream_t st, const char* what, const A& args, int threads = LT) {
   TcKernelInfo ki;
-  int rc = tc_prepare(k, smem, what, ki); if (rc) return rc;
+  int rc = tc_prepare(k, smem, what, ki, threads); if (rc) return rc;
   const int per_sm = ki.ctas_per_sm < tmem_ctas ? ki.ctas_per_sm : tmem_ctas;      // TMEM: 512 columns per SM
   const int ntiles = (args.T + LT - 1) / LT;
   const int cap = ki.sms * per_sm;
   const int grid = ntiles < cap ? ntiles : cap;
-  k<<<grid, LT, smem, st>>>(args);
+  k<<<grid, threads, smem, st>>>(args);
   return check_launch(what);
 }
 
@@ -655,9 +725,9 @@ int lin_tc_fwd(const LinFwd& a, cudaStream_t st) {
 }
 static int lin_tc_bwd_one(const LinBwd& a, cudaStream_t st) {
   const int g = 2;                                   // TMEM: 256 columns per CTA
-  if (a.S) return tc_launch(lin_tc_bwd_kernel<1, true>, lin_tc_bwd_smem<1>(), g, st, "lin_tc_bwd_ln", a);
-  if (a.N == 32) return tc_launch(lin_tc_bwd_kernel<1, false>, lin_tc_bwd_smem<1>(), g, st, "lin_tc_bwd", a);
-  return tc_launch(lin_tc_bwd_kernel<2, false>, lin_tc_bwd_smem<2>(), g, st, "lin_tc_bwd", a);
+  if (a.S) return tc_launch(lin_tc_bwd_kernel<1, true>, lin_tc_bwd_smem<1>(), g, st, "lin_tc_bwd_ln", a, BT);
+  if (a.N == 32) return tc_launch(lin_tc_bwd_kernel<1, false>, lin_tc_bwd_smem<1>(), g, st, "lin_tc_bwd", a, BT);
+  return tc_launch(lin_tc_bwd_kernel<2, false>, lin_tc_bwd_smem<2>(), g, st, "lin_tc_bwd", a, BT);
 }
 int lin_tc_bwd(const LinBwd& a, cudaStream_t st) {
   if (a.N <= 64) return lin_tc_bwd_one(a, st);
@@ -674,3 +744,4 @@ int lin_tc_bwd(const LinBwd& a, cudaStream_t st) {
 }
 
 }  // namespace vaesne
+

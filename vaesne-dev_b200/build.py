@@ -15,6 +15,10 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "--expt-relaxed-constexpr", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 
 
+if os.environ.get("VAESNE_TC_PROFILE"):      # probe build: per-phase clocks in attn_tc_dkv_kernel (tests/probe/attn_tc_check.py TC_PROF=1)
+    FLAGS.append("-DVAESNE_TC_PROFILE")
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 

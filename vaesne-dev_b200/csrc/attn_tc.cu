@@ -52,8 +52,14 @@ constexpr bool kSplitT = VAESNE_TC_SPLIT_T != 0;   // dP = dO V^T with hi/lo-spl
 constexpr int RPT = (MAXL + NTHREADS - 1) / NTHREADS;   // staged rows per thread
 constexpr int TILE_F = MAXL * 8;    // floats of one staged operand array (32 KB)
 
-__device__ long long g_tc_prof[16];   // probe: per-phase clocks of CTA (0,0): warp 0 and the issuer
+__device__ long long g_tc_prof[16];   // probe build (-DVAESNE_TC_PROFILE): per-phase clocks of CTA (0,0), warp 0 of the key pass
+#ifdef VAESNE_TC_PROFILE
 #define TPROF(slot, expr) do { long long _t0 = clock64(); expr; prof[slot] += clock64() - _t0; } while (0)
+#define TPROF_ADD(slot, v) prof[slot] += (v)
+#else
+#define TPROF(slot, expr) do { expr; } while (0)
+#define TPROF_ADD(slot, v) (void)0
+#endif
 __constant__ int g_tc_dbg = 0;      // timing experiments only (tests/probe): 1 = no second-product MMAs, 2 = no exponentials
 struct TcDrop { uint32_t s0, s1, stream, thr; float scale; bool on; };
 __device__ __forceinline__ TcDrop make_tcdrop(float p, const uint64_t* seed, uint32_t stream) {
@@ -651,7 +657,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
+#ifdef VAESNE_TC_PROFILE
   const long long tk0 = clock64();
+#endif
 
   init_pipeline(s, tid, warp);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
@@ -753,7 +761,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
     uint64_t* bars = s.bars + wg * B_PER_WG;
     const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * C_WG);
     const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
+#ifdef VAESNE_TC_PROFILE
     long long prof[16] = {0}; const long long tstart = clock64(); prof[6] = tstart - tk0;
+#endif
     WgPhase ph = {0, 0};
     int it = 0;
     for (int kt = wg; kt < nKT; kt += 2, ++it) {
@@ -777,7 +787,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       const uint32_t cw = dc.on ? drop_col_word(dc, nh, cs) : 1u;
       for (int j = 0; j < NQ; ++j) {
         TPROF(0, ph.wait_s(bars));
+#ifdef VAESNE_TC_PROFILE
         const long long tc0 = clock64();
+#endif
         uint32_t pk[32], dk2[32];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -819,7 +831,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
             dk2[half * 16 + cc * 2] = pack_h2(ss[0], ss[1]); dk2[half * 16 + cc * 2 + 1] = pack_h2(ss[2], ss[3]);
           }
         }
-        prof[1] += clock64() - tc0;
+        TPROF_ADD(1, clock64() - tc0);
         if (j > 0) TPROF(5, ph.wait_out_free(bars));
         tmem_st32(tOUT, pk); tmem_st32(tOUT + 32, dk2);
         TPROF(2, tmem_wait_st());
@@ -843,7 +855,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
       }
       fence_before();
     }
+#ifdef VAESNE_TC_PROFILE
     if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { prof[4] = clock64() - tstart; for (int q = 0; q < 7; ++q) g_tc_prof[q] = prof[q]; }
+#endif
   }
   fence_before();
   __syncthreads();

@@ -161,29 +161,7 @@ def time_cpu(B, steps, warmup, dropout=0.1):
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
-    # ---- encode latents/s (BASELINE.json's second metric; 1 GPU): VAE.encode on resident batches ------------
-    enc = None
-    if world == 1:
-        enc = {}
-        EB = 512
-        xb = synth_batch(EB, 77)
-        xd = [tuple(t.to(dev) for t in mod) for mod in xb]
-        for name, vae, x in (("photometry", model.vaes[0], xd[0]), ("spectra", model.vaes[1], xd[1])):
-            was_training = vae.training
-            for _ in range(3):
-                vae.encode(x)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize(); a.record()
-            for _ in range(10):
-                vae.encode(x)
-            b.record(); torch.cuda.synchronize()
-            enc[name + "_latents_per_s"] = EB * 10 / (a.elapsed_time(b) * 1e-3)
-            vae.train(was_training)
-        enc["batch"] = EB
-        model.train()
-
-    if rank != 0:
-        torch.distributed.destroy_process_group()
+    if rank != 0:            # under torchrun only rank 0 runs the CPU arm; the other ranks exit without work
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)

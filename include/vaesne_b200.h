@@ -139,6 +139,13 @@ int vaesne_step_advance(int* step, unsigned long long* seed, void* stream);
  * global Philox stream (util_layers.py:265-271,283); here every forward call takes one fresh 64-bit seed. */
 int vaesne_seed_next(unsigned long long* cell, unsigned long long* out, void* stream);
 
+/* ---- probe hooks (tests/probe only; not part of the operator surface) ---------------------------
+ * vaesne_debug_tc(flags): timing experiments on the tcgen05 attention key pass (1 = skip the second-product MMAs,
+ * 2 = skip the exponentials; results are then meaningless).  vaesne_debug_tc_prof(out16): per-phase clocks of
+ * CTA (0,0) when the library was built with VAESNE_TC_PROFILE=1. */
+int vaesne_debug_tc(int flags);
+int vaesne_debug_tc_prof(long long* out16 /* host */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,7 +47,8 @@ _SIGS = {
     "vaesne_step_advance": [_vp, _vp, _vp],
     "vaesne_seed_next": [_vp, _vp, _vp],
 }
-EXPORTS = sorted(list(_SIGS) + ["vaesne_last_error", "vaesne_abi_version", "vaesne_is_emulated", "vaesne_launch_count"])
+EXPORTS = sorted(list(_SIGS) + ["vaesne_last_error", "vaesne_abi_version", "vaesne_is_emulated", "vaesne_launch_count",
+                  "vaesne_debug_tc", "vaesne_debug_tc_prof"])      # the last two: probe hooks (tests/probe)
 
 
 def _bind(path: str):

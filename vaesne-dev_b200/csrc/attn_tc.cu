@@ -864,6 +864,310 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
   if (warp == 8) { fence_after(); tmem_dealloc<512>(tb); }
 }
 
+// =================================================================================================
+// backward, fused single pass (default): the key-major pass above extended by dQ, so S, P, dP and dS are computed ONCE.
+// dQ = scale * sum_keys dS[query, key] K[key] contracts over the TMEM-lane index of dS^T, which no TMEM operand can do;
+// the warpgroup therefore also writes dS^T (the fp16 pairs it stores to TMEM anyway) to shared memory as an MN-major
+// A operand [64 queries x 128 keys] (eight conflict-free 16-byte stores per thread), this key tile's K rows sit next to it as
+// an MN-major B operand, and 8 SS MMAs (M=64, N=8, K=16) produce the tile's dQ contribution in 8 TMEM columns
+// (row m -> lane (m&15) + 32*(m>>4)).  One CTA owns all of dq[n, :, h], so the contributions of its key tiles are summed
+// with vector reductions into the zero-initialised output — no second pass, no extra exponentials.
+// To make room (shared memory and TMEM are both full) the dV product takes dO as fp16 hi only and dQ takes K as fp16 hi only.
+// =================================================================================================
+constexpr int C_DQ = 216;                    // per warpgroup: ACC = dK hi|lo (192..207) | dV (208..215) | dQ tile (216..223)
+constexpr int DS_BYTES = 64 * 128 * 2, KB_BYTES = 8 * 128 * 2;
+constexpr size_t BWD_SMEM = (size_t)5 * TILE_F * 4 + HALF_ARR * 2 + 2 * DS_BYTES + 2 * KB_BYTES + 3 * MAXL * 4 + MAXL * 2 + 32 * 4 + 36 * 4 + 16 * 8 + 16;
+static_assert(BWD_SMEM <= 232448, "fused backward does not fit the 227 KB shared-memory window");
+
+__device__ __forceinline__ void put_l2h_hi(__half* dst, int row, const float* x) {
+  __half* p = dst + (row >> 4) * 128 + ((row >> 3) & 1) * 64 + (row & 7);
+#pragma unroll
+  for (int d = 0; d < 8; ++d) p[d * 8] = __float2half_rn(x[d]);
+}
+__device__ __forceinline__ void red_add8(float* p, const float* v) {
+  if (((uintptr_t)p & 15) == 0) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+  } else {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) atomicAdd(p + c, v[c]);
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  TcSmem s;
+  float* const f0 = reinterpret_cast<float*>(tc_smem_raw);
+  float* Qhi = f0; float* Qlo = f0 + TILE_F; float* G1 = f0 + 2 * TILE_F; float* G1lo = f0 + 3 * TILE_F;
+  __half* Q2h = reinterpret_cast<__half*>(f0 + 4 * TILE_F);          // hi | lo
+  __half* G2h = reinterpret_cast<__half*>(f0 + 5 * TILE_F);          // hi only
+  unsigned char* const dsb = tc_smem_raw + (size_t)5 * TILE_F * 4 + HALF_ARR * 2;     // per warpgroup: dS^T tile (A of the dQ product)
+  unsigned char* const kbb = dsb + 2 * DS_BYTES;                                      // per warpgroup: K rows (B of the dQ product)
+  {
+    float* f = reinterpret_cast<float*>(kbb + 2 * KB_BYTES);
+    for (int i = 0; i < 6; ++i) s.arr[i] = nullptr;
+    s.pad = nullptr;
+    s.f0 = f; f += MAXL; s.f1 = f; f += MAXL;
+    s.w0 = (uint32_t*)f; f += MAXL;
+    s.idx = (uint16_t*)f; f += MAXL / 2;
+    s.ballot = (uint32_t*)f; s.pre = s.ballot + 32;
+    s.bars = (uint64_t*)(s.pre + 36);
+    s.tmem = (uint32_t*)(s.bars + 16);
+  }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
+  const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
+
+  init_pipeline(s, tid, warp);
+  if (tid == 0) { mbar_init(&s.bars[12], 1); mbar_init(&s.bars[13], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  const int LkC = compact_keys(a, s, n, tid, warp, lane);
+  for (int j = tid; j < a.Lk; j += NTHREADS) {          // slot -> key index; masked keys get zero gradients
+    const int c = key_slot(s, j);
+    if (c >= 0) { s.idx[c] = (uint16_t)j; continue; }
+    float z[8];
+#pragma unroll
+    for (int c2 = 0; c2 < 8; ++c2) z[c2] = 0.f;
+    st8g(a.dk + ((long long)n * a.Lk + j) * a.lddk + h * 8, z);
+    st8g(a.dv + ((long long)n * a.Lk + j) * a.lddv + h * 8, z);
+  }
+  // query side (as in the key-major pass; delta = rowsum(dO * O) is computed here, dq starts at zero — NaN if every key is masked)
+  const int NQ = (a.Lq + BK - 1) / BK;
+  {
+    float q[RPT][8], g[RPT][8], lse2[RPT], delta[RPT];
+    float gm = 0.f;
+    const float init = LkC > 0 ? 0.f : __int_as_float(0x7fc00000);
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+      const int i = tid + u * NTHREADS;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { q[u][c] = 0.f; g[u][c] = 0.f; }
+      lse2[u] = INFINITY; delta[u] = 0.f;
+      if (i < a.Lq) {
+        float o[8];
+        ld8g(q[u], a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
+        ld8g(g[u], a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
+        ld8g(o, a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8);
+        lse2[u] = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
+        float d = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { d = fmaf(g[u][c], o[c], d); o[c] = init; }
+        delta[u] = d;
+        st8g(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, o);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RPT; ++u)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) gm = fmaxf(gm, fabsf(g[u][c]));
+    gm = isfinite(gm) ? gm : 0.f;
+    if (tid == 0) s.pre[33] = 0u;
+    __syncthreads();
+    atomicMax(&s.pre[33], __float_as_uint(gm));
+    __syncthreads();
+    const float sc = pow2_normaliser(__uint_as_float(s.pre[33]));
+#pragma unroll
+    for (int u = 0; u < RPT; ++u) {
+      const int i = tid + u * NTHREADS;
+      if (i >= NQ * BK) continue;
+      float hi[8], lo[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { q[u][c] *= kQScale; g[u][c] *= sc; }
+      split8(q[u], hi, lo);
+      put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l2h(Q2h, i, q[u]);
+      split8(g[u], hi, lo);
+      put_l1(G1, i, hi); put_l1(G1lo, i, lo); put_l2h_hi(G2h, i, g[u]);
+      s.f0[i] = -lse2[u]; s.f1[i] = -delta[u] * sc;
+      s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
+    }
+  }
+  const float cs_scale = pow2_normaliser(__uint_as_float(s.pre[33]));
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = *s.tmem;
+  const int nKT = (LkC + TCQ - 1) / TCQ;
+  // per warpgroup: IN = S^T (64) | T^T (64) ; OUT = P^T (32) | dS^T (32) fp16 pairs ; ACC = dK hi|lo (16) | dV (8) | dQ tile (8) ; X = Khi | Klo | Vhi | Vlo
+
+  if (warp >= 8) {
+    const int w = warp - 8;
+    uint64_t* b = s.bars + w * B_PER_WG;
+    uint64_t* bdq = s.bars + 12 + w;
+    const uint32_t idS = idesc_tf32(128, BK), idK = idesc_f16(128, 16), idV = idesc_f16(128, 8), idQ = idesc_f16_mn(64, 8, true, true);
+    const uint32_t aQhi = smem_u32(Qhi), aQlo = smem_u32(Qlo), aG1 = smem_u32(G1), aG1lo = smem_u32(G1lo), aQ2 = smem_u32(Q2h), aG2 = smem_u32(G2h);
+    const uint32_t aDS = smem_u32(dsb + w * DS_BYTES), aKB = smem_u32(kbb + w * KB_BYTES);
+    const uint32_t tw = tb + (uint32_t)(w * C_WG);
+    auto issue_st = [&](int j) {
+      const uint32_t d = tw + C_IN, x = tw + C_X;
+      const uint64_t dQhi = smem_desc(aQhi + j * (BK * 32), 128, 256), dQlo = smem_desc(aQlo + j * (BK * 32), 128, 256);
+      mma_ts(d, x, dQhi, idS, 0);
+      mma_ts(d, x + 8, dQhi, idS, 1);
+      mma_ts(d, x, dQlo, idS, 1);
+      const uint64_t dGhi = smem_desc(aG1 + j * (BK * 32), 128, 256), dGlo = smem_desc(aG1lo + j * (BK * 32), 128, 256);
+      mma_ts(d + 64, x + 16, dGhi, idS, 0);
+      if (kSplitT) { mma_ts(d + 64, x + 24, dGhi, idS, 1); mma_ts(d + 64, x + 16, dGlo, idS, 1); }
+    };
+    uint32_t cF = 0, cP = 0;
+    int it = 0;
+    for (int kt = w; kt < nKT; kt += 2, ++it) {
+      const int ksteps = (min(TCQ, LkC - kt * TCQ) + 15) >> 4;
+      mbar_wait(&b[B_X], it & 1);
+      fence_after();
+      if (elect_one()) { issue_st(0); commit(&b[B_S]); }
+      __syncwarp();
+      for (int j = 0; j < NQ; ++j) {
+        const bool last = j + 1 == NQ;
+        if (!last) {
+          mbar_wait(&b[B_F], cF & 1); cF++;
+          fence_after();
+          if (elect_one()) { issue_st(j + 1); commit(&b[B_S]); }
+          __syncwarp();
+        }
+        mbar_wait(&b[B_P], cP & 1); cP++;
+        fence_after();
+        if (elect_one()) {
+          const int nsteps = (min(BK, a.Lq - j * BK) + 15) >> 4;
+          const uint32_t dK = tw + C_ACC, dV = dK + 16;
+          for (int t = 0; t < nsteps; ++t) {
+            const uint32_t off = (uint32_t)(j * (BK / 16) + t) * 256;
+            const uint32_t acc = (j > 0 || t > 0) ? 1u : 0u;
+            mma_ts_f16(dV, tw + C_OUT + (uint32_t)t * 8, smem_desc(aG2 + off, 128, 256), idV, acc);                   // P^T dO
+            mma_ts_f16(dK, tw + C_OUT + 32 + (uint32_t)t * 8, smem_desc(aQ2 + off, 128, HALF_ARR * 2), idK, acc);     // dS^T [Qhi | Qlo]
+          }
+          if (!last) commit(&b[B_OF]);
+          for (int t = 0; t < ksteps; ++t)                                                                             // dS K -> dQ tile
+            mma_ss_f16(tw + C_DQ, smem_desc(aDS + t * 256, 128, 2048), smem_desc(aKB + t * 256, 128, 2048), idQ, t > 0 ? 1u : 0u);
+          commit(last ? &b[B_O] : bdq);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int wg = warp >> 2, r = tid & 127;
+    uint64_t* bars = s.bars + wg * B_PER_WG;
+    uint64_t* bdq = s.bars + 12 + wg;
+    const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * C_WG);
+    const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
+    unsigned char* const ds_row = dsb + wg * DS_BYTES + (r & 7) * 16 + (r >> 3) * 128;      // this key's 16-byte slot in each query group
+    unsigned char* const kb_row = kbb + wg * KB_BYTES + (r & 7) * 16 + (r >> 3) * 128;
+    const float dq_scale = kScale / cs_scale;
+    WgPhase ph = {0, 0};
+    uint32_t cdq = 0;
+    int it = 0;
+    // dQ contribution of query tile jq: accumulator row m (query jq*64 + m) sits in lane (m&15) + 32*(m>>4)
+    auto drain_dq = [&](int jq) {
+      uint32_t v[8];
+      tmem_ld8(tw + C_DQ, v); tmem_wait_ld();
+      const int i = jq * BK + (warp & 3) * 16 + lane;
+      if (lane < 16 && i < a.Lq) {
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[c] = __uint_as_float(v[c]) * dq_scale;
+        red_add8(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, o);
+      }
+    };
+    for (int kt = wg; kt < nKT; kt += 2, ++it) {
+      const int cs = kt * TCQ + r;
+      const bool valid = cs < LkC;
+      const int jk = valid ? (int)s.idx[cs] : 0;
+      float k[8], v[8], hi[8], lo[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { k[c] = 0.f; v[c] = 0.f; }
+      if (valid) {
+        ld8g(k, a.k + ((long long)n * a.Lk + jk) * a.ldk + h * 8);
+        ld8g(v, a.v + ((long long)n * a.Lk + jk) * a.ldv + h * 8);
+      }
+      *reinterpret_cast<uint4*>(kb_row) = make_uint4(pack_h2(k[0], k[1]), pack_h2(k[2], k[3]), pack_h2(k[4], k[5]), pack_h2(k[6], k[7]));
+      split8(k, hi, lo);
+      tmem_put8(tX, hi); tmem_put8(tX + 8, lo);
+      split8(v, hi, lo);
+      tmem_put8(tX + 16, hi); tmem_put8(tX + 24, lo);
+      fence_async_smem();
+      tmem_wait_st();
+      fence_before();
+      mbar_arrive(&bars[B_X]);
+      const uint32_t cw = dc.on ? drop_col_word(dc, nh, cs) : 1u;
+      for (int j = 0; j < NQ; ++j) {
+        ph.wait_s(bars);
+        uint32_t pk[32], dk2[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t sr[32], tr[32];
+          tmem_ld32(tIN + half * 32, sr); tmem_ld32(tIN + 64 + half * 32, tr);
+          tmem_wait_ld();
+          if (half == 1 && j + 1 < NQ) signal_in_free(bars);
+          const float4* l4 = reinterpret_cast<const float4*>(s.f0 + j * BK + half * 32);
+          const float4* d4 = reinterpret_cast<const float4*>(s.f1 + j * BK + half * 32);
+          const uint4* w4 = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            const float4 lv = l4[cc], dv = d4[cc];
+            float pp[4], ss[4];
+            const int c = cc * 4;
+            float x0, x1, x2, x3;
+            upk2(add2(pk2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), pk2(lv.x, lv.y)), x0, x1);
+            upk2(add2(pk2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])), pk2(lv.z, lv.w)), x2, x3);
+            const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);
+            const f32x2 pa = pk2(p0, p1), pb = pk2(p2, p3);
+            const f32x2 ta = pk2(__uint_as_float(tr[c]), __uint_as_float(tr[c + 1])), tb2 = pk2(__uint_as_float(tr[c + 2]), __uint_as_float(tr[c + 3]));
+            if (!dc.on) {
+              pp[0] = p0; pp[1] = p1; pp[2] = p2; pp[3] = p3;
+              upk2(mul2(pa, add2(ta, pk2(dv.x, dv.y))), ss[0], ss[1]);
+              upk2(mul2(pb, add2(tb2, pk2(dv.z, dv.w))), ss[2], ss[3]);
+            } else {
+              const uint4 wv = w4[cc];
+              const float m0 = (wv.x * cw >= dc.thr) ? dc.scale : 0.f, m1 = (wv.y * cw >= dc.thr) ? dc.scale : 0.f;
+              const float m2 = (wv.z * cw >= dc.thr) ? dc.scale : 0.f, m3 = (wv.w * cw >= dc.thr) ? dc.scale : 0.f;
+              const f32x2 ma = pk2(m0, m1), mb = pk2(m2, m3);
+              upk2(mul2(pa, ma), pp[0], pp[1]);
+              upk2(mul2(pb, mb), pp[2], pp[3]);
+              upk2(mul2(pa, fma2(ta, ma, pk2(dv.x, dv.y))), ss[0], ss[1]);
+              upk2(mul2(pb, fma2(tb2, mb, pk2(dv.z, dv.w))), ss[2], ss[3]);
+            }
+            pk[half * 16 + cc * 2] = pack_h2(pp[0], pp[1]); pk[half * 16 + cc * 2 + 1] = pack_h2(pp[2], pp[3]);
+            dk2[half * 16 + cc * 2] = pack_h2(ss[0], ss[1]); dk2[half * 16 + cc * 2 + 1] = pack_h2(ss[2], ss[3]);
+          }
+        }
+        if (j > 0) {
+          ph.wait_out_free(bars);
+          mbar_wait(bdq, cdq & 1); cdq++;       // dQ product of tile j-1 done: its accumulator can be read, the dS^T slot rewritten
+          fence_after();
+          drain_dq(j - 1);
+        }
+        tmem_st32(tOUT, pk); tmem_st32(tOUT + 32, dk2);
+        // padded key rows (zero K, but P = 2^(-lse) may be huge) must contribute exact zeros to dQ
+#pragma unroll
+        for (int g8 = 0; g8 < 8; ++g8)
+          *reinterpret_cast<uint4*>(ds_row + g8 * 2048) = valid ? make_uint4(dk2[g8 * 4], dk2[g8 * 4 + 1], dk2[g8 * 4 + 2], dk2[g8 * 4 + 3]) : make_uint4(0u, 0u, 0u, 0u);
+        fence_async_smem();
+        tmem_wait_st();
+        fence_before();
+        mbar_arrive(&bars[B_P]);
+      }
+      mbar_wait(&bars[B_O], it & 1);
+      fence_after();
+      drain_dq(NQ - 1);
+      uint32_t o[24];
+      tmem_ld16(tA, o); tmem_ld8(tA + 16, o + 16); tmem_wait_ld();
+      if (valid) {
+        float dk[8], dv[8];
+        const float inv = 1.f / cs_scale;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          dk[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * (kLn2 * inv);      // hi + lo parts; Q carried log2(e)
+          dv[c] = __uint_as_float(o[16 + c]) * inv;
+        }
+        st8g(a.dk + ((long long)n * a.Lk + jk) * a.lddk + h * 8, dk);
+        st8g(a.dv + ((long long)n * a.Lk + jk) * a.lddv + h * 8, dv);
+      }
+      fence_before();
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 8) { fence_after(); tmem_dealloc<512>(tb); }
+}
+
 // ------------------------------------------------------------------------------------------------
 static bool env_flag(const char* name) { const char* e = getenv(name); return e && e[0] && e[0] != '0'; }
 
@@ -890,6 +1194,13 @@ int attn_tc_fwd(const AttnArgs& a, cudaStream_t st) {
 }
 
 int attn_tc_bwd(const AttnArgs& a, cudaStream_t st) {
+  static const bool split = env_flag("VAESNE_TC_BWD_SPLIT");      // the two-pass backward (dq kernel + key-major kernel), kept for comparison
+  if (!split) {
+    static int cfg = tc_configure(attn_tc_bwd_kernel, BWD_SMEM, "attn_tc_bwd");
+    if (cfg) return cfg;
+    attn_tc_bwd_kernel<<<dim3(kH, a.N), dim3(NTHREADS), BWD_SMEM, st>>>(a);
+    return check_launch("attn_tc_bwd");
+  }
   static int cfg1 = tc_configure(attn_tc_dq_kernel, DQ_SMEM, "attn_tc_dq");
   static int cfg2 = tc_configure(attn_tc_dkv_kernel, DKV_SMEM, "attn_tc_dkv");
   if (cfg1) return cfg1;

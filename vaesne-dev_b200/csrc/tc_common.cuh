@@ -47,6 +47,18 @@ __device__ __forceinline__ void mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uin
                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
                :: "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+// MN-major ("transposed") fp16 operands in shared memory, no swizzle (validated by tests/probe/tc_probe_f16mn.cu):
+// element (mn, k) at (mn&7)*2 + (mn>>3)*SBO + (k&7)*16 + (k>>3)*LBO bytes, i.e. 128-byte core matrices of 8 k-rows x 8
+// MN-contiguous halfs; descriptor bits 15 / 16 select MN-major A / B.  With M=64 (cta_group::1) accumulator row m sits in
+// TMEM lane (m&15) + 32*(m>>4) (+16 if the D address carries lane 16) and the other 16 lanes of each quarter are untouched.
+__device__ __forceinline__ constexpr uint32_t idesc_f16_mn(int M, int N, bool a_mn, bool b_mn) {
+  return idesc_f16(M, N) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u);
+}
+__device__ __forceinline__ void mma_ss_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }

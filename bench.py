@@ -296,11 +296,11 @@ def main():
             elems = float(Nb) * 4 * Lq * Lk
             flops = 4.0 * elems * 8 * (1.0 if name == "attn_fwd" else 2.5)
             ach = flops / (top["avg_ms"] * 1e-3) / 1e12
-            # the unit that actually binds at head_dim 8: one MUFU.EX2 per score element per pass (1 fwd, 2 bwd),
+            # the unit that actually binds at head_dim 8: one MUFU.EX2 per score element per pass,
             # 16 per clock per SM (tests/probe/tc_rates.cu), at the SM clock seen under load
             mhz = (clk or {}).get("sm_mhz") or 1965.0
             ex2_rate = 148 * 16 * mhz * 1e6
-            ex2_floor_ms = elems * (1 if name == "attn_fwd" else 2) / ex2_rate * 1e3
+            ex2_floor_ms = elems / ex2_rate * 1e3            # the fused backward also exponentiates each element once
             roof = {"kernel": f"{name}[N={Nb},Lq={Lq},Lk={Lk}] (attn_tc_* kernels: tcgen05 kind::tf32 + kind::f16)", "bound": "tensor",
                     "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                     "frac": ach / pk["tf_sust"],

@@ -17,20 +17,13 @@
 #include "tc_common.cuh"
 using namespace vaesne::tc;
 
-__device__ __forceinline__ uint32_t idesc_f16_mn(int M, int N, int amn, int bmn) {
-  return (1u << 4) | ((uint32_t)amn << 15) | ((uint32_t)bmn << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_ss_f16(uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-               :: "r"(d), "l"(a), "l"(b), "r"(id), "r"(acc) : "memory");
-}
 __host__ __device__ inline int mn_off(int mn, int k, int lbo, int sbo) { return (mn & 7) * 2 + (mn >> 3) * sbo + (k & 7) * 16 + (k >> 3) * lbo; }
 
 constexpr int KT = 128;       // contraction length (keys)
 constexpr int A_SBO = 2048, A_LBO = 128, B_SBO = 2048, B_LBO = 128;
 
 // mode: M (64|128), N (8|16), lane_off (0|16) of the D address
-__global__ void __launch_bounds__(128) probe(const __half* A, const __half* B, float* D, int M, int N, int lane_off, long long* clk, int reps) {
+__global__ void __launch_bounds__(128) probe(const __half* A, const __half* B, float* D, int M, int N, int lane_off, long long* clk, int reps, int indep) {
   extern __shared__ __align__(1024) unsigned char raw[];
   unsigned char* sA = raw;                      // 16 m-groups x 2048 B = 32 KB
   unsigned char* sB = raw + 32768;              // 2 n-groups x 2048 B
@@ -48,7 +41,7 @@ __global__ void __launch_bounds__(128) probe(const __half* A, const __half* B, f
   { uint32_t v[16]; for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(-777.f); tmem_st16(tl, v); tmem_st16(tl + 16, v); tmem_wait_st(); }
   fence_before(); __syncthreads();
   uint32_t ph = 0;
-  const uint32_t id = idesc_f16_mn(M, N, 1, 1);
+  const uint32_t id = idesc_f16_mn(M, N, true, true);
   const uint32_t dst = tb + ((uint32_t)lane_off << 16);
   if (tid == 0) {
     fence_after();
@@ -65,7 +58,7 @@ __global__ void __launch_bounds__(128) probe(const __half* A, const __half* B, f
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r)
       for (int t = 0; t < KT / 16; ++t)
-        mma_ss_f16(dst + 16, smem_desc(smem_u32(sA) + t * 256, A_LBO, A_SBO), smem_desc(smem_u32(sB) + t * 256, B_LBO, B_SBO), id, 1);
+        mma_ss_f16(dst + 16 + ((indep && (t & 1)) ? (16u << 16) : 0u), smem_desc(smem_u32(sA) + t * 256, A_LBO, A_SBO), smem_desc(smem_u32(sB) + t * 256, B_LBO, B_SBO), id, 1);
     commit(bar);
     const long long t1 = clock64();
     mbar_wait(bar, ph);
@@ -93,12 +86,12 @@ int main() {
     double s = 0; for (int k = 0; k < KT; ++k) s += (double)__half2float(A[m * KT + k]) * __half2float(B[n * KT + k]);
     want[m * 16 + n] = s;
   }
-  const int cfg[][3] = {{128, 16, 0}, {128, 8, 0}, {64, 16, 0}, {64, 8, 0}, {64, 16, 16}, {64, 8, 16}};
+  const int cfg[][4] = {{128, 16, 0, 0}, {128, 8, 0, 0}, {64, 16, 0, 0}, {64, 8, 0, 0}, {64, 16, 16, 0}, {64, 8, 16, 0}, {64, 8, 0, 1}};
   for (auto& c : cfg) {
     const int M = c[0], N = c[1], lo = c[2], reps = 64;
-    probe<<<1, 128, smem>>>(dA, dB, dD, M, N, lo, dC, reps);
+    probe<<<1, 128, smem>>>(dA, dB, dD, M, N, lo, dC, reps, c[3]);
     cudaError_t e = cudaDeviceSynchronize();
-    printf("M=%d N=%d lane_off=%d: %s\n", M, N, lo, cudaGetErrorString(e));
+    printf("M=%d N=%d lane_off=%d two-accumulators=%d: %s\n", M, N, lo, c[3], cudaGetErrorString(e));
     if (e != cudaSuccess) return 1;
     std::vector<float> D(128 * 16); long long clk[2];
     cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost); cudaMemcpy(clk, dC, 16, cudaMemcpyDeviceToHost);

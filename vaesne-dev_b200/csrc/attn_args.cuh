@@ -32,6 +32,10 @@ int attn_tc_bwd(const AttnArgs& a, cudaStream_t st);
 bool attn_small_eligible(const AttnArgs& a);
 int attn_small_fwd(const AttnArgs& a, cudaStream_t st);
 int attn_small_bwd(const AttnArgs& a, cudaStream_t st);
+// short sequences on both sides (attn_mid.cu): 8 < Lk <= 64, Lq <= 64 — one CTA per batch row
+bool attn_mid_eligible(const AttnArgs& a);
+int attn_mid_fwd(const AttnArgs& a, cudaStream_t st);
+int attn_mid_bwd(const AttnArgs& a, cudaStream_t st);
 #endif
 
 }  // namespace vaesne

@@ -87,6 +87,7 @@ __device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64
 __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float max3(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rn_tf32(float x) { uint32_t h; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x)); return __uint_as_float(h); }
 __device__ __forceinline__ bool elect_one() {
@@ -223,9 +224,25 @@ __device__ __forceinline__ int key_slot(const TcSmem& s, int j) {     // -1 if m
 // Stage the unmasked keys of (n, h) as tf32 hi + lo parts.  Khi/Klo: L1 of K.  V1hi/V1lo: L1 of V.
 // V2hi/V2lo, K2hi/K2lo: L2 of V / K (the lo array sits one TILE_F after the hi array: it is the second 8-row
 // group of the N=16 operand, so the accumulator's columns 8..15 collect the lo-part product for free).
+// Two phases: load_key_rows() issues every thread's global loads (up to RPT rows) BEFORE the key compaction, so that
+// their round trip overlaps it — the prologue is a chain of memory latencies with nothing else resident on the SM;
+// stage_keys() then writes the rows to their compacted slots.
+struct KeyRows { float kk[RPT][8], vv[RPT][8]; };
+__device__ __forceinline__ void load_key_rows(const AttnArgs& a, int n, int h, int tid, KeyRows& kr) {
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    const int j = tid + u * NTHREADS;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { kr.kk[u][c] = 0.f; kr.vv[u][c] = 0.f; }
+    if (j < a.Lk) {
+      ld8g(kr.kk[u], a.k + ((long long)n * a.Lk + j) * a.ldk + h * 8);
+      ld8g(kr.vv[u], a.v + ((long long)n * a.Lk + j) * a.ldv + h * 8);
+    }
+  }
+}
 __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, int n, int h, int tid, int LkC, int tile,
                                            float* Khi, float* Klo, float* V1hi, float* V1lo, __half* V2h, __half* K2h,
-                                           const TcDrop& dc) {
+                                           const TcDrop& dc, const KeyRows& kr) {
   const int Lpad = ((LkC + tile - 1) / tile) * tile;
   float z[8];
 #pragma unroll
@@ -238,30 +255,18 @@ __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, i
   }
   const int nh = n * kH + h;
   if (dc.on) for (int c = tid; c < Lpad; c += NTHREADS) s.w0[c] = drop_col_word(dc, nh, c);
-  // every thread owns up to RPT rows; all their global loads are issued before the first one is consumed
-  // (the prologue is latency-bound: one round trip instead of RPT)
-  float kk[RPT][8], vv[RPT][8];
-  int cc[RPT];
 #pragma unroll
   for (int u = 0; u < RPT; ++u) {
     const int j = tid + u * NTHREADS;
-    cc[u] = j < a.Lk ? key_slot(s, j) : -1;
-    if (cc[u] >= 0) {
-      ld8g(kk[u], a.k + ((long long)n * a.Lk + j) * a.ldk + h * 8);
-      ld8g(vv[u], a.v + ((long long)n * a.Lk + j) * a.ldv + h * 8);
-    }
-  }
-#pragma unroll
-  for (int u = 0; u < RPT; ++u) {
-    const int c = cc[u];
+    const int c = j < a.Lk ? key_slot(s, j) : -1;
     if (c < 0) continue;
     float hi[8], lo[8];
-    split8(kk[u], hi, lo);
+    split8(kr.kk[u], hi, lo);
     put_l1(Khi, c, hi); put_l1(Klo, c, lo);
-    if (K2h) put_l2h(K2h, c, kk[u]);
-    split8(vv[u], hi, lo);
+    if (K2h) put_l2h(K2h, c, kr.kk[u]);
+    split8(kr.vv[u], hi, lo);
     if (V1hi) { put_l1(V1hi, c, hi); put_l1(V1lo, c, lo); }
-    if (V2h) put_l2h(V2h, c, vv[u]);
+    if (V2h) put_l2h(V2h, c, kr.vv[u]);
   }
 }
 
@@ -340,9 +345,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
 
+  KeyRows kr;
+  load_key_rows(a, n, h, tid, kr);
   init_pipeline(s, tid, warp);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
-  stage_keys(a, s, n, h, tid, LkC, FK, Khi, Klo, nullptr, nullptr, V2h, nullptr, dc);
+  stage_keys(a, s, n, h, tid, LkC, FK, Khi, Klo, nullptr, nullptr, V2h, nullptr, dc, kr);
   fence_async_smem();
   fence_before();
   __syncthreads();
@@ -417,7 +424,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
         float mt = -1e30f;
         if (nvalid == FK) {
 #pragma unroll
-          for (int c = 0; c < 128; ++c) mt = fmaxf(mt, __uint_as_float(sr[c]));
+          for (int c = 0; c < 128; c += 2) mt = max3(mt, __uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));      // FMNMX3: half the issue slots
         } else {
 #pragma unroll
           for (int c = 0; c < 128; ++c) { if (c >= nvalid) sr[c] = 0xff800000u; mt = fmaxf(mt, __uint_as_float(sr[c])); }
@@ -501,9 +508,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
 
+  KeyRows kr;
+  load_key_rows(a, n, h, tid, kr);
   init_pipeline(s, tid, warp);
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
-  stage_keys(a, s, n, h, tid, LkC, BK, Khi, Klo, V1, V1lo, nullptr, K2h, dc);
+  stage_keys(a, s, n, h, tid, LkC, BK, Khi, Klo, V1, V1lo, nullptr, K2h, dc, kr);
   fence_async_smem();
   fence_before();
   __syncthreads();
@@ -917,13 +926,37 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
+#ifdef VAESNE_TC_PROFILE
+  const long long tk0 = clock64();
+#endif
 
+  // query side: every thread owns up to RPT queries; their loads are issued first so that the round trip overlaps the key
+  // compaction below (the prologue is a chain of global-memory latencies and nothing else runs on the SM meanwhile)
+  float q[RPT][8], g[RPT][8], o[RPT][8], lse2[RPT];
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    const int i = tid + u * NTHREADS;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { q[u][c] = 0.f; g[u][c] = 0.f; o[u][c] = 0.f; }
+    lse2[u] = INFINITY;
+    if (i < a.Lq) {
+      ld8g(q[u], a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
+      ld8g(g[u], a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
+      ld8g(o[u], a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8);
+      lse2[u] = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
+    }
+  }
   init_pipeline(s, tid, warp);
-  if (tid == 0) { mbar_init(&s.bars[12], 1); mbar_init(&s.bars[13], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid == 0) { mbar_init(&s.bars[12], 1); mbar_init(&s.bars[13], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); s.pre[33] = 0u; }
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
-  for (int j = tid; j < a.Lk; j += NTHREADS) {          // slot -> key index; masked keys get zero gradients
+  const int nKT = (LkC + TCQ - 1) / TCQ;
+  // Key tiles go to the two warpgroups in pairs; an odd last tile is SHARED: each warpgroup takes half of its query tiles
+  // and the two partial dK/dV are summed by reductions into zero-initialised rows (an odd count would otherwise leave one
+  // warpgroup idle for a whole tile: 4 vs 3 at the usual ~800-900 unmasked keys).
+  const int nPair = nKT >> 1, shared_from = (nKT & 1) ? (nKT - 1) * TCQ : (1 << 30);
+  for (int j = tid; j < a.Lk; j += NTHREADS) {          // slot -> key index; masked keys (and the shared tile's rows) start at zero
     const int c = key_slot(s, j);
-    if (c >= 0) { s.idx[c] = (uint16_t)j; continue; }
+    if (c >= 0) { s.idx[c] = (uint16_t)j; if (c < shared_from) continue; }
     float z[8];
 #pragma unroll
     for (int c2 = 0; c2 < 8; ++c2) z[c2] = 0.f;
@@ -933,36 +966,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
   // query side (as in the key-major pass; delta = rowsum(dO * O) is computed here, dq starts at zero — NaN if every key is masked)
   const int NQ = (a.Lq + BK - 1) / BK;
   {
-    float q[RPT][8], g[RPT][8], lse2[RPT], delta[RPT];
+    float delta[RPT];
     float gm = 0.f;
     const float init = LkC > 0 ? 0.f : __int_as_float(0x7fc00000);
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
       const int i = tid + u * NTHREADS;
+      float d = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) { q[u][c] = 0.f; g[u][c] = 0.f; }
-      lse2[u] = INFINITY; delta[u] = 0.f;
-      if (i < a.Lq) {
-        float o[8];
-        ld8g(q[u], a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
-        ld8g(g[u], a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
-        ld8g(o, a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8);
-        lse2[u] = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
-        float d = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { d = fmaf(g[u][c], o[c], d); o[c] = init; }
-        delta[u] = d;
-        st8g(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, o);
-      }
+      for (int c = 0; c < 8; ++c) { d = fmaf(g[u][c], o[u][c], d); o[u][c] = init; gm = fmaxf(gm, fabsf(g[u][c])); }
+      delta[u] = d;
+      if (i < a.Lq) st8g(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, o[u]);
     }
-#pragma unroll
-    for (int u = 0; u < RPT; ++u)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) gm = fmaxf(gm, fabsf(g[u][c]));
     gm = isfinite(gm) ? gm : 0.f;
-    if (tid == 0) s.pre[33] = 0u;
-    __syncthreads();
-    atomicMax(&s.pre[33], __float_as_uint(gm));
+    atomicMax(&s.pre[33], __float_as_uint(gm));       // pre[33] was cleared before the barriers of compact_keys
     __syncthreads();
     const float sc = pow2_normaliser(__uint_as_float(s.pre[33]));
 #pragma unroll
@@ -986,7 +1003,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
   __syncthreads();
   fence_after();
   const uint32_t tb = *s.tmem;
-  const int nKT = (LkC + TCQ - 1) / TCQ;
+  const int nIter = nPair + (nKT & 1);
   // per warpgroup: IN = S^T (64) | T^T (64) ; OUT = P^T (32) | dS^T (32) fp16 pairs ; ACC = dK hi|lo (16) | dV (8) | dQ tile (8) ; X = Khi | Klo | Vhi | Vlo
 
   if (warp >= 8) {
@@ -1000,23 +1017,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     auto issue_st = [&](int j) {
       const uint32_t d = tw + C_IN, x = tw + C_X;
       const uint64_t dQhi = smem_desc(aQhi + j * (BK * 32), 128, 256), dQlo = smem_desc(aQlo + j * (BK * 32), 128, 256);
+      const uint64_t dGhi = smem_desc(aG1 + j * (BK * 32), 128, 256), dGlo = smem_desc(aG1lo + j * (BK * 32), 128, 256);
       mma_ts(d, x, dQhi, idS, 0);
       mma_ts(d, x + 8, dQhi, idS, 1);
       mma_ts(d, x, dQlo, idS, 1);
-      const uint64_t dGhi = smem_desc(aG1 + j * (BK * 32), 128, 256), dGlo = smem_desc(aG1lo + j * (BK * 32), 128, 256);
       mma_ts(d + 64, x + 16, dGhi, idS, 0);
       if (kSplitT) { mma_ts(d + 64, x + 24, dGhi, idS, 1); mma_ts(d + 64, x + 16, dGlo, idS, 1); }
     };
     uint32_t cF = 0, cP = 0;
     int it = 0;
-    for (int kt = w; kt < nKT; kt += 2, ++it) {
+    for (; it < nIter; ++it) {
+      const bool shared = it == nPair;
+      const int kt = shared ? nKT - 1 : 2 * it + w;
+      const int jb = (shared && w) ? NQ / 2 : 0, je = (shared && !w) ? NQ / 2 : NQ;
       const int ksteps = (min(TCQ, LkC - kt * TCQ) + 15) >> 4;
       mbar_wait(&b[B_X], it & 1);
       fence_after();
-      if (elect_one()) { issue_st(0); commit(&b[B_S]); }
+      if (elect_one()) { issue_st(jb); commit(&b[B_S]); }
       __syncwarp();
-      for (int j = 0; j < NQ; ++j) {
-        const bool last = j + 1 == NQ;
+      for (int j = jb; j < je; ++j) {
+        const bool last = j + 1 == je;
         if (!last) {
           mbar_wait(&b[B_F], cF & 1); cF++;
           fence_after();
@@ -1030,7 +1050,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
           const uint32_t dK = tw + C_ACC, dV = dK + 16;
           for (int t = 0; t < nsteps; ++t) {
             const uint32_t off = (uint32_t)(j * (BK / 16) + t) * 256;
-            const uint32_t acc = (j > 0 || t > 0) ? 1u : 0u;
+            const uint32_t acc = (j > jb || t > 0) ? 1u : 0u;
             mma_ts_f16(dV, tw + C_OUT + (uint32_t)t * 8, smem_desc(aG2 + off, 128, 256), idV, acc);                   // P^T dO
             mma_ts_f16(dK, tw + C_OUT + 32 + (uint32_t)t * 8, smem_desc(aQ2 + off, 128, HALF_ARR * 2), idK, acc);     // dS^T [Qhi | Qlo]
           }
@@ -1054,6 +1074,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     WgPhase ph = {0, 0};
     uint32_t cdq = 0;
     int it = 0;
+#ifdef VAESNE_TC_PROFILE
+    long long prof[16] = {0}; const long long tstart = clock64(); prof[6] = tstart - tk0;
+#endif
     // dQ contribution of query tile jq: accumulator row m (query jq*64 + m) sits in lane (m&15) + 32*(m>>4)
     auto drain_dq = [&](int jq) {
       uint32_t v[8];
@@ -1066,7 +1089,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
         red_add8(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, o);
       }
     };
-    for (int kt = wg; kt < nKT; kt += 2, ++it) {
+    for (; it < nIter; ++it) {
+      const bool shared = it == nPair;
+      const int kt = shared ? nKT - 1 : 2 * it + wg;
+      const int jb = (shared && wg) ? NQ / 2 : 0, je = (shared && !wg) ? NQ / 2 : NQ;
       const int cs = kt * TCQ + r;
       const bool valid = cs < LkC;
       const int jk = valid ? (int)s.idx[cs] : 0;
@@ -1087,15 +1113,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
       fence_before();
       mbar_arrive(&bars[B_X]);
       const uint32_t cw = dc.on ? drop_col_word(dc, nh, cs) : 1u;
-      for (int j = 0; j < NQ; ++j) {
-        ph.wait_s(bars);
+      for (int j = jb; j < je; ++j) {
+        TPROF(0, ph.wait_s(bars));
+#ifdef VAESNE_TC_PROFILE
+        const long long tc0 = clock64();
+#endif
         uint32_t pk[32], dk2[32];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t sr[32], tr[32];
           tmem_ld32(tIN + half * 32, sr); tmem_ld32(tIN + 64 + half * 32, tr);
           tmem_wait_ld();
-          if (half == 1 && j + 1 < NQ) signal_in_free(bars);
+          if (half == 1 && j + 1 < je) signal_in_free(bars);
           const float4* l4 = reinterpret_cast<const float4*>(s.f0 + j * BK + half * 32);
           const float4* d4 = reinterpret_cast<const float4*>(s.f1 + j * BK + half * 32);
           const uint4* w4 = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
@@ -1128,12 +1157,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
             dk2[half * 16 + cc * 2] = pack_h2(ss[0], ss[1]); dk2[half * 16 + cc * 2 + 1] = pack_h2(ss[2], ss[3]);
           }
         }
-        if (j > 0) {
-          ph.wait_out_free(bars);
-          mbar_wait(bdq, cdq & 1); cdq++;       // dQ product of tile j-1 done: its accumulator can be read, the dS^T slot rewritten
+        TPROF_ADD(1, clock64() - tc0);
+        if (j > jb) {
+          TPROF(5, ph.wait_out_free(bars));
+          TPROF(7, mbar_wait(bdq, cdq & 1)); cdq++;       // dQ product of tile j-1 done: its accumulator can be read, the dS^T slot rewritten
           fence_after();
-          drain_dq(j - 1);
+          TPROF(8, drain_dq(j - 1));
         }
+#ifdef VAESNE_TC_PROFILE
+        const long long ts0 = clock64();
+#endif
         tmem_st32(tOUT, pk); tmem_st32(tOUT + 32, dk2);
         // padded key rows (zero K, but P = 2^(-lse) may be huge) must contribute exact zeros to dQ
 #pragma unroll
@@ -1143,10 +1176,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
         tmem_wait_st();
         fence_before();
         mbar_arrive(&bars[B_P]);
+        TPROF_ADD(2, clock64() - ts0);
       }
-      mbar_wait(&bars[B_O], it & 1);
+      TPROF(3, mbar_wait(&bars[B_O], it & 1));
       fence_after();
-      drain_dq(NQ - 1);
+      drain_dq(je - 1);
       uint32_t o[24];
       tmem_ld16(tA, o); tmem_ld8(tA + 16, o + 16); tmem_wait_ld();
       if (valid) {
@@ -1157,11 +1191,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
           dk[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * (kLn2 * inv);      // hi + lo parts; Q carried log2(e)
           dv[c] = __uint_as_float(o[16 + c]) * inv;
         }
-        st8g(a.dk + ((long long)n * a.Lk + jk) * a.lddk + h * 8, dk);
-        st8g(a.dv + ((long long)n * a.Lk + jk) * a.lddv + h * 8, dv);
+        float* pk_ = a.dk + ((long long)n * a.Lk + jk) * a.lddk + h * 8;
+        float* pv_ = a.dv + ((long long)n * a.Lk + jk) * a.lddv + h * 8;
+        if (shared) { red_add8(pk_, dk); red_add8(pv_, dv); }
+        else { st8g(pk_, dk); st8g(pv_, dv); }
       }
       fence_before();
     }
+#ifdef VAESNE_TC_PROFILE
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { prof[4] = clock64() - tstart; for (int q = 0; q < 9; ++q) g_tc_prof[q] = prof[q]; }
+#endif
   }
   fence_before();
   __syncthreads();

@@ -195,9 +195,10 @@ __device__ __forceinline__ TcSmem carve(unsigned char* raw, int narr, bool cols)
 }
 
 // key compaction: ballot of kept keys per 32-key chunk + exclusive prefix.  Returns the number of kept keys.
+template <int NT = NTHREADS>
 __device__ __forceinline__ int compact_keys(const AttnArgs& a, const TcSmem& s, int n, int tid, int warp, int lane) {
   const unsigned char* mrow = a.mask ? a.mask + (long long)(n % a.mask_rows) * a.mask_len : nullptr;
-  for (int it = warp; it < 32; it += NTHREADS / 32) {
+  for (int it = warp; it < 32; it += NT / 32) {
     const int j = it * 32 + lane;
     const bool keep = j < a.Lk && !(mrow && j < a.mask_len && mrow[j]);
     const uint32_t b = __ballot_sync(0xffffffffu, keep);
@@ -227,11 +228,13 @@ __device__ __forceinline__ int key_slot(const TcSmem& s, int j) {     // -1 if m
 // Two phases: load_key_rows() issues every thread's global loads (up to RPT rows) BEFORE the key compaction, so that
 // their round trip overlaps it — the prologue is a chain of memory latencies with nothing else resident on the SM;
 // stage_keys() then writes the rows to their compacted slots.
-struct KeyRows { float kk[RPT][8], vv[RPT][8]; };
-__device__ __forceinline__ void load_key_rows(const AttnArgs& a, int n, int h, int tid, KeyRows& kr) {
+template <int NT> struct KeyRowsT { static constexpr int R = (MAXL + NT - 1) / NT; float kk[R][8], vv[R][8]; };
+using KeyRows = KeyRowsT<NTHREADS>;
+template <int NT>
+__device__ __forceinline__ void load_key_rows(const AttnArgs& a, int n, int h, int tid, KeyRowsT<NT>& kr) {
 #pragma unroll
-  for (int u = 0; u < RPT; ++u) {
-    const int j = tid + u * NTHREADS;
+  for (int u = 0; u < KeyRowsT<NT>::R; ++u) {
+    const int j = tid + u * NT;
 #pragma unroll
     for (int c = 0; c < 8; ++c) { kr.kk[u][c] = 0.f; kr.vv[u][c] = 0.f; }
     if (j < a.Lk) {
@@ -240,24 +243,25 @@ __device__ __forceinline__ void load_key_rows(const AttnArgs& a, int n, int h, i
     }
   }
 }
+template <int NT>
 __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, int n, int h, int tid, int LkC, int tile,
                                            float* Khi, float* Klo, float* V1hi, float* V1lo, __half* V2h, __half* K2h,
-                                           const TcDrop& dc, const KeyRows& kr) {
+                                           const TcDrop& dc, const KeyRowsT<NT>& kr) {
   const int Lpad = ((LkC + tile - 1) / tile) * tile;
   float z[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) z[c] = 0.f;
-  for (int c = LkC + tid; c < Lpad; c += NTHREADS) {
+  for (int c = LkC + tid; c < Lpad; c += NT) {
     put_l1(Khi, c, z); put_l1(Klo, c, z);
     if (V1hi) { put_l1(V1hi, c, z); put_l1(V1lo, c, z); }
     if (V2h) put_l2h(V2h, c, z);
     if (K2h) put_l2h(K2h, c, z);
   }
   const int nh = n * kH + h;
-  if (dc.on) for (int c = tid; c < Lpad; c += NTHREADS) s.w0[c] = drop_col_word(dc, nh, c);
+  if (dc.on) for (int c = tid; c < Lpad; c += NT) s.w0[c] = drop_col_word(dc, nh, c);
 #pragma unroll
-  for (int u = 0; u < RPT; ++u) {
-    const int j = tid + u * NTHREADS;
+  for (int u = 0; u < KeyRowsT<NT>::R; ++u) {
+    const int j = tid + u * NT;
     const int c = j < a.Lk ? key_slot(s, j) : -1;
     if (c < 0) continue;
     float hi[8], lo[8];
@@ -299,12 +303,12 @@ __device__ __forceinline__ void init_pipeline(const TcSmem& s, int tid, int warp
 
 // Issuer of warpgroup w: row tiles w, w+2, ... ; T column tiles each.
 // issue_in(j): first product of column tile j into IN.   issue_acc(j): second product of tile j from OUT into ACC.
-template <class FIn, class FAcc>
+template <int STRIDE = 2, class FIn, class FAcc>
 __device__ __forceinline__ void mma_issuer(uint64_t* b, int w, int nRT, int T, FIn issue_in, FAcc issue_acc) {
   if (T <= 0) return;
   uint32_t cF = 0, cP = 0;
   int it = 0;
-  for (int rt = w; rt < nRT; rt += 2, ++it) {
+  for (int rt = w; rt < nRT; rt += STRIDE, ++it) {
     mbar_wait(&b[B_X], it & 1);
     fence_after();
     if (elect_one()) { issue_in(0); commit(&b[B_S]); }
@@ -493,6 +497,192 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
   fence_before();
   __syncthreads();
   if (warp == 8) { fence_after(); tmem_dealloc<512>(tb); }
+}
+
+// =================================================================================================
+// forward, four warpgroups (default): same arithmetic and pipeline as attn_tc_fwd_kernel with 64-key tiles, so that a
+// warpgroup needs 128 TMEM columns (IN 64 | OUT 32 | ACC 16 | X 16) and FOUR query tiles are in flight per CTA.
+// The exponentiation loop is a dependent chain per thread (subtract, MUFU, accumulate, convert) and with two warps per
+// scheduler half the issue slots went to dependency stalls (ncu: 22 % wait + 26 % long scoreboard); four warps per
+// scheduler hide them.  Tile MMAs get smaller (N=64), which the tensor pipe has room for in the forward (< 25 % busy).
+// =================================================================================================
+constexpr int F4_THREADS = 640;          // 16 softmax warps + 4 issuer warps (one per warpgroup)
+constexpr int F4_FK = 64;
+constexpr int F4_IN = 0, F4_OUT = 64, F4_ACC = 96, F4_X = 112, F4_CW = 128;
+constexpr size_t FWD4_SMEM = (size_t)3 * TILE_F * 4 + MAXL * 4 + 32 * 4 + 36 * 4 + 24 * 8 + 16;
+
+__global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a) {
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  TcSmem s;
+  float* const fb = reinterpret_cast<float*>(tc_smem_raw);
+  float* Khi = fb; float* Klo = fb + TILE_F; __half* V2h = reinterpret_cast<__half*>(fb + 2 * TILE_F);
+  {
+    float* f = fb + 3 * TILE_F;
+    for (int i = 0; i < 6; ++i) s.arr[i] = nullptr;
+    s.pad = nullptr; s.f0 = s.f1 = nullptr; s.idx = nullptr;
+    s.w0 = (uint32_t*)f; f += MAXL;
+    s.ballot = (uint32_t*)f; s.pre = s.ballot + 32;
+    s.bars = (uint64_t*)(s.pre + 36);
+    s.tmem = (uint32_t*)(s.bars + 24);
+  }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
+  const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
+
+  KeyRowsT<F4_THREADS> kr;
+  load_key_rows<F4_THREADS>(a, n, h, tid, kr);
+  if (tid == 0) {
+    for (int w = 0; w < 4; ++w) {
+      uint64_t* b = s.bars + w * B_PER_WG;
+      mbar_init(&b[B_X], 128); mbar_init(&b[B_S], 1); mbar_init(&b[B_F], 128); mbar_init(&b[B_P], 128); mbar_init(&b[B_OF], 1); mbar_init(&b[B_O], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 16) tmem_alloc<512>(s.tmem);
+  const int LkC = compact_keys<F4_THREADS>(a, s, n, tid, warp, lane);
+  stage_keys<F4_THREADS>(a, s, n, h, tid, LkC, F4_FK, Khi, Klo, nullptr, nullptr, V2h, nullptr, dc, kr);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = *s.tmem;
+  const int T = (LkC + F4_FK - 1) / F4_FK;
+  const int nQT = (a.Lq + TCQ - 1) / TCQ;
+
+  if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");       // the issuer warpgroup hands its registers to the softmax warpgroups
+    const int w = warp - 16;
+    const uint32_t idQK = idesc_tf32(128, F4_FK), idPV = idesc_f16(128, 16);
+    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV2 = smem_u32(V2h);
+    const uint32_t tw = tb + (uint32_t)(w * F4_CW);
+    auto issue_qk = [&](int j) {
+      const uint32_t d = tw + F4_IN, q = tw + F4_X;
+      const uint64_t dKhi = smem_desc(aKhi + j * (F4_FK * 32), 128, 256), dKlo = smem_desc(aKlo + j * (F4_FK * 32), 128, 256);
+      mma_ts(d, q, dKhi, idQK, 0);
+      mma_ts(d, q + 8, dKhi, idQK, 1);
+      mma_ts(d, q, dKlo, idQK, 1);
+    };
+    auto issue_pv = [&](int j) {
+      const int nsteps = (min(F4_FK, LkC - j * F4_FK) + 15) >> 4;
+      for (int t = 0; t < nsteps; ++t) {
+        const uint32_t v = aV2 + (uint32_t)(j * (F4_FK / 16) + t) * 256;
+        mma_ts_f16(tw + F4_ACC, tw + F4_OUT + (uint32_t)t * 8, smem_desc(v, 128, HALF_ARR * 2), idPV, (j > 0 || t > 0) ? 1u : 0u);   // [Vhi | Vlo]
+      }
+    };
+    mma_issuer<4>(s.bars + w * B_PER_WG, w, nQT, T, issue_qk, issue_pv);
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int wg = warp >> 2, r = tid & 127;
+    uint64_t* bars = s.bars + wg * B_PER_WG;
+    const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * F4_CW);
+    const uint32_t tIN = tw + F4_IN, tOUT = tw + F4_OUT, tO = tw + F4_ACC, tQ = tw + F4_X;
+    WgPhase ph = {0, 0};
+    int it = 0;
+    for (int qt = wg; qt < nQT; qt += 4, ++it) {
+      const int i = qt * TCQ + r;
+      const bool valid = i < a.Lq;
+      if (T == 0) {       // every key masked: softmax of an empty set (the reference yields NaN)
+        if (valid) {
+          float* op = a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8;
+          for (int c = 0; c < 8; ++c) op[c] = __int_as_float(0x7fc00000);
+          a.LSE[(long long)nh * a.Lq + i] = -INFINITY;
+        }
+        continue;
+      }
+      {   // Q row -> TMEM (scaled, hi/lo split)
+        float q[8], hi[8], lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) q[c] = 0.f;
+        if (valid) {
+          ld8g(q, a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) q[c] *= kQScale;
+        }
+        split8(q, hi, lo);
+        tmem_put8(tQ, hi); tmem_put8(tQ + 8, lo);
+        tmem_wait_st();
+        fence_before();
+        mbar_arrive(&bars[B_X]);
+      }
+      const uint32_t rw = dc.on ? drop_row_word(dc, nh, a.Lq, valid ? i : 0) : 1u;
+      float m_used = -1e30f, lsum = 0.f;
+      for (int j = 0; j < T; ++j) {
+        ph.wait_s(bars);
+        const int nvalid = min(F4_FK, LkC - j * F4_FK);
+        uint32_t sr[64];
+        tmem_ld32(tIN, sr); tmem_ld32(tIN + 32, sr + 32);
+        tmem_wait_ld();
+        if (j + 1 < T) signal_in_free(bars);          // QK^T of the next tile runs under this tile's softmax
+        float mt = -1e30f;
+        if (nvalid == F4_FK) {
+#pragma unroll
+          for (int c = 0; c < 64; c += 2) mt = max3(mt, __uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) { if (c >= nvalid) sr[c] = 0xff800000u; mt = fmaxf(mt, __uint_as_float(sr[c])); }
+        }
+        const float m_new = fmaxf(m_used, mt);
+        const bool resc = __any_sync(0xffffffffu, m_new > m_used + kLazy);    // warp-uniform: TMEM ld/st are warp-collective
+        float alpha = 1.f;
+        if (resc) { alpha = ex2(m_used - m_new); lsum *= alpha; m_used = m_new; }   // first tile: 2^(-1e30 - m) = 0
+        uint32_t pk[32];
+        float l0 = 0.f, l1 = 0.f;                     // two partial sums: shorter dependency chains
+        if (!dc.on) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float p0 = ex2(__uint_as_float(sr[2 * c]) - m_used), p1 = ex2(__uint_as_float(sr[2 * c + 1]) - m_used);
+            l0 += p0; l1 += p1;
+            pk[c] = pack_h2(p0, p1);
+          }
+        } else {
+          const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * F4_FK);
+#pragma unroll
+          for (int cc = 0; cc < 16; ++cc) {
+            const uint4 bq = bw[cc];
+            const uint32_t bb[4] = {bq.x, bq.y, bq.z, bq.w};
+            float pp[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pp[e] = ex2(__uint_as_float(sr[cc * 4 + e]) - m_used);
+            l0 += pp[0] + pp[2]; l1 += pp[1] + pp[3];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pp[e] = (rw * bb[e] >= dc.thr) ? pp[e] : 0.f;
+            pk[cc * 2] = pack_h2(pp[0], pp[1]); pk[cc * 2 + 1] = pack_h2(pp[2], pp[3]);
+          }
+        }
+        lsum += l0 + l1;
+        if (j > 0) {
+          ph.wait_out_free(bars);                    // PV of tile j-1 has consumed OUT and updated O
+          if (resc) {
+            uint32_t o[16];
+            tmem_ld16(tO, o); tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st16(tO, o);
+          }
+        }
+        tmem_st32(tOUT, pk);
+        tmem_wait_st();
+        fence_before();
+        mbar_arrive(&bars[B_P]);
+      }
+      mbar_wait(&bars[B_O], it & 1);
+      fence_after();
+      uint32_t o[16];
+      tmem_ld16(tO, o); tmem_wait_ld();
+      if (valid) {
+        const float inv = dc.scale / lsum;
+        float out[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) out[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * inv;
+        st8g(a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8, out);
+        a.LSE[(long long)nh * a.Lq + i] = (m_used + log2f(lsum)) * kLn2;
+      }
+      fence_before();
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 16) { fence_after(); tmem_dealloc<512>(tb); }
 }
 
 // =================================================================================================
@@ -1226,6 +1416,13 @@ static int tc_configure(K k, size_t bytes, const char* what) {
 }
 
 int attn_tc_fwd(const AttnArgs& a, cudaStream_t st) {
+  static const bool two_wg = env_flag("VAESNE_TC_FWD2");      // the two-warpgroup forward (128-key tiles), kept for comparison
+  if (!two_wg) {
+    static int cfg4 = tc_configure(attn_tc_fwd4_kernel, FWD4_SMEM, "attn_tc_fwd4");
+    if (cfg4) return cfg4;
+    attn_tc_fwd4_kernel<<<dim3(kH, a.N), dim3(F4_THREADS), FWD4_SMEM, st>>>(a);
+    return check_launch("attn_tc_fwd4");
+  }
   static int cfg = tc_configure(attn_tc_fwd_kernel, FWD_SMEM, "attn_tc_fwd");
   if (cfg) return cfg;
   attn_tc_fwd_kernel<<<dim3(kH, a.N), dim3(NTHREADS), FWD_SMEM, st>>>(a);

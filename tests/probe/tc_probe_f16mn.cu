@@ -26,8 +26,8 @@ constexpr int A_SBO = 2048, A_LBO = 128, B_SBO = 2048, B_LBO = 128;
 __global__ void __launch_bounds__(128) probe(const __half* A, const __half* B, float* D, int M, int N, int lane_off, long long* clk, int reps, int indep) {
   extern __shared__ __align__(1024) unsigned char raw[];
   unsigned char* sA = raw;                      // 16 m-groups x 2048 B = 32 KB
-  unsigned char* sB = raw + 32768;              // 2 n-groups x 2048 B
-  uint64_t* bar = reinterpret_cast<uint64_t*>(raw + 32768 + 4096);
+  unsigned char* sB = raw + 32768;              // up to 16 n-groups x 2048 B
+  uint64_t* bar = reinterpret_cast<uint64_t*>(raw + 32768 + 32768);
   uint32_t* tmem_s = reinterpret_cast<uint32_t*>(bar + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < 128 * KT; i += 128) { const int m = i / KT, k = i % KT; *reinterpret_cast<__half*>(sA + mn_off(m, k, A_LBO, A_SBO)) = A[i]; }
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(128) probe(const __half* A, const __half* B, f
   if (tid == 0) mbar_init(bar, 1);
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   fence_async_smem();
-  if (warp == 0) tmem_alloc<64>(tmem_s);
+  if (warp == 0) tmem_alloc<512>(tmem_s);
   fence_before(); __syncthreads(); fence_after();
   const uint32_t tb = *tmem_s, tl = tb + ((uint32_t)(warp * 32) << 16);
   { uint32_t v[16]; for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(-777.f); tmem_st16(tl, v); tmem_st16(tl + 16, v); tmem_wait_st(); }
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128) probe(const __half* A, const __half* B, f
     const long long t0 = clock64();
     for (int r = 0; r < reps; ++r)
       for (int t = 0; t < KT / 16; ++t)
-        mma_ss_f16(dst + 16 + ((indep && (t & 1)) ? (16u << 16) : 0u), smem_desc(smem_u32(sA) + t * 256, A_LBO, A_SBO), smem_desc(smem_u32(sB) + t * 256, B_LBO, B_SBO), id, 1);
+        mma_ss_f16(dst + 256 + ((indep && (t & 1)) ? (16u << 16) : 0u), smem_desc(smem_u32(sA) + t * 256, A_LBO, A_SBO), smem_desc(smem_u32(sB) + t * 256, B_LBO, B_SBO), id, 1);
     commit(bar);
     const long long t1 = clock64();
     mbar_wait(bar, ph);
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) probe(const __half* A, const __half* B, f
   }
   __syncthreads();
   fence_before(); __syncthreads();
-  if (warp == 0) { fence_after(); tmem_dealloc<64>(tb); }
+  if (warp == 0) { fence_after(); tmem_dealloc<512>(tb); }
 }
 
 int main() {
@@ -79,14 +79,14 @@ int main() {
   __half *dA, *dB; float* dD; long long* dC;
   cudaMalloc(&dA, A.size() * 2); cudaMalloc(&dB, B.size() * 2); cudaMalloc(&dD, 128 * 16 * 4); cudaMalloc(&dC, 16);
   cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice); cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice);
-  const size_t smem = 32768 + 4096 + 64;
+  const size_t smem = 32768 + 32768 + 64;
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   std::vector<double> want(128 * 16);
   for (int m = 0; m < 128; ++m) for (int n = 0; n < 16; ++n) {
     double s = 0; for (int k = 0; k < KT; ++k) s += (double)__half2float(A[m * KT + k]) * __half2float(B[n * KT + k]);
     want[m * 16 + n] = s;
   }
-  const int cfg[][4] = {{128, 16, 0, 0}, {128, 8, 0, 0}, {64, 16, 0, 0}, {64, 8, 0, 0}, {64, 16, 16, 0}, {64, 8, 16, 0}, {64, 8, 0, 1}};
+  const int cfg[][4] = {{128, 16, 0, 0}, {128, 8, 0, 0}, {64, 16, 0, 0}, {64, 8, 0, 0}, {64, 16, 16, 0}, {64, 8, 16, 0}, {64, 8, 0, 1}, {128, 64, 0, 0}, {128, 96, 0, 0}, {128, 128, 0, 0}, {128, 32, 0, 0}};
   for (auto& c : cfg) {
     const int M = c[0], N = c[1], lo = c[2], reps = 64;
     probe<<<1, 128, smem>>>(dA, dB, dD, M, N, lo, dC, reps, c[3]);

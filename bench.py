@@ -352,6 +352,19 @@ def main():
             enc[name + "_latents_per_s"] = EB * 10 / (a.elapsed_time(b) * 1e-3)
             vae.train(was_training)
         enc["batch"] = EB
+        # paper-scale inference, reconstruct(data, K=100) — all four cross-modal decodes of K samples per object
+        # (decoder layer-0 self-attention is shared across the K samples and both sources: the queries are the data's embeddings)
+        RB, RK = 8, 100
+        xr = [tuple(t[:RB].contiguous() for t in mod) for mod in xd]
+        for _ in range(2):
+            model.reconstruct(xr, K=RK)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); a.record()
+        for _ in range(3):
+            model.reconstruct(xr, K=RK)
+        b.record(); torch.cuda.synchronize()
+        enc["reconstruct_K100_objects_per_s"] = RB * 3 / (a.elapsed_time(b) * 1e-3)
+        enc["reconstruct_batch"] = RB
         model.train()
 
     if rank != 0:

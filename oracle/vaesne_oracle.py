@@ -92,14 +92,14 @@ def div_term(dim: int, step: int, dtype) -> Tensor:
 
 def sinusoid(x: Tensor, dim: int) -> Tensor:
     """SinusoidalPositionalEmbedding.forward, util_layers.py:125-129."""
-    d = div_term(dim, 2, x.dtype)
+    d = div_term(dim, 2, x.dtype).to(x.device)
     a = x[..., None] * d
     return torch.cat([torch.sin(a), torch.cos(a)], dim=-1)
 
 
 def sinusoid_mlp(p: Params, name: str, x: Tensor, dim: int) -> Tensor:
     """SinusoidalMLPPositionalEmbedding.forward, util_layers.py:142-149."""
-    d = div_term(dim, 1, x.dtype)
+    d = div_term(dim, 1, x.dtype).to(x.device)        # the reference moves div_term to x.device on every call (:146)
     a = x[..., None] * d
     enc = torch.cat([torch.sin(a), torch.cos(a)], dim=-1)      # 2*dim wide
     return linear(p, name + ".fc2", F.relu(linear(p, name + ".fc1", enc)))
@@ -200,7 +200,7 @@ def spectra_encoder(p: Params, name: str, arg1, arg2, phase, mask, H: int, dropo
     phase_emb = sinusoid_mlp(p, name + ".phase_embd_layer", phase[:, None], D)
     ctx = torch.cat([emb, phase_emb], dim=1)
     if mask is not None:                            # :129-131, one extra un-masked key for the phase token
-        mask = torch.cat([mask, torch.zeros(mask.shape[0], 1, dtype=torch.bool)], dim=1)
+        mask = torch.cat([mask, torch.zeros(mask.shape[0], 1, dtype=torch.bool, device=mask.device)], dim=1)
     x = p[name + ".initbottleneck"][None].repeat(ctx.shape[0], 1, 1)
     h = x
     for i in range(_num_blocks(p, name)):
@@ -299,7 +299,7 @@ def vae_enc(p: Params, name: str, cfg: VAEConfig, x, dropout: float = 0.0) -> Tu
 def mask_scale(cfg: VAEConfig, mask: Tensor, dtype) -> Tensor:
     """PhotometricVAE.py:91-93 (1e8) / SpectraVAE.py:84-86 (1e10): ones + big*mask, evaluated in fp32."""
     big = 1e8 if cfg.kind == "photometry" else 1e10
-    s = torch.ones(mask.shape, dtype=torch.float32)
+    s = torch.ones(mask.shape, dtype=torch.float32, device=mask.device)
     s += big * mask
     return s.to(dtype)
 

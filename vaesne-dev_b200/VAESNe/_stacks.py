@@ -16,6 +16,8 @@ from __future__ import annotations
 import itertools
 from typing import Dict, List, Optional, Sequence
 
+import os
+
 import torch
 
 from . import _ops as P
@@ -255,14 +257,33 @@ def head(tape: Tape, pv: PView, prefix: str, X, Xadd):
 # ------------------------------------------------------------------------------------------------
 # TransformerBlock (util_layers.py:285-309)
 # ------------------------------------------------------------------------------------------------
-def block_forward(tape: Tape, pv: PView, pre: str, x, ctx, mask, ctx_mask, Nb: int, Lq: int, Lc: int):
-    """x [Nb*Lq, 32], ctx [Nb*Lc, 32] (2-D, contiguous) -> [Nb*Lq, 32]."""
+_NO_SHARED = os.environ.get("VAESNE_NO_SHARED_LAYER0", "0") not in ("", "0")      # A/B switch for the measurement in bench.py
+
+
+def block_forward(tape: Tape, pv: PView, pre: str, x, ctx, mask, ctx_mask, Nb: int, Lq: int, Lc: int, shared=None):
+    """x [Nb*Lq, 32], ctx [Nb*Lc, 32] (2-D, contiguous) -> [Nb*Lq, 32].
+
+    `shared = (xs, copies)`: x is `copies` replicas of xs [Nb/copies * Lq, 32] (a decoder's first block: its queries are
+    the position embeddings of the data, identical for all K samples and both sources).  Without dropout the first
+    sub-layer LN1(x + SelfMHA(x)) is then identical across the replicas as well, so it runs once per object and is
+    replicated afterwards — for the 982-token spectra decoder that removes one of its four 982 x 982 attentions from
+    (copies-1)/copies of the rows (reconstruct / generate at K=100; training only when dropout is 0, because the
+    reference draws an independent dropout mask per replica)."""
     sa, ca = _j(pre, "self_attn"), _j(pre, "cross_attn")
     pre = pre + "." if pre else ""
-    qkv = t_lin(tape, pv, x, sa + ".in_proj_weight", sa + ".in_proj_bias")
-    q3 = qkv.view(Nb, Lq, 96)
-    a = t_attn(tape, q3, q3[..., 0:32], q3, q3[..., 32:64], q3[..., 64:96], mask)
-    x1 = t_lin(tape, pv, a.view(Nb * Lq, 32), sa + ".out_proj.weight", sa + ".out_proj.bias", R=x, ln=pre + "layernorm1", dropout=True)
+    if shared is not None and tape.drop_p == 0.0 and shared[1] > 1 and not _NO_SHARED:
+        xs, copies = shared
+        Ns = Nb // copies
+        qkv = t_lin(tape, pv, xs, sa + ".in_proj_weight", sa + ".in_proj_bias")
+        q3 = qkv.view(Ns, Lq, 96)
+        a = t_attn(tape, q3, q3[..., 0:32], q3, q3[..., 32:64], q3[..., 64:96], mask)
+        x1s = t_lin(tape, pv, a.view(Ns * Lq, 32), sa + ".out_proj.weight", sa + ".out_proj.bias", R=xs, ln=pre + "layernorm1", dropout=True)
+        x1 = t_expand(tape, x1s.view(Ns, Lq * 32), copies).view(Nb * Lq, 32)
+    else:
+        qkv = t_lin(tape, pv, x, sa + ".in_proj_weight", sa + ".in_proj_bias")
+        q3 = qkv.view(Nb, Lq, 96)
+        a = t_attn(tape, q3, q3[..., 0:32], q3, q3[..., 32:64], q3[..., 64:96], mask)
+        x1 = t_lin(tape, pv, a.view(Nb * Lq, 32), sa + ".out_proj.weight", sa + ".out_proj.bias", R=x, ln=pre + "layernorm1", dropout=True)
 
     c = ctx
     if pv.has(pre + "context_self_attn.in_proj_weight"):        # :296-299, the update stays local to this block
@@ -372,7 +393,7 @@ def photo_decoder_forward(tape, pv: PView, aux, time, band, z, mask, copies: int
     ctx = mlp2(tape, pv, "contextfc", z.reshape(Nb * Tl, z.shape[2]))
     h = x0
     for i in range(_num_blocks(pv)):
-        h = block_forward(tape, pv, f"transformerblocks.{i}", h, ctx, mask, None, Nb, L, Tl)
+        h = block_forward(tape, pv, f"transformerblocks.{i}", h, ctx, mask, None, Nb, L, Tl, shared=(q0, copies) if i == 0 else None)
     return head(tape, pv, "get_photo", x0, h).view(Nb, L)
 
 
@@ -390,5 +411,5 @@ def spectra_decoder_forward(tape, pv: PView, aux, wavelength, phase, z, mask, co
     ctx = t_concat_tokens(tape, cz.view(Nb, Tl, 32), pe_n.view(Nb, 1, 32)).view(Nb * (Tl + 1), 32)
     h = x0
     for i in range(_num_blocks(pv)):
-        h = block_forward(tape, pv, f"transformerblocks.{i}", h, ctx, mask, None, Nb, L, Tl + 1)
+        h = block_forward(tape, pv, f"transformerblocks.{i}", h, ctx, mask, None, Nb, L, Tl + 1, shared=(q0, copies) if i == 0 else None)
     return head(tape, pv, "get_flux", x0, h).view(Nb, L)

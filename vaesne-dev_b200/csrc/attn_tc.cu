@@ -1077,6 +1077,7 @@ constexpr int C_DQ = 216;                    // per warpgroup: ACC = dK hi|lo (1
 constexpr int DS_BYTES = 64 * 128 * 2, KB_BYTES = 8 * 128 * 2;
 constexpr size_t BWD_SMEM = (size_t)5 * TILE_F * 4 + HALF_ARR * 2 + 2 * DS_BYTES + 2 * KB_BYTES + 3 * MAXL * 4 + MAXL * 2 + 32 * 4 + 36 * 4 + 16 * 8 + 16;
 static_assert(BWD_SMEM <= 232448, "fused backward does not fit the 227 KB shared-memory window");
+constexpr size_t BWD16_SMEM = BWD_SMEM - (size_t)4 * TILE_F * 4 + HALF_ARR * 2;      // no tf32 arrays, dO lo part added
 
 __device__ __forceinline__ void put_l2h_hi(__half* dst, int row, const float* x) {
   __half* p = dst + (row >> 4) * 128 + ((row >> 3) & 1) * 64 + (row & 7);
@@ -1093,14 +1094,20 @@ __device__ __forceinline__ void red_add8(float* p, const float* v) {
   }
 }
 
+// F16: the first products (S^T = K Q^T, T^T = V dO^T) also run as kind::f16 on fp16 hi/lo operands — K/V rows as
+// [hi | lo] half pairs in TMEM, and the SAME fp16 arrays the second products use ([d][query], 8x8 core matrices) read as
+// an MN-major B operand whose two 8-wide K chunks are the same memory (LBO = 0): [hi|lo] x [Qhi|Qhi] + [hi|0] x [Qlo|Qlo]
+// = hi*hi + lo*hi + hi*lo in TWO MMAs per product instead of three, and the four 32 KB tf32 arrays disappear.
+template <bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   TcSmem s;
   float* const f0 = reinterpret_cast<float*>(tc_smem_raw);
+  constexpr int NL1 = F16 ? 0 : 4;                                   // tf32 operand arrays of the first products
   float* Qhi = f0; float* Qlo = f0 + TILE_F; float* G1 = f0 + 2 * TILE_F; float* G1lo = f0 + 3 * TILE_F;
-  __half* Q2h = reinterpret_cast<__half*>(f0 + 4 * TILE_F);          // hi | lo
-  __half* G2h = reinterpret_cast<__half*>(f0 + 5 * TILE_F);          // hi only
-  unsigned char* const dsb = tc_smem_raw + (size_t)5 * TILE_F * 4 + HALF_ARR * 2;     // per warpgroup: dS^T tile (A of the dQ product)
+  __half* Q2h = reinterpret_cast<__half*>(f0 + NL1 * TILE_F);        // hi | lo
+  __half* G2h = reinterpret_cast<__half*>(f0 + (NL1 + 1) * TILE_F);  // hi (| lo with F16)
+  unsigned char* const dsb = tc_smem_raw + (size_t)(NL1 + 1) * TILE_F * 4 + (F16 ? 2 : 1) * HALF_ARR * 2;     // per warpgroup: dS^T tile (A of the dQ product)
   unsigned char* const kbb = dsb + 2 * DS_BYTES;                                      // per warpgroup: K rows (B of the dQ product)
   {
     float* f = reinterpret_cast<float*>(kbb + 2 * KB_BYTES);
@@ -1179,10 +1186,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
       float hi[8], lo[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) { q[u][c] *= kQScale; g[u][c] *= sc; }
-      split8(q[u], hi, lo);
-      put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l2h(Q2h, i, q[u]);
-      split8(g[u], hi, lo);
-      put_l1(G1, i, hi); put_l1(G1lo, i, lo); put_l2h_hi(G2h, i, g[u]);
+      if (F16) {
+        put_l2h(Q2h, i, q[u]); put_l2h(G2h, i, g[u]);
+      } else {
+        split8(q[u], hi, lo);
+        put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l2h(Q2h, i, q[u]);
+        split8(g[u], hi, lo);
+        put_l1(G1, i, hi); put_l1(G1lo, i, lo); put_l2h_hi(G2h, i, g[u]);
+      }
       s.f0[i] = -lse2[u]; s.f1[i] = -delta[u] * sc;
       s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
     }
@@ -1204,8 +1215,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     const uint32_t aQhi = smem_u32(Qhi), aQlo = smem_u32(Qlo), aG1 = smem_u32(G1), aG1lo = smem_u32(G1lo), aQ2 = smem_u32(Q2h), aG2 = smem_u32(G2h);
     const uint32_t aDS = smem_u32(dsb + w * DS_BYTES), aKB = smem_u32(kbb + w * KB_BYTES);
     const uint32_t tw = tb + (uint32_t)(w * C_WG);
+    const uint32_t idF = idesc_f16_mn(128, BK, false, true);
     auto issue_st = [&](int j) {
       const uint32_t d = tw + C_IN, x = tw + C_X;
+      if (F16) {       // B = [N = 64 queries][K = 8 features, read twice], MN-major view of the [d][query] fp16 arrays
+        const uint32_t off = (uint32_t)j * (BK / 8) * 128;
+        mma_ts_f16(d, x, smem_desc(aQ2 + off, 0, 128), idF, 0);                          // [Khi | Klo] x [Qhi | Qhi]
+        mma_ts_f16(d, x + 8, smem_desc(aQ2 + HALF_ARR * 2 + off, 0, 128), idF, 1);       // [Khi | 0  ] x [Qlo | Qlo]
+        mma_ts_f16(d + 64, x + 16, smem_desc(aG2 + off, 0, 128), idF, 0);                // [Vhi | Vlo] x [Ghi | Ghi]
+        mma_ts_f16(d + 64, x + 24, smem_desc(aG2 + HALF_ARR * 2 + off, 0, 128), idF, 1); // [Vhi | 0  ] x [Glo | Glo]
+        return;
+      }
       const uint64_t dQhi = smem_desc(aQhi + j * (BK * 32), 128, 256), dQlo = smem_desc(aQlo + j * (BK * 32), 128, 256);
       const uint64_t dGhi = smem_desc(aG1 + j * (BK * 32), 128, 256), dGlo = smem_desc(aG1lo + j * (BK * 32), 128, 256);
       mma_ts(d, x, dQhi, idS, 0);
@@ -1294,10 +1314,27 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
         ld8g(v, a.v + ((long long)n * a.Lk + jk) * a.ldv + h * 8);
       }
       *reinterpret_cast<uint4*>(kb_row) = make_uint4(pack_h2(k[0], k[1]), pack_h2(k[2], k[3]), pack_h2(k[4], k[5]), pack_h2(k[6], k[7]));
-      split8(k, hi, lo);
-      tmem_put8(tX, hi); tmem_put8(tX + 8, lo);
-      split8(v, hi, lo);
-      tmem_put8(tX + 16, hi); tmem_put8(tX + 24, lo);
+      if (F16) {       // A operands: columns 0-3 = hi pairs, 4-7 = lo pairs (K index 0-7 hi, 8-15 lo); second operand: [hi | 0]
+        uint32_t xa[8], xb[8];
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const float* src = pass ? v : k;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const __half2 h2 = __floats2half2_rn(src[2 * c], src[2 * c + 1]);
+            const float2 hf = __half22float2(h2);
+            xa[c] = *reinterpret_cast<const uint32_t*>(&h2);
+            xa[4 + c] = pack_h2(src[2 * c] - hf.x, src[2 * c + 1] - hf.y);
+            xb[c] = xa[c]; xb[4 + c] = 0u;
+          }
+          tmem_st8(tX + pass * 16, xa); tmem_st8(tX + pass * 16 + 8, xb);
+        }
+      } else {
+        split8(k, hi, lo);
+        tmem_put8(tX, hi); tmem_put8(tX + 8, lo);
+        split8(v, hi, lo);
+        tmem_put8(tX + 16, hi); tmem_put8(tX + 24, lo);
+      }
       fence_async_smem();
       tmem_wait_st();
       fence_before();
@@ -1432,10 +1469,17 @@ int attn_tc_fwd(const AttnArgs& a, cudaStream_t st) {
 int attn_tc_bwd(const AttnArgs& a, cudaStream_t st) {
   static const bool split = env_flag("VAESNE_TC_BWD_SPLIT");      // the two-pass backward (dq kernel + key-major kernel), kept for comparison
   if (!split) {
-    static int cfg = tc_configure(attn_tc_bwd_kernel, BWD_SMEM, "attn_tc_bwd");
-    if (cfg) return cfg;
-    attn_tc_bwd_kernel<<<dim3(kH, a.N), dim3(NTHREADS), BWD_SMEM, st>>>(a);
-    return check_launch("attn_tc_bwd");
+    static const bool tf32_first = env_flag("VAESNE_TC_BWD_TF32");      // first products as 3xTF32 (kept for comparison)
+    if (tf32_first) {
+      static int cfg = tc_configure(attn_tc_bwd_kernel<false>, BWD_SMEM, "attn_tc_bwd");
+      if (cfg) return cfg;
+      attn_tc_bwd_kernel<false><<<dim3(kH, a.N), dim3(NTHREADS), BWD_SMEM, st>>>(a);
+      return check_launch("attn_tc_bwd");
+    }
+    static int cfg16 = tc_configure(attn_tc_bwd_kernel<true>, BWD16_SMEM, "attn_tc_bwd16");
+    if (cfg16) return cfg16;
+    attn_tc_bwd_kernel<true><<<dim3(kH, a.N), dim3(NTHREADS), BWD16_SMEM, st>>>(a);
+    return check_launch("attn_tc_bwd16");
   }
   static int cfg1 = tc_configure(attn_tc_dq_kernel, DQ_SMEM, "attn_tc_dq");
   static int cfg2 = tc_configure(attn_tc_dkv_kernel, DKV_SMEM, "attn_tc_dkv");

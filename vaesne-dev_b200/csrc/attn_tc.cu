@@ -1067,23 +1067,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
 // backward, fused single pass (default): the key-major pass above extended by dQ, so S, P, dP and dS are computed ONCE.
 // dQ = scale * sum_keys dS[query, key] K[key] contracts over the TMEM-lane index of dS^T, which no TMEM operand can do;
 // the warpgroup therefore also writes dS^T (the fp16 pairs it stores to TMEM anyway) to shared memory as an MN-major
-// A operand [64 queries x 128 keys] (eight conflict-free 16-byte stores per thread), this key tile's K rows sit next to it as
-// an MN-major B operand, and 8 SS MMAs (M=64, N=8, K=16) produce the tile's dQ contribution in 8 TMEM columns
-// (row m -> lane (m&15) + 32*(m>>4)).  One CTA owns all of dq[n, :, h], so the contributions of its key tiles are summed
+// A operand [queries x 128 keys] (eight conflict-free 16-byte stores per thread and tile), this key tile's K rows sit next to it
+// as an MN-major B operand, and every second query tile 8 SS MMAs (M=128 = two query tiles, N=8, K=16) produce the pair's dQ
+// contribution in 8 TMEM columns (row m -> lane m).  One CTA owns all of dq[n, :, h], so the contributions of its key tiles are summed
 // with vector reductions into the zero-initialised output — no second pass, no extra exponentials.
-// To make room (shared memory and TMEM are both full) the dV product takes dO as fp16 hi only and dQ takes K as fp16 hi only.
+// TMEM is full (IN 128 | OUT 64 | ACC 32 | X 32 per warpgroup), so the dV product takes dO as fp16 hi only and dQ takes K as
+// fp16 hi only (their accumulators are 8 columns instead of 16).  fp16 operands assume |q|, |k|, |v| < 65504 (they are
+// projections of LayerNorm outputs); dO is normalised per (row, head) by an exact power of two.
 // =================================================================================================
 constexpr int C_DQ = 216;                    // per warpgroup: ACC = dK hi|lo (192..207) | dV (208..215) | dQ tile (216..223)
-constexpr int DS_BYTES = 64 * 128 * 2, KB_BYTES = 8 * 128 * 2;
-constexpr size_t BWD_SMEM = (size_t)5 * TILE_F * 4 + HALF_ARR * 2 + 2 * DS_BYTES + 2 * KB_BYTES + 3 * MAXL * 4 + MAXL * 2 + 32 * 4 + 36 * 4 + 16 * 8 + 16;
+constexpr int DS_BYTES = 128 * 128 * 2, KB_BYTES = 8 * 128 * 2;      // dS^T of a tile pair (128 queries x 128 keys fp16), K rows
+constexpr size_t BWD_SMEM = (size_t)2 * TILE_F * 4 + 2 * DS_BYTES + 2 * KB_BYTES + 3 * MAXL * 4 + MAXL * 2 + 32 * 4 + 36 * 4 + 16 * 8 + 16;
 static_assert(BWD_SMEM <= 232448, "fused backward does not fit the 227 KB shared-memory window");
-constexpr size_t BWD16_SMEM = BWD_SMEM - (size_t)4 * TILE_F * 4 + HALF_ARR * 2;      // no tf32 arrays, dO lo part added
 
-__device__ __forceinline__ void put_l2h_hi(__half* dst, int row, const float* x) {
-  __half* p = dst + (row >> 4) * 128 + ((row >> 3) & 1) * 64 + (row & 7);
-#pragma unroll
-  for (int d = 0; d < 8; ++d) p[d * 8] = __float2half_rn(x[d]);
-}
 __device__ __forceinline__ void red_add8(float* p, const float* v) {
   if (((uintptr_t)p & 15) == 0) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
@@ -1094,20 +1090,18 @@ __device__ __forceinline__ void red_add8(float* p, const float* v) {
   }
 }
 
-// F16: the first products (S^T = K Q^T, T^T = V dO^T) also run as kind::f16 on fp16 hi/lo operands — K/V rows as
+// The first products (S^T = K Q^T, T^T = V dO^T) run as kind::f16 on fp16 hi/lo operands as well — K/V rows as
 // [hi | lo] half pairs in TMEM, and the SAME fp16 arrays the second products use ([d][query], 8x8 core matrices) read as
 // an MN-major B operand whose two 8-wide K chunks are the same memory (LBO = 0): [hi|lo] x [Qhi|Qhi] + [hi|0] x [Qlo|Qlo]
-// = hi*hi + lo*hi + hi*lo in TWO MMAs per product instead of three, and the four 32 KB tf32 arrays disappear.
-template <bool F16>
+// = hi*hi + lo*hi + hi*lo in TWO MMAs per product instead of three (3xTF32 needed three and four more 32 KB arrays).
+// The shared memory this frees holds dS^T of TWO query tiles, so the dQ product runs once per tile pair with M = 128.
 __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   TcSmem s;
   float* const f0 = reinterpret_cast<float*>(tc_smem_raw);
-  constexpr int NL1 = F16 ? 0 : 4;                                   // tf32 operand arrays of the first products
-  float* Qhi = f0; float* Qlo = f0 + TILE_F; float* G1 = f0 + 2 * TILE_F; float* G1lo = f0 + 3 * TILE_F;
-  __half* Q2h = reinterpret_cast<__half*>(f0 + NL1 * TILE_F);        // hi | lo
-  __half* G2h = reinterpret_cast<__half*>(f0 + (NL1 + 1) * TILE_F);  // hi (| lo with F16)
-  unsigned char* const dsb = tc_smem_raw + (size_t)(NL1 + 1) * TILE_F * 4 + (F16 ? 2 : 1) * HALF_ARR * 2;     // per warpgroup: dS^T tile (A of the dQ product)
+  __half* Q2h = reinterpret_cast<__half*>(f0);                       // Q  hi | lo  ([d][query] fp16, 16 KB each)
+  __half* G2h = reinterpret_cast<__half*>(f0 + TILE_F);              // dO hi | lo
+  unsigned char* const dsb = tc_smem_raw + (size_t)2 * TILE_F * 4;   // per warpgroup: dS^T of a tile pair (A of the dQ product)
   unsigned char* const kbb = dsb + 2 * DS_BYTES;                                      // per warpgroup: K rows (B of the dQ product)
   {
     float* f = reinterpret_cast<float*>(kbb + 2 * KB_BYTES);
@@ -1183,17 +1177,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     for (int u = 0; u < RPT; ++u) {
       const int i = tid + u * NTHREADS;
       if (i >= NQ * BK) continue;
-      float hi[8], lo[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) { q[u][c] *= kQScale; g[u][c] *= sc; }
-      if (F16) {
-        put_l2h(Q2h, i, q[u]); put_l2h(G2h, i, g[u]);
-      } else {
-        split8(q[u], hi, lo);
-        put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l2h(Q2h, i, q[u]);
-        split8(g[u], hi, lo);
-        put_l1(G1, i, hi); put_l1(G1lo, i, lo); put_l2h_hi(G2h, i, g[u]);
-      }
+      put_l2h(Q2h, i, q[u]); put_l2h(G2h, i, g[u]);
       s.f0[i] = -lse2[u]; s.f1[i] = -delta[u] * sc;
       s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
     }
@@ -1211,28 +1197,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     const int w = warp - 8;
     uint64_t* b = s.bars + w * B_PER_WG;
     uint64_t* bdq = s.bars + 12 + w;
-    const uint32_t idS = idesc_tf32(128, BK), idK = idesc_f16(128, 16), idV = idesc_f16(128, 8), idQ = idesc_f16_mn(64, 8, true, true);
-    const uint32_t aQhi = smem_u32(Qhi), aQlo = smem_u32(Qlo), aG1 = smem_u32(G1), aG1lo = smem_u32(G1lo), aQ2 = smem_u32(Q2h), aG2 = smem_u32(G2h);
+    const uint32_t idK = idesc_f16(128, 16), idV = idesc_f16(128, 8), idQ = idesc_f16_mn(128, 8, true, true);
+    const uint32_t aQ2 = smem_u32(Q2h), aG2 = smem_u32(G2h);
     const uint32_t aDS = smem_u32(dsb + w * DS_BYTES), aKB = smem_u32(kbb + w * KB_BYTES);
     const uint32_t tw = tb + (uint32_t)(w * C_WG);
     const uint32_t idF = idesc_f16_mn(128, BK, false, true);
     auto issue_st = [&](int j) {
       const uint32_t d = tw + C_IN, x = tw + C_X;
-      if (F16) {       // B = [N = 64 queries][K = 8 features, read twice], MN-major view of the [d][query] fp16 arrays
-        const uint32_t off = (uint32_t)j * (BK / 8) * 128;
-        mma_ts_f16(d, x, smem_desc(aQ2 + off, 0, 128), idF, 0);                          // [Khi | Klo] x [Qhi | Qhi]
-        mma_ts_f16(d, x + 8, smem_desc(aQ2 + HALF_ARR * 2 + off, 0, 128), idF, 1);       // [Khi | 0  ] x [Qlo | Qlo]
-        mma_ts_f16(d + 64, x + 16, smem_desc(aG2 + off, 0, 128), idF, 0);                // [Vhi | Vlo] x [Ghi | Ghi]
-        mma_ts_f16(d + 64, x + 24, smem_desc(aG2 + HALF_ARR * 2 + off, 0, 128), idF, 1); // [Vhi | 0  ] x [Glo | Glo]
-        return;
-      }
-      const uint64_t dQhi = smem_desc(aQhi + j * (BK * 32), 128, 256), dQlo = smem_desc(aQlo + j * (BK * 32), 128, 256);
-      const uint64_t dGhi = smem_desc(aG1 + j * (BK * 32), 128, 256), dGlo = smem_desc(aG1lo + j * (BK * 32), 128, 256);
-      mma_ts(d, x, dQhi, idS, 0);
-      mma_ts(d, x + 8, dQhi, idS, 1);
-      mma_ts(d, x, dQlo, idS, 1);
-      mma_ts(d + 64, x + 16, dGhi, idS, 0);
-      if (kSplitT) { mma_ts(d + 64, x + 24, dGhi, idS, 1); mma_ts(d + 64, x + 16, dGlo, idS, 1); }
+      // B = [N = 64 queries][K = 8 features, read twice], MN-major view of the [d][query] fp16 arrays
+      const uint32_t off = (uint32_t)j * (BK / 8) * 128;
+      mma_ts_f16(d, x, smem_desc(aQ2 + off, 0, 128), idF, 0);                          // [Khi | Klo] x [Qhi | Qhi]
+      mma_ts_f16(d, x + 8, smem_desc(aQ2 + HALF_ARR * 2 + off, 0, 128), idF, 1);       // [Khi | 0  ] x [Qlo | Qlo]
+      mma_ts_f16(d + 64, x + 16, smem_desc(aG2 + off, 0, 128), idF, 0);                // [Vhi | Vlo] x [Ghi | Ghi]
+      mma_ts_f16(d + 64, x + 24, smem_desc(aG2 + HALF_ARR * 2 + off, 0, 128), idF, 1); // [Vhi | 0  ] x [Glo | Glo]
     };
     uint32_t cF = 0, cP = 0;
     int it = 0;
@@ -1265,9 +1242,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
             mma_ts_f16(dK, tw + C_OUT + 32 + (uint32_t)t * 8, smem_desc(aQ2 + off, 128, HALF_ARR * 2), idK, acc);     // dS^T [Qhi | Qlo]
           }
           if (!last) commit(&b[B_OF]);
-          for (int t = 0; t < ksteps; ++t)                                                                             // dS K -> dQ tile
-            mma_ss_f16(tw + C_DQ, smem_desc(aDS + t * 256, 128, 2048), smem_desc(aKB + t * 256, 128, 2048), idQ, t > 0 ? 1u : 0u);
-          commit(last ? &b[B_O] : bdq);
+          if (((j - jb) & 1) || last) {                    // dS K -> dQ of the tile pair (M = 128: two 64-query tiles)
+            for (int t = 0; t < ksteps; ++t)
+              mma_ss_f16(tw + C_DQ, smem_desc(aDS + t * 256, 128, 2048), smem_desc(aKB + t * 256, 128, 2048), idQ, t > 0 ? 1u : 0u);
+            commit(last ? &b[B_O] : bdq);
+          }
         }
         __syncwarp();
       }
@@ -1287,12 +1266,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
 #ifdef VAESNE_TC_PROFILE
     long long prof[16] = {0}; const long long tstart = clock64(); prof[6] = tstart - tk0;
 #endif
-    // dQ contribution of query tile jq: accumulator row m (query jq*64 + m) sits in lane (m&15) + 32*(m>>4)
-    auto drain_dq = [&](int jq) {
+    // dQ contribution of the tile pair starting at query tile jq: accumulator row m (query jq*64 + m) sits in lane m
+    auto drain_dq = [&](int jq, int nrows) {
       uint32_t v[8];
       tmem_ld8(tw + C_DQ, v); tmem_wait_ld();
-      const int i = jq * BK + (warp & 3) * 16 + lane;
-      if (lane < 16 && i < a.Lq) {
+      const int i = jq * BK + r;
+      if (r < nrows && i < a.Lq) {
         float o[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) o[c] = __uint_as_float(v[c]) * dq_scale;
@@ -1306,7 +1285,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
       const int cs = kt * TCQ + r;
       const bool valid = cs < LkC;
       const int jk = valid ? (int)s.idx[cs] : 0;
-      float k[8], v[8], hi[8], lo[8];
+      float k[8], v[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) { k[c] = 0.f; v[c] = 0.f; }
       if (valid) {
@@ -1314,7 +1293,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
         ld8g(v, a.v + ((long long)n * a.Lk + jk) * a.ldv + h * 8);
       }
       *reinterpret_cast<uint4*>(kb_row) = make_uint4(pack_h2(k[0], k[1]), pack_h2(k[2], k[3]), pack_h2(k[4], k[5]), pack_h2(k[6], k[7]));
-      if (F16) {       // A operands: columns 0-3 = hi pairs, 4-7 = lo pairs (K index 0-7 hi, 8-15 lo); second operand: [hi | 0]
+      {                // A operands: columns 0-3 = hi pairs, 4-7 = lo pairs (K index 0-7 hi, 8-15 lo); second operand: [hi | 0]
         uint32_t xa[8], xb[8];
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
@@ -1329,11 +1308,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
           }
           tmem_st8(tX + pass * 16, xa); tmem_st8(tX + pass * 16 + 8, xb);
         }
-      } else {
-        split8(k, hi, lo);
-        tmem_put8(tX, hi); tmem_put8(tX + 8, lo);
-        split8(v, hi, lo);
-        tmem_put8(tX + 16, hi); tmem_put8(tX + 24, lo);
       }
       fence_async_smem();
       tmem_wait_st();
@@ -1385,11 +1359,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
           }
         }
         TPROF_ADD(1, clock64() - tc0);
-        if (j > jb) {
-          TPROF(5, ph.wait_out_free(bars));
-          TPROF(7, mbar_wait(bdq, cdq & 1)); cdq++;       // dQ product of tile j-1 done: its accumulator can be read, the dS^T slot rewritten
+        const int par = (j - jb) & 1;
+        if (j > jb) TPROF(5, ph.wait_out_free(bars));
+        if (par == 0 && j > jb) {
+          TPROF(7, mbar_wait(bdq, cdq & 1)); cdq++;       // dQ product of the previous tile pair done: read its accumulator, reuse the dS^T buffer
           fence_after();
-          TPROF(8, drain_dq(j - 1));
+          TPROF(8, drain_dq(j - 2, 2 * BK));
         }
 #ifdef VAESNE_TC_PROFILE
         const long long ts0 = clock64();
@@ -1398,7 +1373,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
         // padded key rows (zero K, but P = 2^(-lse) may be huge) must contribute exact zeros to dQ
 #pragma unroll
         for (int g8 = 0; g8 < 8; ++g8)
-          *reinterpret_cast<uint4*>(ds_row + g8 * 2048) = valid ? make_uint4(dk2[g8 * 4], dk2[g8 * 4 + 1], dk2[g8 * 4 + 2], dk2[g8 * 4 + 3]) : make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(ds_row + (par * 8 + g8) * 2048) = valid ? make_uint4(dk2[g8 * 4], dk2[g8 * 4 + 1], dk2[g8 * 4 + 2], dk2[g8 * 4 + 3]) : make_uint4(0u, 0u, 0u, 0u);
         fence_async_smem();
         tmem_wait_st();
         fence_before();
@@ -1407,7 +1382,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
       }
       TPROF(3, mbar_wait(&bars[B_O], it & 1));
       fence_after();
-      drain_dq(je - 1);
+      if ((je - jb) & 1) drain_dq(je - 1, BK); else drain_dq(je - 2, 2 * BK);     // an odd last tile sits alone in rows 0..63
       uint32_t o[24];
       tmem_ld16(tA, o); tmem_ld8(tA + 16, o + 16); tmem_wait_ld();
       if (valid) {
@@ -1469,17 +1444,10 @@ int attn_tc_fwd(const AttnArgs& a, cudaStream_t st) {
 int attn_tc_bwd(const AttnArgs& a, cudaStream_t st) {
   static const bool split = env_flag("VAESNE_TC_BWD_SPLIT");      // the two-pass backward (dq kernel + key-major kernel), kept for comparison
   if (!split) {
-    static const bool tf32_first = env_flag("VAESNE_TC_BWD_TF32");      // first products as 3xTF32 (kept for comparison)
-    if (tf32_first) {
-      static int cfg = tc_configure(attn_tc_bwd_kernel<false>, BWD_SMEM, "attn_tc_bwd");
-      if (cfg) return cfg;
-      attn_tc_bwd_kernel<false><<<dim3(kH, a.N), dim3(NTHREADS), BWD_SMEM, st>>>(a);
-      return check_launch("attn_tc_bwd");
-    }
-    static int cfg16 = tc_configure(attn_tc_bwd_kernel<true>, BWD16_SMEM, "attn_tc_bwd16");
-    if (cfg16) return cfg16;
-    attn_tc_bwd_kernel<true><<<dim3(kH, a.N), dim3(NTHREADS), BWD16_SMEM, st>>>(a);
-    return check_launch("attn_tc_bwd16");
+    static int cfg = tc_configure(attn_tc_bwd_kernel, BWD_SMEM, "attn_tc_bwd");
+    if (cfg) return cfg;
+    attn_tc_bwd_kernel<<<dim3(kH, a.N), dim3(NTHREADS), BWD_SMEM, st>>>(a);
+    return check_launch("attn_tc_bwd");
   }
   static int cfg1 = tc_configure(attn_tc_dq_kernel, DQ_SMEM, "attn_tc_dq");
   static int cfg2 = tc_configure(attn_tc_dkv_kernel, DKV_SMEM, "attn_tc_dkv");

@@ -1,0 +1,58 @@
+"""The comparison paths kept next to the default kernels stay correct: the two-warpgroup forward (VAESNE_TC_FWD2), the
+two-pass backward (VAESNE_TC_BWD_SPLIT) and the general kernels behind the specialised ones (VAESNE_NO_MID_ATTN,
+VAESNE_NO_SMALL_ATTN).  The switches are read once per process, so each combination runs in a child process."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CHILD = r"""
+import sys, os
+sys.path[:0] = [os.path.join(ROOT, "tests"), os.path.join(ROOT, "vaesne-dev_b200"), ROOT]
+import torch
+import ops_cases as OC
+from helpers import rel_err
+from VAESNe import _ops as P
+dev = "cuda"
+worst = 0.0
+for c in CASES:
+    (q, k, v, mask, mask_full, dO), (qd, kd, vd) = OC.make_attn_inputs(c, dev, 1.0)
+    o_ref, lse_ref, dq_ref, dk_ref, dv_ref = OC.attn_reference(q, k, v, mask_full, dO)
+    md = mask.to(dev) if mask is not None else None
+    O, LSE = P.attn_fwd(qd, kd, vd, md)
+    if c["packed"] == "qkv":
+        dqkv = torch.zeros(c["N"], c["Lq"], 96, device=dev); dq, dk, dv = dqkv[..., :32], dqkv[..., 32:64], dqkv[..., 64:]
+    else:
+        dq = torch.zeros(c["N"], c["Lq"], 32, device=dev); dkv = torch.zeros(c["N"], c["Lk"], 64, device=dev); dk, dv = dkv[..., :32], dkv[..., 32:]
+    P.attn_bwd(qd, kd, vd, md, O, LSE, dO.to(dev), dq, dk, dv)
+    torch.cuda.synchronize()
+    errs = [rel_err(O.cpu(), o_ref), rel_err(LSE.cpu(), lse_ref), rel_err(dq.cpu(), dq_ref), rel_err(dk.cpu(), dk_ref), rel_err(dv.cpu(), dv_ref)]
+    assert max(errs) < TOL, (c["id"], errs)
+    worst = max(worst, max(errs))
+print("ok", worst)
+"""
+
+
+def _run(env, cases, tol):
+    code = f"ROOT = {ROOT!r}\nCASES = {cases!r}\nTOL = {tol}\n" + CHILD
+    e = dict(os.environ, **env)
+    out = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().startswith("ok"), out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_two_warpgroup_forward_and_two_pass_backward():
+    cases = [dict(id="self_982_mask_rowmod", N=4, Lq=982, Lk=982, mask=True, mask_rows=2, packed="qkv"),
+             dict(id="self_300x260_mask", N=3, Lq=300, Lk=260, mask=True, packed="q+kv")]
+    _run({"VAESNE_TC_FWD2": "1", "VAESNE_TC_BWD_SPLIT": "1"}, cases, 1e-3)
+
+
+def test_general_kernels_behind_the_specialised_ones():
+    cases = [dict(id="self_60x60_mask_rowmod", N=4, Lq=60, Lk=60, mask=True, mask_rows=2, packed="qkv"),
+             dict(id="cross_60x4", N=2, Lq=60, Lk=4, mask=False, packed="q+kv"),
+             dict(id="cross_8x61_mask", N=2, Lq=8, Lk=61, mask=True, mask_len=60, packed="q+kv")]
+    _run({"VAESNE_NO_MID_ATTN": "1", "VAESNE_NO_SMALL_ATTN": "1"}, cases, 2e-5)

@@ -31,8 +31,8 @@ sys.path.insert(0, "/root/reference/package")
 import torch.distributions as dist  # noqa: E402
 from oracle import vaesne_oracle as O  # noqa: E402
 
-from VAESNe.PhotometricVAE import PhotometricVAE  # noqa: E402  (reference)
-from VAESNe.SpectraVAE import SpectraVAE  # noqa: E402
+from VAESNe.PhotometricVAE import PhotometricVAE, BrightPhotometricVAE  # noqa: E402  (reference)
+from VAESNe.SpectraVAE import SpectraVAE, BrightSpectraVAE  # noqa: E402
 from VAESNe.mmVAE import photospecMMVAE  # noqa: E402
 from VAESNe.losses import elbo, m_iwae, negInfoNCE  # noqa: E402
 from VAESNe.contrastiveNets import ContraPhotSpec  # noqa: E402
@@ -112,6 +112,29 @@ def case_spec_elbo():
     enc_mean = m.encode(x)
     save("spec_elbo", seed=12, noise_seed=102, u=u.numpy(), loss=loss.item(), loc=px.loc.numpy(), zs=zs.numpy(),
          mu=qz.loc.numpy(), scale=qz.scale.numpy(), enc_mean=enc_mean.numpy(), **pack_x("x", x), **grads_of(m))
+
+
+def _bright(m, x, seed, noise_seed, K, name, ushape):
+    load_random(m, seed)
+    (u,) = record_noise(noise_seed, [ushape])
+    m.train()
+    loss = elbo(m, x, K=K)
+    loss.backward()
+    torch.manual_seed(noise_seed)
+    with torch.no_grad():
+        qz, px, zs = m(x, K)
+    save(name, seed=seed, noise_seed=noise_seed, K=K, u=u.numpy(), loss=loss.item(), loc=px.loc.numpy(), zs=zs.numpy(),
+         mu=qz.loc.numpy(), scale=qz.scale.numpy(), **pack_x("x", x), **grads_of(m))
+
+
+def case_bright():
+    """Bright variants (imported by cannon/ZTF_photospect.py:12-13, test_photospectra.py:12-13): K=2 ELBO, dropout 0."""
+    m = BrightPhotometricVAE(num_bands=6, latent_len=4, latent_dim=2, model_dim=32, num_heads=4, ff_dim=32,
+                             num_layers=2, dropout=0.0, selfattn=False, beta=0.5)
+    _bright(m, O.synth_photometry(3, 60, 6, seed=31), 31, 131, 2, "bright_photo_elbo", (2, 3, 4, 2))
+    m = BrightSpectraVAE(latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=2,
+                         dropout=0.0, selfattn=False, beta=1.0)
+    _bright(m, O.synth_spectra(2, 300, seed=32), 32, 132, 2, "bright_spec_elbo", (2, 2, 4, 4))
 
 
 def _mm(num_bands, K, B, beta, selfattn_spec, seed, noise_seed, name, Lp=60, Ls=982, family=dist.Laplace):
@@ -212,3 +235,4 @@ if __name__ == "__main__":
     case_mm_normal()
     case_contrast()
     case_end2end()
+    case_bright()

@@ -49,6 +49,7 @@ class VAEConfig:
     likelihood: str = "laplace"
     posterior: str = "laplace"
     llik_scaling: Optional[float] = None  # default 1/beta (PhotometricVAE.py:151)
+    bright: bool = False        # BrightPhotometricVAE / BrightSpectraVAE: brightness token + mean-centred reconstruction
 
     def scaling(self) -> float:
         return (1.0 / self.beta) if self.llik_scaling is None else self.llik_scaling
@@ -316,8 +317,14 @@ def vae_decode(p: Params, name: str, cfg: VAEConfig, zs: Tensor, x, dropout: flo
         _, wavelength, phase, mask = x
         loc = spectra_decoder(p, name + ".dec.generativetransformer", ex(wavelength), ex(phase), zf, ex(mask), cfg.num_heads, dropout)
     L = loc.shape[-1]
+    loc = loc.reshape(K, B, L)
+    if cfg.bright:      # Bright*VAE.decode: PhotometricVAE.py:318-332 / SpectraVAE.py:308-322
+        feats = zs[:, :, 0, :]
+        if cfg.kind == "spectra":
+            feats = torch.cat([feats, x[2][None, :, None].expand(K, B, 1)], dim=-1)
+        loc = loc + mlp(p, name + ".brightnessfc", feats) - loc.mean(dim=2)[:, :, None]
     scale = mask_scale(cfg, mask, loc.dtype)[None].expand(K, B, L)
-    return loc.reshape(K, B, L), scale
+    return loc, scale
 
 
 def vae_forward(p: Params, name: str, cfg: VAEConfig, x, noise: Tensor, dropout: float = 0.0):

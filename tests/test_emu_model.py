@@ -39,3 +39,8 @@ def test_mm_goldstein(emu):
 
 def test_mm_ztf(emu):
     MC.run_mm_case("mm_ztf", "cpu")
+
+
+@pytest.mark.parametrize("name", ["bright_photo_elbo", "bright_spec_elbo"])
+def test_bright_variants(emu, name):
+    MC.run_bright_case(name, "cpu")

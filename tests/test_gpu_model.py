@@ -28,3 +28,8 @@ def test_end2end(name):
 
 def test_regression_head_encode_path():
     MC.run_reghead_case("cuda")
+
+
+@pytest.mark.parametrize("name", ["bright_photo_elbo", "bright_spec_elbo"])
+def test_bright_variants(name):
+    MC.run_bright_case(name, "cuda")

@@ -9,6 +9,7 @@ from . import _ops as P
 from ._functions import latent_step
 from ._vae_common import FusedVAEMixin, masked_scale_tensor
 from .base_vae import VAE
+from .util_layers import MLP
 from .PhotometricLayers import photometricTransformerDecoder, photometricTransformerEncoder
 
 
@@ -81,3 +82,21 @@ class PhotometricVAE(FusedVAEMixin, VAE):
             pz = self.pz(*self.pz_params)
             zs = pz.rsample(torch.Size([N, time.shape[0]]))
             return self._decode_loc(zs, (None, time, band, mask))
+
+
+class BrightPhotometricVAE(PhotometricVAE):
+    """Drop-in for ``BrightPhotometricVAE`` (reference ``PhotometricVAE.py:225-332``): the first latent token carries the
+    overall brightness — ``loc = dec(z) - mean_L(dec(z)) + brightnessfc(z[:, :, 0, :])``.  Same encoder / decoder stacks
+    and fused objectives as ``PhotometricVAE``; the brightness head is a 2-layer MLP on K*B rows."""
+
+    def __init__(self, num_bands=6, latent_len=8, latent_dim=4, model_dim=64, num_heads=4, ff_dim=64, num_layers=4,
+                 dropout=0.1, selfattn=False, beta=1., prior=dist.Laplace, likelihood=dist.Laplace, posterior=dist.Laplace):
+        assert latent_len > 1, "first token for overall brightness"
+        super().__init__(num_bands, latent_len, latent_dim, model_dim, num_heads, ff_dim, num_layers, dropout, selfattn,
+                         True, beta, prior, likelihood, posterior)
+        self.brightnessfc = MLP(latent_dim, 1, [model_dim])
+
+    def _decode_loc(self, zs, x, copies=None):
+        loc = super()._decode_loc(zs, x)
+        brightness = self.brightnessfc(zs[:, :, 0, :])                       # [R, B, 1]
+        return loc + brightness - loc.mean(dim=2, keepdim=True)

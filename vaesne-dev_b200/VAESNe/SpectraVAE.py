@@ -7,6 +7,7 @@ from torch import nn
 from ._functions import latent_step
 from ._vae_common import FusedVAEMixin, masked_scale_tensor
 from .base_vae import VAE
+from .util_layers import MLP
 from .SpectraLayers import spectraTransformerDecoder, spectraTransformerEncoder
 
 
@@ -78,3 +79,22 @@ class SpectraVAE(FusedVAEMixin, VAE):
         with torch.no_grad():
             zs = self.pz(*self.pz_params).rsample(torch.Size([N, 1]))
             return self._decode_loc(zs, x).unsqueeze(0)
+
+
+class BrightSpectraVAE(SpectraVAE):
+    """Drop-in for ``BrightSpectraVAE`` (reference ``SpectraVAE.py:208-322``): ``loc = dec(z) - mean_L(dec(z)) +
+    brightnessfc([z[:, :, 0, :], phase])`` — the brightness head also sees the phase."""
+
+    def __init__(self, latent_len=4, latent_dim=2, model_dim=32, num_heads=4, ff_dim=32, num_layers=4, dropout=0.1,
+                 selfattn=False, beta=1., prior=dist.Laplace, likelihood=dist.Laplace, posterior=dist.Laplace):
+        assert latent_len > 1, "Need at least one token for overall brightness"
+        super().__init__(latent_len, latent_dim, model_dim, num_heads, ff_dim, num_layers, dropout, selfattn, True, beta,
+                         prior, likelihood, posterior)
+        self.brightnessfc = MLP(latent_dim + 1, 1, [model_dim])          # phase is added
+
+    def _decode_loc(self, zs, x):
+        loc = super()._decode_loc(zs, x)
+        phase = x[2]
+        feats = torch.cat([zs[:, :, 0, :], phase[None, :, None].expand(zs.shape[0], -1, 1).to(zs.dtype)], dim=-1)
+        brightness = self.brightnessfc(feats)                               # [R, B, 1]
+        return loc + brightness - loc.mean(dim=2, keepdim=True)

@@ -44,3 +44,9 @@ def test_mm_ztf(emu):
 @pytest.mark.parametrize("name", ["bright_photo_elbo", "bright_spec_elbo"])
 def test_bright_variants(emu, name):
     MC.run_bright_case(name, "cpu")
+
+
+def test_script_flow(emu):
+    """cannon/ZTF_photospect.py's construction / DataLoader / AdamW / training_step / torch.save flow."""
+    import script_flow
+    script_flow.run("cpu")

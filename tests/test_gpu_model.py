@@ -33,3 +33,8 @@ def test_regression_head_encode_path():
 @pytest.mark.parametrize("name", ["bright_photo_elbo", "bright_spec_elbo"])
 def test_bright_variants(name):
     MC.run_bright_case(name, "cuda")
+
+
+def test_script_flow():
+    import script_flow
+    script_flow.run("cuda", n=12, Lp=60, Ls=982, K=2)

@@ -98,8 +98,11 @@ def run_bright_case(name, device):
     assert abs(loss.item() - float(g["loss"])) < FWD_TOL * abs(float(g["loss"])), (loss.item(), float(g["loss"]))
     # Tolerance.  fp32 kernels (the emulator; the GPU with VAESNE_NO_TC=1 measures 1.3e-5): the usual 1e-3.  With the
     # tcgen05 attention (spectra, L >= 256) the second products take P / dS as 11-bit operands — the "TF32 path" of the
-    # north star — and the mean-centred loss amplifies that round-off about 20x: tests/probe/bright_debug.py measures
-    # 2.6e-4 .. 2.4e-3 over parameter draws and lengths (plain SpectraVAE: 2e-5 .. 6e-4), hence 5e-3 here.
+    # north star.  The reconstruction still agrees to 4e-5, but the Laplace likelihood's gradient sign(loc - x) / s is
+    # discontinuous: an element with loc within round-off of x flips, which moves a parameter gradient by a fixed quantum
+    # (one of K*B*L elements), and the mean-centred Bright loss shrinks the decoder gradients that quantum is measured
+    # against.  tests/probe/bright_debug.py measures 2.6e-4 .. 2.4e-3 over parameter draws and lengths (plain SpectraVAE:
+    # 2e-5 .. 6e-4, the upper end being single sign flips), hence 5e-3 here.
     tc_attention = str(device).startswith("cuda") and name == "bright_spec_elbo"
     worst = _check_grads(m, g, tol=5e-3 if tc_attention else GRAD_TOL, scale_floor=0.1)
     _noise.inject([u])

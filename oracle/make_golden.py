@@ -137,6 +137,16 @@ def case_bright():
     _bright(m, O.synth_spectra(2, 300, seed=32), 32, 132, 2, "bright_spec_elbo", (2, 2, 4, 4))
 
 
+def case_noconcat():
+    """concat=False embeddings (sum instead of concat + MLP; PhotometricLayers.py:132-135, SpectraLayers.py:124-126)."""
+    m = PhotometricVAE(num_bands=6, latent_len=4, latent_dim=2, model_dim=32, num_heads=4, ff_dim=32, num_layers=2,
+                       dropout=0.0, selfattn=False, concat=False, beta=0.5)
+    _bright(m, O.synth_photometry(3, 60, 6, seed=41), 41, 141, 2, "noconcat_photo_elbo", (2, 3, 4, 2))
+    m = SpectraVAE(latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=2, dropout=0.0,
+                   selfattn=True, concat=False, beta=1.0)
+    _bright(m, O.synth_spectra(2, 200, seed=42), 42, 142, 2, "noconcat_spec_elbo", (2, 2, 4, 4))
+
+
 def _mm(num_bands, K, B, beta, selfattn_spec, seed, noise_seed, name, Lp=60, Ls=982, family=dist.Laplace):
     pv = PhotometricVAE(num_bands=num_bands, latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32,
                         num_layers=4, dropout=0.0, selfattn=False, concat=True,
@@ -236,3 +246,4 @@ if __name__ == "__main__":
     case_contrast()
     case_end2end()
     case_bright()
+    case_noconcat()

@@ -114,6 +114,37 @@ def run_bright_case(name, device):
     return loss.item(), worst
 
 
+def run_noconcat_case(name, device):
+    """concat=False embeddings against the live-reference goldens."""
+    from VAESNe import _noise
+    from VAESNe.PhotometricVAE import PhotometricVAE
+    from VAESNe.SpectraVAE import SpectraVAE
+    from VAESNe.losses import elbo
+    g = load_golden(name)
+    if name == "noconcat_photo_elbo":
+        m = PhotometricVAE(num_bands=6, latent_len=4, latent_dim=2, model_dim=32, num_heads=4, ff_dim=32, num_layers=2,
+                           dropout=0.0, selfattn=False, concat=False, beta=0.5)
+    else:
+        m = SpectraVAE(latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=2, dropout=0.0,
+                       selfattn=True, concat=False, beta=1.0)
+    assert set(m.state_dict().keys()) == set(golden_params(g).keys())
+    m.load_state_dict(golden_params(g))
+    m.to(device).train()
+    x = _to(golden_x(g, "x"), device)
+    u = torch.from_numpy(g["u"])
+    K = int(g["K"])
+    _noise.clear(); _noise.inject([u])
+    loss = elbo(m, x, K=K)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < FWD_TOL * abs(float(g["loss"])), (loss.item(), float(g["loss"]))
+    worst = _check_grads(m, g)
+    _noise.inject([u])
+    with torch.no_grad():
+        qz, px, zs = m(x, K)
+    assert rel_err(qz.loc.cpu(), g["mu"]) < FWD_TOL and rel_err(px.loc.cpu(), g["loc"]) < FWD_TOL
+    return loss.item(), worst
+
+
 def build_mm(g, device, dropout=0.0):
     from VAESNe.PhotometricVAE import PhotometricVAE
     from VAESNe.SpectraVAE import SpectraVAE

@@ -50,3 +50,8 @@ def test_script_flow(emu):
     """cannon/ZTF_photospect.py's construction / DataLoader / AdamW / training_step / torch.save flow."""
     import script_flow
     script_flow.run("cpu")
+
+
+@pytest.mark.parametrize("name", ["noconcat_photo_elbo", "noconcat_spec_elbo"])
+def test_concat_false_embeddings(emu, name):
+    MC.run_noconcat_case(name, "cpu")

@@ -38,3 +38,8 @@ def test_bright_variants(name):
 def test_script_flow():
     import script_flow
     script_flow.run("cuda", n=12, Lp=60, Ls=982, K=2)
+
+
+@pytest.mark.parametrize("name", ["noconcat_photo_elbo", "noconcat_spec_elbo"])
+def test_concat_false_embeddings(name):
+    MC.run_noconcat_case(name, "cuda")

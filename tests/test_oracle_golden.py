@@ -62,6 +62,20 @@ def test_bright_elbo_matches_reference(name, kind, Z, beta):
     _check_grads(_grads(loss, p), golden_grads(g), 2e-4)
 
 
+@pytest.mark.parametrize("name,kind,Z,beta", [("noconcat_photo_elbo", "photometry", 2, 0.5), ("noconcat_spec_elbo", "spectra", 4, 1.0)])
+def test_concat_false_elbo_matches_reference(name, kind, Z, beta):
+    g = load_golden(name)
+    p = _req(golden_params(g))
+    x = golden_x(g, "x")
+    cfg = O.VAEConfig(kind, 4, Z, num_layers=2, beta=beta)
+    u = torch.from_numpy(g["u"])
+    (mu, s), (loc, _), zs = O.vae_forward(_strip(p), "", cfg, x, u)
+    assert rel_err(mu, g["mu"]) < TOL and rel_err(loc, g["loc"]) < TOL
+    loss = O.elbo(_strip(p), "", cfg, x, u)
+    assert abs(loss.item() - float(g["loss"])) < TOL * abs(float(g["loss"]))
+    _check_grads(_grads(loss, p), golden_grads(g), 2e-4)
+
+
 def _strip(p):
     """single-VAE parameter names have no 'vaes.N' prefix; the oracle joins name + '.enc...'"""
     return {"." + k: v for k, v in p.items()}

@@ -322,12 +322,18 @@ def _check_geometry(pv: PView, key: str):
 
 
 def photo_encoder_forward(tape, pv: PView, aux, flux, time, band, mask):
-    """PhotometricLayers.py:117-143 (concat=True)."""
+    """PhotometricLayers.py:117-143: concat=True -> LCfc(cat[fluxfc, SinMLP(time), bandembd]); concat=False -> their sum with
+    the parameter-free sinusoid (:132-135)."""
     _check_geometry(pv, "initbottleneck")
-    if not pv.has("LCfc.mlp.0.weight"):
-        raise NotImplementedError("concat=False photometric encoder is not on the accelerated path yet")
     B, L = flux.shape
     T = B * L
+    if not pv.has("LCfc.mlp.0.weight"):
+        ctx = t_lin(tape, pv, flux.reshape(T, 1), "fluxfc.weight", "fluxfc.bias", need_dX=False)
+        pos = torch.empty(T, 32, device=flux.device, dtype=torch.float32)
+        P.sincos_feat(time.reshape(T), aux["div_half"], pos)
+        ctx.add_(pos)                                   # no parameters behind it: d(ctx) passes through unchanged
+        t_gather(tape, pv, band.reshape(T), "bandembd.weight", ctx, accumulate=True)
+        return _encoder_tail(tape, pv, ctx, B, L, mask)
     feats = torch.empty(T, 96, device=flux.device, dtype=torch.float32)
     t_lin(tape, pv, flux.reshape(T, 1), "fluxfc.weight", "fluxfc.bias", need_dX=False, Y=feats[:, 0:32])
     sin_mlp(tape, pv, "time_embd", time.reshape(T), aux["div_full"], Y=feats[:, 32:64])
@@ -339,17 +345,27 @@ def photo_encoder_forward(tape, pv: PView, aux, flux, time, band, mask):
 
 
 def spectra_encoder_forward(tape, pv: PView, aux, arg1, arg2, phase, mask):
-    """SpectraLayers.py:112-138 (concat=True): forward(wavelength=arg1, flux=arg2, phase, mask)."""
+    """SpectraLayers.py:112-138: forward(wavelength=arg1, flux=arg2, phase, mask).  concat=True -> spectrafc(cat[flux_embd(arg2),
+    Sin(arg1)]); concat=False -> flux_embd(arg2) + SinMLP(arg1) (:124-126)."""
     _check_geometry(pv, "initbottleneck")
-    if not pv.has("spectrafc.mlp.0.weight"):
-        raise NotImplementedError("concat=False spectra encoder is not on the accelerated path yet")
     B, L = arg1.shape
     T = B * L
-    feats = torch.empty(T, 64, device=arg1.device, dtype=torch.float32)
-    t_lin(tape, pv, arg2.reshape(T, 1), "flux_embd.weight", "flux_embd.bias", need_dX=False, Y=feats[:, 0:32])
-    P.sincos_feat(arg1.reshape(T), aux["div_half"], feats[:, 32:64])
-    _alias_feature_grads(tape, feats, [(0, 32)])
-    emb = mlp2(tape, pv, "spectrafc", feats, need_dX=True)
+    if not pv.has("spectrafc.mlp.0.weight"):
+        emb = sin_mlp(tape, pv, "wavelength_embd_layer", arg1.reshape(T), aux["div_full"])
+        lin = t_lin(tape, pv, arg2.reshape(T, 1), "flux_embd.weight", "flux_embd.bias", need_dX=False)
+        emb.add_(lin)
+
+        def share_grad(bw: _Bwd, _a=emb, _b=lin):      # d(sum) is the gradient of both addends
+            d = bw.peek(_a)
+            if d is not None:
+                bw.seed(_b, d)
+        tape.push(share_grad)
+    else:
+        feats = torch.empty(T, 64, device=arg1.device, dtype=torch.float32)
+        t_lin(tape, pv, arg2.reshape(T, 1), "flux_embd.weight", "flux_embd.bias", need_dX=False, Y=feats[:, 0:32])
+        P.sincos_feat(arg1.reshape(T), aux["div_half"], feats[:, 32:64])
+        _alias_feature_grads(tape, feats, [(0, 32)])
+        emb = mlp2(tape, pv, "spectrafc", feats, need_dX=True)
     pe = sin_mlp(tape, pv, "phase_embd_layer", phase.reshape(B), aux["div_full"])
     ctx = t_concat_tokens(tape, emb.view(B, L, 32), pe.view(B, 1, 32)).view(B * (L + 1), 32)
     # one extra, never-masked key for the phase token (:129-131): handled in-kernel by mask_len = L

@@ -43,3 +43,9 @@ def test_script_flow():
 @pytest.mark.parametrize("name", ["noconcat_photo_elbo", "noconcat_spec_elbo"])
 def test_concat_false_embeddings(name):
     MC.run_noconcat_case(name, "cuda")
+
+
+def test_reference_checkpoint_loads():
+    """torch.load of a whole-module pickle written by the reference (cannon/test_photospectra.py:153)."""
+    import pickle_case
+    pickle_case.run("cuda")

@@ -5,7 +5,7 @@ import torch
 from torch import nn
 
 from . import _stacks as S
-from ._functions import run_stack, _prep
+from ._functions import run_stack, _prep, model_dim_of
 from .util_layers import (MLP, SinusoidalMLPPositionalEmbedding, SinusoidalPositionalEmbedding,
                           TransformerBlock, aux_tables, singlelayerMLP)
 
@@ -29,9 +29,9 @@ class photometricTransformerDecoder(nn.Module):
     def decode_replicated(self, time, band, z, mask, copies):
         """time/band/mask are the un-replicated [B, L] inputs; z is [copies*B, T, Z] with row r = c*B + b
         (the K-sample / source replication of PhotometricVAE.py:191-197 without materialising the copies)."""
-        if self.donotmask:
+        if getattr(self, "donotmask", False):
             mask = None
-        aux = aux_tables(self.model_dim, z.device)
+        aux = aux_tables(model_dim_of(self), z.device)
         time, band, mask, z = _prep(time, torch.float32), _prep(band, torch.int64), _prep(mask), _prep(z, torch.float32)
 
         def run(tape, pv, t, b, zz, m):
@@ -65,7 +65,7 @@ class photometricTransformerEncoder(nn.Module):
         self._drop_p = float(dropout)
 
     def forward(self, flux, time, band, mask=None):
-        aux = aux_tables(self.model_dim, flux.device)
+        aux = aux_tables(model_dim_of(self), flux.device)
         flux, time, band, mask = _prep(flux, torch.float32), _prep(time, torch.float32), _prep(band, torch.int64), _prep(mask)
 
         def run(tape, pv, f, t, b, m):

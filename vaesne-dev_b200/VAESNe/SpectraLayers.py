@@ -5,7 +5,7 @@ import torch
 from torch import nn
 
 from . import _stacks as S
-from ._functions import run_stack, _prep
+from ._functions import run_stack, _prep, model_dim_of
 from .util_layers import (MLP, SinusoidalMLPPositionalEmbedding, SinusoidalPositionalEmbedding,
                           TransformerBlock, aux_tables, singlelayerMLP)
 
@@ -27,7 +27,7 @@ class spectraTransformerDecoder(nn.Module):
     def decode_replicated(self, wavelength, phase, z, mask, copies):
         """wavelength/mask [B, L], phase [B] un-replicated; z [copies*B, T, Z] with row r = c*B + b
         (SpectraVAE.py:189-194 without materialising the copies)."""
-        aux = aux_tables(self._model_dim, z.device)
+        aux = aux_tables(model_dim_of(self), z.device)
         wavelength, phase, mask, z = _prep(wavelength, torch.float32), _prep(phase, torch.float32), _prep(mask), _prep(z, torch.float32)
 
         def run(tape, pv, w, p, zz, m):
@@ -63,7 +63,7 @@ class spectraTransformerEncoder(nn.Module):
         self._drop_p = float(dropout)
 
     def forward(self, wavelength, flux, phase, mask=None):
-        aux = aux_tables(self._model_dim, flux.device)
+        aux = aux_tables(model_dim_of(self), flux.device)
         a1, a2, phase, mask = _prep(wavelength, torch.float32), _prep(flux, torch.float32), _prep(phase, torch.float32), _prep(mask)
 
         def run(tape, pv, x1, x2, ph, m):

@@ -74,9 +74,36 @@ class _StackFn(torch.autograd.Function):
         return (None, None, None, None, *dgrads, *pgrads)
 
 
+def drop_p_of(module: torch.nn.Module) -> float:
+    """Dropout probability of a stack.  Modules built here record it; a module unpickled from a REFERENCE checkpoint
+    (whole-module torch.save, cannon/test_photospectra.py:153) only has the reference's attributes, so it is recovered from
+    the first Dropout / MultiheadAttention layer inside and cached."""
+    p = module.__dict__.get("_drop_p")
+    if p is None:
+        p = 0.0
+        for sub in module.modules():
+            if isinstance(sub, torch.nn.Dropout):
+                p = float(sub.p)
+                break
+            if isinstance(sub, torch.nn.MultiheadAttention):
+                p = float(sub.dropout)
+                break
+        module.__dict__["_drop_p"] = p
+    return float(p)
+
+
+def model_dim_of(module: torch.nn.Module) -> int:
+    """Width of a stack (recorded at construction, or read off the first LayerNorm of an unpickled reference module)."""
+    d = module.__dict__.get("_model_dim")
+    if d is None:
+        d = next(int(sub.normalized_shape[0]) for sub in module.modules() if isinstance(sub, torch.nn.LayerNorm))
+        module.__dict__["_model_dim"] = d
+    return int(d)
+
+
 def run_stack(module: torch.nn.Module, runner: Callable, data: Sequence):
     names, params = zip(*module.named_parameters())
-    drop_p = float(getattr(module, "_drop_p", 0.0)) if module.training else 0.0
+    drop_p = drop_p_of(module) if module.training else 0.0
     return _StackFn.apply(runner, names, len(data), drop_p, *data, *params)
 
 

@@ -156,7 +156,7 @@ class TransformerBlock(nn.Module):
             self._unsupported = None
 
     def forward(self, x, context=None, mask=None, context_mask=None):
-        if self._unsupported:
+        if self.__dict__.get("_unsupported"):
             raise NotImplementedError(f"VAESNe-B200 kernels support embed_dim=32 / 4 heads only ({self._unsupported})")
         if context is None:
             raise NotImplementedError("TransformerBlock without a context is not used by the VAESNe hot path")

@@ -304,9 +304,9 @@ extern "C" int vaesne_attn_fwd(const float* q, long long ldq, const float* k, lo
 #ifndef VAESNE_EMU
   // the forward and backward of one attention call must pick the same path (their dropout masks differ)
   if (attn_tc_eligible(a) && (a.p_drop == 0.f || attn_tc_has_bwd())) return attn_tc_fwd(a, st);
+#endif
   if (attn_small_eligible(a)) return attn_small_fwd(a, st);
   if (attn_mid_eligible(a)) return attn_mid_fwd(a, st);
-#endif
   dim3 block(AT);
   if (Lq <= 32) { dim3 grid((Lq + 3) / 4, kH, N); auto kf = attn_fwd_kernel<32>; VLAUNCH(kf, grid, block, 0, st, a); }
   else { dim3 grid((Lq + AT - 1) / AT, kH, N); auto kf = attn_fwd_kernel<1>; VLAUNCH(kf, grid, block, 0, st, a); }
@@ -330,9 +330,9 @@ extern "C" int vaesne_attn_bwd(const float* q, long long ldq, const float* k, lo
   cudaStream_t st = (cudaStream_t)stream;
 #ifndef VAESNE_EMU
   if (attn_tc_eligible(a) && attn_tc_has_bwd()) return attn_tc_bwd(a, st);
+#endif
   if (attn_small_eligible(a)) return attn_small_bwd(a, st);
   if (attn_mid_eligible(a)) return attn_mid_bwd(a, st);
-#endif
   dim3 block(AT);
   if (Lq <= 32) { dim3 grid((Lq + 3) / 4, kH, N); auto kf = attn_bwd_dq_kernel<32>; VLAUNCH(kf, grid, block, 0, st, a); }
   else { dim3 grid((Lq + AT - 1) / AT, kH, N); auto kf = attn_bwd_dq_kernel<1>; VLAUNCH(kf, grid, block, 0, st, a); }

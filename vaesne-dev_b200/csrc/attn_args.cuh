@@ -28,6 +28,7 @@ bool attn_tc_eligible(const AttnArgs& a);
 bool attn_tc_has_bwd();
 int attn_tc_fwd(const AttnArgs& a, cudaStream_t st);
 int attn_tc_bwd(const AttnArgs& a, cudaStream_t st);
+#endif
 // few-key cross attention (attn_small.cu): Lk <= 8
 bool attn_small_eligible(const AttnArgs& a);
 int attn_small_fwd(const AttnArgs& a, cudaStream_t st);
@@ -36,6 +37,5 @@ int attn_small_bwd(const AttnArgs& a, cudaStream_t st);
 bool attn_mid_eligible(const AttnArgs& a);
 int attn_mid_fwd(const AttnArgs& a, cudaStream_t st);
 int attn_mid_bwd(const AttnArgs& a, cudaStream_t st);
-#endif
 
 }  // namespace vaesne

@@ -197,11 +197,11 @@ bool attn_mid_eligible(const AttnArgs& a) {
   return !off && a.Lk > 8 && a.Lk <= ML && a.Lq <= ML && a.Lq >= 1;
 }
 int attn_mid_fwd(const AttnArgs& a, cudaStream_t st) {
-  attn_mid_fwd_kernel<<<a.N, 256, 0, st>>>(a);
+  VLAUNCH(attn_mid_fwd_kernel, dim3(a.N), dim3(256), 0, st, a);
   return check_launch("attn_mid_fwd");
 }
 int attn_mid_bwd(const AttnArgs& a, cudaStream_t st) {
-  attn_mid_bwd_kernel<<<a.N, 256, 0, st>>>(a);
+  VLAUNCH(attn_mid_bwd_kernel, dim3(a.N), dim3(256), 0, st, a);
   return check_launch("attn_mid_bwd");
 }
 

@@ -168,13 +168,13 @@ bool attn_small_eligible(const AttnArgs& a) {
 }
 int attn_small_fwd(const AttnArgs& a, cudaStream_t st) {
   const dim3 grid((a.Lq + 63) / 64, a.N), block(256);
-  if (a.Lk <= 5) attn_small_fwd_kernel<5><<<grid, block, 0, st>>>(a);
-  else attn_small_fwd_kernel<8><<<grid, block, 0, st>>>(a);
+  if (a.Lk <= 5) { auto kf = attn_small_fwd_kernel<5>; VLAUNCH(kf, grid, block, 0, st, a); }
+  else { auto kf = attn_small_fwd_kernel<8>; VLAUNCH(kf, grid, block, 0, st, a); }
   return check_launch("attn_small_fwd");
 }
 int attn_small_bwd(const AttnArgs& a, cudaStream_t st) {
-  if (a.Lk <= 5) attn_small_bwd_kernel<5><<<a.N, 128, 0, st>>>(a);
-  else attn_small_bwd_kernel<8><<<a.N, 128, 0, st>>>(a);
+  if (a.Lk <= 5) { auto kf = attn_small_bwd_kernel<5>; VLAUNCH(kf, dim3(a.N), dim3(128), 0, st, a); }
+  else { auto kf = attn_small_bwd_kernel<8>; VLAUNCH(kf, dim3(a.N), dim3(128), 0, st, a); }
   return check_launch("attn_small_bwd");
 }
 

@@ -18,6 +18,10 @@ def build(objective):
     pv = PhotometricVAE(num_bands=2, latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=1, dropout=0.0)
     if objective == "elbo":
         return pv
+    if objective == "contrast":
+        from VAESNe.contrastiveNets import ContraPhotSpec
+        torch.manual_seed(3)
+        return ContraPhotSpec(4, 4, 8, 2, 32, 4, 32, 1, 0.0, 32, 4, 1, 32, 0.0, False)
     sv = SpectraVAE(latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=1, dropout=0.0, selfattn=True)
     return photospecMMVAE([pv, sv], beta=0.5)
 
@@ -39,6 +43,9 @@ def step(model, x, us, objective, average):
     if objective == "elbo":
         _noise.inject([us[0]])
         loss = -elbo(model, x[0], K=2)
+    elif objective == "contrast":
+        from VAESNe.losses import negInfoNCE
+        loss = -negInfoNCE(model, x, temperature=0.1)
     else:
         _noise.inject(us)
         loss = -m_iwae(model, x, K=2)

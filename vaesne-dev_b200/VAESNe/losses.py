@@ -96,6 +96,17 @@ def negInfoNCE(model, x, temperature=0.07):
     z1, z2 = model(x)
     z1 = F.normalize(z1, dim=-1)
     z2 = F.normalize(z2, dim=-1)
+    from . import parallel
+    if parallel.enabled():
+        # batch-sharded data parallelism: the negatives are the GLOBAL batch (the projections of all ranks are gathered, tiny
+        # messages); each rank returns its rows' share of the global mean, so the ranks' losses — and, through the SUM
+        # all-reduce of the gradient buckets, their gradients — add up to the single-process objective on the whole batch
+        z1g, z2g = parallel.gather_batch(z1), parallel.gather_batch(z2)
+        n, world = z1.size(0), parallel.world_size()
+        labels = torch.arange(n, device=z1.device) + parallel.rank() * n
+        rows = F.cross_entropy(z1 @ z2g.T / temperature, labels, reduction="sum")
+        cols = F.cross_entropy(z2 @ z1g.T / temperature, labels, reduction="sum")
+        return -(rows + cols) / (2 * n * world)
     logits = z1 @ z2.T / temperature
     labels = torch.arange(z1.size(0), device=z1.device)
     return -(F.cross_entropy(logits, labels) + F.cross_entropy(logits.T, labels)) / 2

@@ -83,3 +83,31 @@ def all_reduce_scalar(t: torch.Tensor, average: bool = False) -> torch.Tensor:
         if average:
             t = t / world_size()
     return t
+
+
+class _GatherBatch(torch.autograd.Function):
+    """cat over ranks along dim 0, differentiable on any backend: the backward sums the gradient of the gathered tensor
+    over the ranks and keeps this rank's rows."""
+
+    @staticmethod
+    def forward(ctx, t):
+        parts = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(parts, t.contiguous())
+        ctx.n = t.shape[0]
+        return torch.cat(parts, 0)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        r = dist.get_rank()
+        return g[r * ctx.n:(r + 1) * ctx.n]
+
+
+def gather_batch(t: torch.Tensor) -> torch.Tensor:
+    """All ranks' rows of `t` (equal shard sizes), with gradients flowing back to their owners; identity without DP."""
+    return _GatherBatch.apply(t) if _enabled else t
+
+
+def rank() -> int:
+    return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0

@@ -62,3 +62,19 @@ def test_attention_dropout_mask_is_the_restated_one(emu, case):
     P.attn_bwd(qd, kd, vd, mask, O, LSE, dO, dq, dk, dv, drop)
     for name, got, ref in (("dq", dq, dq_ref), ("dk", dk, dk_ref), ("dv", dv, dv_ref)):
         assert rel_err(got, ref) < OC.TOL, (name, rel_err(got, ref))
+
+
+def test_empty_inputs(emu):
+    import edge_cases
+    edge_cases.run_empty("cpu")
+
+
+@pytest.mark.parametrize("L", [5, 40, 100])
+def test_fully_masked_row_is_nan_like_the_reference(emu, L):
+    import edge_cases
+    edge_cases.run_fully_masked_row("cpu", L)
+
+
+def test_boundary_lengths(emu):
+    import edge_cases
+    edge_cases.run_boundary_lengths("cpu", edge_cases.BOUNDARY_SMALL)

@@ -40,3 +40,19 @@ def test_adamw():
 def test_native_library_is_the_cuda_build():
     from VAESNe import _native
     assert not _native.is_emulated()
+
+
+def test_empty_inputs():
+    import edge_cases
+    edge_cases.run_empty("cuda")
+
+
+@pytest.mark.parametrize("L", [5, 40, 100, 300, 982])
+def test_fully_masked_row_is_nan_like_the_reference(L):
+    import edge_cases
+    edge_cases.run_fully_masked_row("cuda", L)
+
+
+def test_boundary_lengths():
+    import edge_cases
+    edge_cases.run_boundary_lengths("cuda", edge_cases.BOUNDARY_SMALL + edge_cases.BOUNDARY_GPU)

@@ -297,9 +297,9 @@ extern "C" int vaesne_attn_fwd(const float* q, long long ldq, const float* k, lo
   a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.N = N; a.Lq = Lq; a.Lk = Lk;
   a.mask = mask; a.mask_rows = mask_rows; a.mask_len = mask_len; a.p_drop = p_drop; a.seed = seed; a.stream_id = stream_id;
   a.O = O; a.ldo = ldo; a.LSE = LSE;
+  if (N == 0) return V_OK;                  // an empty batch has no buffers: torch hands out null pointers for it
   int rc = check_common(a, "attn_fwd"); if (rc) return rc;
   V_REQUIRE(O && LSE, V_ENULL, "attn_fwd: null O/LSE");
-  if (N == 0) return V_OK;
   cudaStream_t st = (cudaStream_t)stream;
 #ifndef VAESNE_EMU
   // the forward and backward of one attention call must pick the same path (their dropout masks differ)
@@ -324,9 +324,9 @@ extern "C" int vaesne_attn_bwd(const float* q, long long ldq, const float* k, lo
   a.mask = mask; a.mask_rows = mask_rows; a.mask_len = mask_len; a.p_drop = p_drop; a.seed = seed; a.stream_id = stream_id;
   a.O = const_cast<float*>(O); a.ldo = ldo; a.LSE = const_cast<float*>(LSE); a.dO = dO; a.lddo = lddo; a.delta = delta_ws;
   a.dq = dq; a.lddq = lddq; a.dk = dk; a.lddk = lddk; a.dv = dv; a.lddv = lddv;
+  if (N == 0) return V_OK;
   int rc = check_common(a, "attn_bwd"); if (rc) return rc;
   V_REQUIRE(O && LSE && dO && delta_ws && dq && dk && dv, V_ENULL, "attn_bwd: null argument");
-  if (N == 0) return V_OK;
   cudaStream_t st = (cudaStream_t)stream;
 #ifndef VAESNE_EMU
   if (attn_tc_eligible(a) && attn_tc_has_bwd()) return attn_tc_bwd(a, st);

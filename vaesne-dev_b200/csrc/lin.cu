@@ -381,10 +381,10 @@ extern "C" int vaesne_lin_fwd(const float* X, long long ldx, const float* Xadd, 
                               const float* R, long long ldr, const float* gamma, const float* beta, float eps,
                               float* S, float p_drop, const uint64_t* seed, uint32_t stream_id,
                               float* Y, long long ldy, void* stream) {
-  V_REQUIRE(X && W && Y, V_ENULL, "lin_fwd: null X/W/Y");
   V_REQUIRE(T >= 0 && K >= 1 && K <= 128 && N >= 1 && N <= 128, V_EBADSHAPE, "lin_fwd: need 1<=K,N<=128 (K=%d N=%d)", K, N);
   V_REQUIRE(act >= 0 && act <= 2, V_EBADSHAPE, "lin_fwd: act %d", act);
-  if (T == 0) return V_OK;
+  if (T == 0) return V_OK;                  // no tokens: torch hands out null pointers for empty tensors
+  V_REQUIRE(X && W && Y, V_ENULL, "lin_fwd: null X/W/Y");
   const bool ln = R != nullptr;
   if (ln) {
     V_REQUIRE(N == 32 && gamma && beta, V_EUNSUPPORTED, "lin_fwd: LayerNorm epilogue needs N==32 and gamma/beta (N=%d)", N);
@@ -414,11 +414,11 @@ extern "C" int vaesne_lin_bwd(const float* dY, long long lddy, int T, int K, int
                               const float* X, long long ldx, const float* Xadd, long long ldxa,
                               const float* W, float* dW, float* db,
                               float* dX, long long lddx, int dX_acc, void* stream) {
-  V_REQUIRE(dY && W, V_ENULL, "lin_bwd: null dY/W");
   V_REQUIRE(T >= 0 && K >= 1 && K <= 128 && N >= 1 && N <= 128, V_EBADSHAPE, "lin_bwd: need 1<=K,N<=128 (K=%d N=%d)", K, N);
+  if (T == 0) return V_OK;
+  V_REQUIRE(dY && W, V_ENULL, "lin_bwd: null dY/W");
   V_REQUIRE(act >= 0 && act <= 2 && (act == 0 || A), V_EBADSHAPE, "lin_bwd: act %d needs the saved activation", act);
   V_REQUIRE(dW == nullptr || X != nullptr, V_ENULL, "lin_bwd: dW requested without X");
-  if (T == 0) return V_OK;
   const bool ln = S != nullptr;
   if (ln) V_REQUIRE(N == 32 && gamma && act == 0, V_EUNSUPPORTED, "lin_bwd: LayerNorm path needs N==32, gamma, act none");
   LinBwd a{dY, lddy, T, K, N, S, gamma, eps, dgamma, dbeta, dR, lddr, dR_acc, p_drop, seed, stream_id,

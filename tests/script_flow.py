@@ -8,7 +8,7 @@ from torch.optim import AdamW
 from torch.utils.data import DataLoader, TensorDataset
 
 
-def run(device, n=8, Lp=20, Ls=40, K=2, epochs=2):
+def run(device, n=9, Lp=20, Ls=40, K=2, epochs=2):      # 9 samples at batch 4: the last batch holds a single sample
     from VAESNe.SpectraVAE import SpectraVAE
     from VAESNe.PhotometricVAE import PhotometricVAE
     from VAESNe.mmVAE import photospecMMVAE

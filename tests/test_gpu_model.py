@@ -37,7 +37,7 @@ def test_bright_variants(name):
 
 def test_script_flow():
     import script_flow
-    script_flow.run("cuda", n=12, Lp=60, Ls=982, K=2)
+    script_flow.run("cuda", n=13, Lp=60, Ls=982, K=2)
 
 
 @pytest.mark.parametrize("name", ["noconcat_photo_elbo", "noconcat_spec_elbo"])

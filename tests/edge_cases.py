@@ -71,3 +71,15 @@ BOUNDARY_GPU = [
     dict(id="self_1025", N=1, Lq=1025, Lk=1025, mask=True, packed="qkv"),      # past it: general kernels
     dict(id="cross_300x1030", N=1, Lq=300, Lk=1030, mask=True, packed="q+kv"),
 ]
+
+
+def run_many_rows(device):
+    """More batch rows than one launch takes: the binding splits the rows (here with the limit lowered to 5)."""
+    from VAESNe import _ops as P
+    old = P._MAX_ROWS
+    P._MAX_ROWS = 5
+    try:
+        run_boundary_lengths(device, [dict(id="rows_13_mask2", N=13, Lq=20, Lk=20, mask=True, mask_rows=2, packed="qkv"),
+                                      dict(id="rows_12_cross", N=12, Lq=40, Lk=5, mask=False, packed="q+kv")])
+    finally:
+        P._MAX_ROWS = old

@@ -78,3 +78,8 @@ def test_fully_masked_row_is_nan_like_the_reference(emu, L):
 def test_boundary_lengths(emu):
     import edge_cases
     edge_cases.run_boundary_lengths("cpu", edge_cases.BOUNDARY_SMALL)
+
+
+def test_more_rows_than_one_launch(emu):
+    import edge_cases
+    edge_cases.run_many_rows("cpu")

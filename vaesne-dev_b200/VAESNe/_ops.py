@@ -151,9 +151,26 @@ def _mask_args(mask: Optional[torch.Tensor]):
     return mask.data_ptr(), mask.shape[0], mask.shape[1]
 
 
+_MAX_ROWS = 65535          # batch rows of one attention launch (a CUDA grid dimension)
+
+
+def _row_chunks(Nb: int, mask):
+    """Row ranges of at most _MAX_ROWS whose starts are multiples of the mask's row count (the kernels index it n % rows)."""
+    if Nb <= _MAX_ROWS:
+        return None
+    period = mask.shape[0] if mask is not None else 1
+    step = max(period, (_MAX_ROWS // period) * period)
+    return [(a, min(Nb, a + step)) for a in range(0, Nb, step)]
+
+
 def attn_fwd(q, k, v, mask, drop: Drop = NO_DROP):
     """q [N,Lq,32] view, k/v [N,Lk,32] views -> O [N,Lq,32], LSE [N,4,Lq]."""
     Nb, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+    chunks = _row_chunks(Nb, mask)
+    if chunks is not None:      # more batch rows than one launch takes (K=100 reconstructions of large batches): rows are independent
+        outs = [attn_fwd(q[a:b], k[a:b], v[a:b], mask, Drop(drop.p, drop.seed, drop.sid + 7919 * (i + 1)) if drop.seed is not None else drop)
+                for i, (a, b) in enumerate(chunks)]
+        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
     O = torch.empty(Nb, Lq, 32, device=q.device, dtype=torch.float32)
     LSE = torch.empty(Nb, 4, Lq, device=q.device, dtype=torch.float32)
     qp, ldq = _attn_operand(q, "q"); kp, ldk = _attn_operand(k, "k"); vp, ldv = _attn_operand(v, "v")
@@ -167,6 +184,12 @@ def attn_fwd(q, k, v, mask, drop: Drop = NO_DROP):
 def attn_bwd(q, k, v, mask, O, LSE, dO, dq, dk, dv, drop: Drop = NO_DROP):
     """Writes dq/dk/dv (views shaped like q/k/v)."""
     Nb, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+    chunks = _row_chunks(Nb, mask)
+    if chunks is not None:
+        for i, (a, b) in enumerate(chunks):
+            attn_bwd(q[a:b], k[a:b], v[a:b], mask, O[a:b], LSE[a:b], dO[a:b], dq[a:b], dk[a:b], dv[a:b],
+                     Drop(drop.p, drop.seed, drop.sid + 7919 * (i + 1)) if drop.seed is not None else drop)
+        return
     qp, ldq = _attn_operand(q, "q"); kp, ldk = _attn_operand(k, "k"); vp, ldv = _attn_operand(v, "v")
     dqp, lddq = _attn_operand(dq, "dq"); dkp, lddk = _attn_operand(dk, "dk"); dvp, lddv = _attn_operand(dv, "dv")
     dop, lddo = _attn_operand(dO, "dO")

@@ -68,7 +68,11 @@ int vaesne_lin_bwd(const float* dY, long long lddy, int T, int K, int N,
  * util_layers.py:289,297,301.  q/k/v/O are [N, L, ld] with head h at columns h*8..h*8+7 of the
  * pointer passed.  mask is torch.bool storage [mask_rows, mask_len]; batch row n uses row
  * n % mask_rows (K-sample / source replication, PhotometricVAE.py:191-197), key j >= mask_len is
- * never masked (the appended phase token, SpectraLayers.py:129-131).  LSE is [N,4,Lq]. */
+ * never masked (the appended phase token, SpectraLayers.py:129-131).  LSE is [N,4,Lq].
+ * N = 0 returns VAESNE_OK without touching the (possibly null) pointers; N <= 65535 per call (the Python binding splits
+ * larger batches, rows are independent).  A row whose keys are all masked yields NaN, as the reference does.
+ * Four kernel families serve the call, chosen by shape only (forward and backward always agree): tcgen05 (256 <= Lq, Lk
+ * <= 1024), few keys (Lk <= 8), short sequences (Lq, Lk <= 64), general. */
 int vaesne_attn_fwd(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
                     int N, int Lq, int Lk, const unsigned char* mask, int mask_rows, int mask_len,
                     float p_drop, const uint64_t* seed, uint32_t stream_id,

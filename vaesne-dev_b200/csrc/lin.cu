@@ -371,6 +371,90 @@ static int grid_for(int T) {
   return g < 1 ? 1 : g;
 }
 
+// ------------------------------------------------------------------------------------------------
+// output heads: Linear(32 -> 1) over every token (get_flux.fc2 / get_photo.fc2, util_layers.py:9-18).  One thread per token
+// reads its 128-byte row with eight 16-byte loads (a warp covers 4 KB of consecutive rows), so these stream at memory
+// speed instead of staging rows through shared memory for a single output column.
+// ------------------------------------------------------------------------------------------------
+constexpr int HT = 256;
+__global__ void __launch_bounds__(HT) lin_head_fwd_kernel(LinFwd a) {
+  __shared__ float sW[32];
+  if (threadIdx.x < 32) sW[threadIdx.x] = a.W[threadIdx.x];
+  __syncthreads();
+  const float b = a.b ? a.b[0] : 0.f;
+  for (long long t = (long long)blockIdx.x * HT + threadIdx.x; t < a.T; t += (long long)gridDim.x * HT) {
+    float x[32];
+    ld_row<32>(x, a.X + t * a.ldx, true);
+    float acc0 = b, acc1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) { acc0 = fmaf(x[k], sW[k], acc0); acc1 = fmaf(x[k + 1], sW[k + 1], acc1); }
+    a.Y[t * a.ldy] = acc0 + acc1;
+  }
+}
+
+__global__ void __launch_bounds__(HT) lin_head_bwd_kernel(LinBwd a) {
+  __shared__ float sW[32];
+  __shared__ float sAcc[HT / 32][33];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 32) sW[tid] = a.W[tid];
+  __syncthreads();
+  const bool wgrad = a.dW != nullptr;
+  float dw[32], dbs = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) dw[k] = 0.f;
+  for (long long t = (long long)blockIdx.x * HT + tid; t < a.T; t += (long long)gridDim.x * HT) {
+    const float dy = a.dY[t * a.lddy];
+    dbs += dy;
+    if (wgrad) {
+      float x[32];
+      ld_row<32>(x, a.X + t * a.ldx, true);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) dw[k] = fmaf(dy, x[k], dw[k]);
+    }
+    if (a.dX) {
+      float g[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) g[k] = 0.f;
+      if (a.dX_acc) ld_row<32>(g, a.dX + t * a.lddx, true);
+#pragma unroll
+      for (int k = 0; k < 32; ++k) g[k] = fmaf(dy, sW[k], g[k]);
+      st_row<32>(a.dX + t * a.lddx, g, true);
+    }
+  }
+  // column k of the per-thread sums -> lane k of every warp (butterfly transpose-reduction), then over the warps
+  if (wgrad) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = up ? dw[i] : dw[i + off];
+        const float keep = up ? dw[i + off] : dw[i];
+        dw[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    sAcc[warp][lane] = dw[0];
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) dbs += __shfl_xor_sync(0xffffffffu, dbs, off);
+  if (lane == 0) sAcc[warp][32] = dbs;
+  __syncthreads();
+  if (tid < 33 && wgrad) {
+    float x = 0.f;
+#pragma unroll
+    for (int w = 0; w < HT / 32; ++w) x += sAcc[w][tid];
+    if (tid < 32) atomicAdd(&a.dW[tid], x);
+    else if (a.db) atomicAdd(&a.db[0], x);
+  }
+}
+
+static bool head_fwd_eligible(const LinFwd& a) {
+  return a.N == 1 && a.K == 32 && a.act == 0 && !a.R && !a.H && !a.Xadd && vec_ok(a.X, a.ldx);
+}
+static bool head_bwd_eligible(const LinBwd& a) {
+  return a.N == 1 && a.K == 32 && a.act == 0 && !a.S && !a.Xadd && (a.X == nullptr || vec_ok(a.X, a.ldx)) && vec_ok(a.dX, a.lddx);
+}
+
 }  // namespace vaesne
 
 using namespace vaesne;
@@ -394,6 +478,11 @@ extern "C" int vaesne_lin_fwd(const float* X, long long ldx, const float* Xadd, 
 #ifndef VAESNE_EMU
   if (lin_tc_fwd_eligible(a)) return lin_tc_fwd(a, (cudaStream_t)stream);
 #endif
+  if (head_fwd_eligible(a)) {
+    const long long blocks = ((long long)T + HT - 1) / HT;
+    VLAUNCH(lin_head_fwd_kernel, dim3((unsigned)(blocks < 148 * 16 ? blocks : 148 * 16)), dim3(HT), 0, (cudaStream_t)stream, a);
+    return check_launch("lin_head_fwd");
+  }
   const int NC = ln ? 32 : (N <= 4 ? 4 : (N <= 8 ? 8 : 32));
   const int Np = ((N + NC - 1) / NC) * NC;
   const size_t smem = sizeof(float) * ((size_t)K * Np + Np + 64 + (size_t)TT * (K + 1));
@@ -426,6 +515,11 @@ extern "C" int vaesne_lin_bwd(const float* dY, long long lddy, int T, int K, int
 #ifndef VAESNE_EMU
   if (lin_tc_bwd_eligible(a)) return lin_tc_bwd(a, (cudaStream_t)stream);
 #endif
+  if (head_bwd_eligible(a)) {
+    const long long blocks = ((long long)T + HT - 1) / HT;
+    VLAUNCH(lin_head_bwd_kernel, dim3((unsigned)(blocks < 148 * 8 ? blocks : 148 * 8)), dim3(HT), 0, (cudaStream_t)stream, a);
+    return check_launch("lin_head_bwd");
+  }
   const int Kp = ((K + 7) / 8) * 8;
   a.smem_acc = (N * Kp <= 96 * 96) ? 1 : 0;
   const size_t smem = sizeof(float) * ((size_t)(1 + a.smem_acc) * N * Kp + ((N + 3) / 4) * 4 + 96 + (size_t)TT * (Kp + 4) + (size_t)TT * (N + 1));

@@ -146,9 +146,14 @@ def t_lin(tape: Tape, pv: PView, X, wname: str, bname: str, *, rows: Optional[sl
                   dX=dX, dX_acc=bool(dXacc), drop=drop, **kw)
         if Xadd is not None and need_dX:
             assert not dXacc, "Xadd input must receive the first gradient contribution"
-            dA, acc = bw.slot(Xadd)
-            n = dX.numel()
-            P.copy3d(dX, 0, 0, dA, 0, 0, 1, 1, n, accumulate=acc)
+            if bw.peek(Xadd) is None:
+                # d(X + Xadd) is the gradient of both addends: hand the SAME buffer to Xadd instead of copying it (1 GB at the
+                # spectra head).  Safe on the tape: Xadd's producer takes (reads) it in the very next backward ops, X keeps
+                # accumulating into it only later (X is the stack input, consumed by the first block / the expansion).
+                bw.seed(Xadd, dX.view(Xadd.shape) if dX.shape != Xadd.shape else dX)
+            else:
+                dA, acc = bw.slot(Xadd)
+                P.copy3d(dX, 0, 0, dA, 0, 0, 1, 1, dX.numel(), accumulate=acc)
     tape.push(bwd)
     return Y
 

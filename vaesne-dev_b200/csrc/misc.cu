@@ -58,6 +58,24 @@ __global__ void expand_kernel(const float* src, long long row_elems, long long B
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     dst[i] = src[i % per];
 }
+// 16-byte variants (per % 4 == 0, aligned pointers): every source vector is read once and written `copies` times — no
+// per-element 64-bit modulo, four times fewer memory instructions
+__global__ void expand4_kernel(const float4* src, long long per4, int copies, float4* dst) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = src[i];
+    for (int c = 0; c < copies; ++c) dst[(long long)c * per4 + i] = v;
+  }
+}
+__global__ void expand4_bwd_kernel(const float4* ddst, long long per4, int copies, float4* dsrc, int acc) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per4; i += (long long)gridDim.x * blockDim.x) {
+    float4 s = acc ? dsrc[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < copies; ++c) {
+      const float4 v = ddst[(long long)c * per4 + i];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    dsrc[i] = s;
+  }
+}
 // dsrc[b, :] (+)= sum_c ddst[(c*Bs + b), :]
 __global__ void expand_bwd_kernel(const float* ddst, long long row_elems, long long Bs, int copies, float* dsrc, int acc) {
   const long long per = row_elems * Bs;
@@ -158,6 +176,13 @@ extern "C" int vaesne_scatter_rows(const long long* idx, long long T, const floa
 extern "C" int vaesne_expand_rows(const float* src, long long row_elems, long long Bs, int copies, float* dst, void* stream) {
   V_REQUIRE(src && dst, V_ENULL, "expand_rows: null argument");
   if (row_elems * Bs * copies == 0) return V_OK;
+  const long long per = row_elems * Bs;
+  if ((per & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+    auto k4 = expand4_kernel;
+    VLAUNCH(k4, dim3(ew_grid(per / 4, 256)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(src), per / 4, copies,
+            reinterpret_cast<float4*>(dst));
+    return check_launch("expand_rows");
+  }
   auto k = expand_kernel;
   VLAUNCH(k, dim3(ew_grid(row_elems * Bs * copies, 256)), dim3(256), 0, (cudaStream_t)stream, src, row_elems, Bs, copies, dst);
   return check_launch("expand_rows");
@@ -166,6 +191,13 @@ extern "C" int vaesne_expand_rows(const float* src, long long row_elems, long lo
 extern "C" int vaesne_expand_rows_bwd(const float* ddst, long long row_elems, long long Bs, int copies, float* dsrc, int accumulate, void* stream) {
   V_REQUIRE(ddst && dsrc, V_ENULL, "expand_rows_bwd: null argument");
   if (row_elems * Bs == 0) return V_OK;
+  const long long per = row_elems * Bs;
+  if ((per & 3) == 0 && (((uintptr_t)ddst | (uintptr_t)dsrc) & 15) == 0) {
+    auto k4 = expand4_bwd_kernel;
+    VLAUNCH(k4, dim3(ew_grid(per / 4, 256)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<const float4*>(ddst), per / 4, copies,
+            reinterpret_cast<float4*>(dsrc), accumulate);
+    return check_launch("expand_rows_bwd");
+  }
   auto k = expand_bwd_kernel;
   VLAUNCH(k, dim3(ew_grid(row_elems * Bs, 256)), dim3(256), 0, (cudaStream_t)stream, ddst, row_elems, Bs, copies, dsrc, accumulate);
   return check_launch("expand_rows_bwd");

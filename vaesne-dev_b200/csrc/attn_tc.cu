@@ -2,31 +2,35 @@
 // (982 decoder tokens / 983 encoder-context tokens, 4 heads x head_dim 8) — forward and backward.
 //
 // Same arithmetic as attn.cu (nn.MultiheadAttention core, util_layers.py:289,297): q*sqrt(1/8), QK^T,
-// key-padding mask, softmax, dropout(P), PV — restructured for sm_100a.  Three kernels share one skeleton:
+// key-padding mask, softmax, dropout(P), PV — restructured for sm_100a.  The kernels share one skeleton:
 //
-//   pass   TMEM lanes (rows)   staged once per CTA (columns)        per tile
-//   fwd    128 queries         K (hi+lo), V of all unmasked keys    S=QK^T -> P=2^(S-m) -> O += P[V|1]
-//   dq     128 queries         K (hi+lo), V, K                      S, T=dO V^T -> dS=P(T-delta) -> dQ += dS K
-//   dkv    128 keys            Q (hi+lo), dO, Q, dO, lse, delta     S^T, T^T -> P^T, dS^T -> dV += P^T dO, dK += dS^T Q
+//   kernel        TMEM lanes (rows)   staged once per CTA (columns)           per tile
+//   fwd4 (default) 128 queries x 4 wg  K (tf32 hi+lo), V (fp16 hi|lo)          S=QK^T (64 keys) -> P=2^(S-m) -> O += P V
+//   bwd  (default) 128 keys   x 2 wg   Q, dO (fp16 hi|lo), lse, delta, words   S^T, T^T -> P^T, dS^T -> dV += P^T dO, dK += dS^T Q,
+//                                                                              dS^T also to smem -> dQ += dS K (per tile pair)
+//   fwd           128 queries x 2 wg   as fwd4, 128-key tiles                  kept for comparison (VAESNE_TC_FWD2)
+//   dq + dkv      queries / keys       tf32 operands                           the two-pass backward (VAESNE_TC_BWD_SPLIT)
 //
-//   * one CTA per (batch row, head); the column-side operands are staged ONCE in shared memory as K-major
-//     tcgen05 operand tiles.  Masked keys are compacted away while staging — the key-padding mask is never
-//     materialised and masked keys cost nothing.
-//   * the score products run on the tensor core (tcgen05.mma kind::tf32, M=128, K=8) with fp32 accumulation in
-//     TMEM.  kind::tf32 truncates its inputs to 10 mantissa bits, so the operands of S are pre-split into
-//     tf32 hi + lo parts (3 MMAs) which restores fp32-level scores; the other operands are rounded to nearest.
-//   * the row-side operands (Q or K/V/dO rows) live in TMEM: each thread stores its own row, no smem staging.
-//   * two 128-row tiles are in flight, each owned by one warpgroup whose thread r holds row r (32x32b TMEM
-//     loads: max / exp / sum need no shuffles).  P (and dS) are written back over S (and T) in TMEM and used
-//     directly as the A operand of the second product (tcgen05.mma .ts form, N=16).
-//   * a ninth warp issues all MMAs from ONE ELECTED lane (elect.sync: without it ptxas wraps every UTCMMA in
-//     a divergence loop, 103 instead of 24 clk per issue — tests/probe/tc_rates.cu) and tracks completion
+//   * one CTA per (batch row, head); the column-side operands are staged ONCE in shared memory as tcgen05 operand
+//     tiles.  Masked keys are compacted away while staging — the key-padding mask is never materialised and masked
+//     keys cost nothing.
+//   * every product runs on the tensor core with fp32 accumulation in TMEM.  Scores need fp32-level inputs (an absolute
+//     error in S is a relative error in P): kind::tf32 truncates to 10 mantissa bits, so S uses hi + lo operand pairs —
+//     tf32 (3 MMAs) in the forward, fp16 [hi | lo] with K = 16 (2 MMAs) in the fused backward; P and dS are 11-bit
+//     operands (fp16, exact power-of-two range management), i.e. TF32-class second products.
+//   * the row-side operands (Q or K/V rows) live in TMEM: each thread stores its own row, no smem staging.
+//   * each warpgroup owns a 128-row tile whose thread r holds row r (32x32b TMEM loads: max / exp / sum need no
+//     shuffles); P (and dS) go back to a separate TMEM region as fp16 pairs and are the A operand of the second
+//     product (tcgen05.mma .ts form), so the next tile's first product runs under this tile's exponentials.
+//   * one extra warp per warpgroup issues its MMAs from ONE ELECTED lane (elect.sync: without it ptxas wraps every
+//     UTCMMA in a divergence loop, 103 instead of 24 clk per issue — tests/probe/tc_rates.cu) and tracks completion
 //     with tcgen05.commit -> mbarrier.
 //   * dropout keeps element (query i, key slot c) iff  A_i * B_c >= p * 2^32  (A_i odd per-query hash word,
-//     B_c per-slot hash word): two integer ops per element in either orientation, so the row-major passes and
-//     the key-major pass regenerate identical masks.  tests/attn_tc_ref.py restates it in numpy.
+//     B_c per-slot hash word): two integer ops per element in either orientation, so the row-major forward and
+//     the key-major backward regenerate identical masks.  tests/attn_tc_ref.py restates it in numpy.
 //
-// At head_dim 8 the kernel is bound by MUFU.EX2 (16/clk/SM: 32 tensor FLOP per exponential); see DESIGN.md.
+// At head_dim 8 the kernels are bound by MUFU.EX2 and instruction issue, not by tensor math (32 tensor FLOP per
+// exponential); see DESIGN.md §4.
 #include "common.cuh"
 #include "vaesne_b200.h"
 #include "attn_args.cuh"

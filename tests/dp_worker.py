@@ -34,10 +34,32 @@ def data(B):
     return x, us
 
 
+def step_torch_optimizer_accumulating(model, x, us):
+    """What a reference script does — torch.optim.AdamW, nothing that knows about the buckets — plus gradient accumulation
+    over two backward passes: the gradients must be fully reduced when backward() returns, and the second pass must add
+    REDUCED values to the first pass's (reduced) gradients."""
+    from VAESNe import _noise
+    from VAESNe.losses import m_iwae
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2)
+    total = 0.0
+    for _ in range(2):
+        _noise.clear()
+        _noise.inject(us)
+        loss = -m_iwae(model, x, K=2)
+        loss.backward()
+        total += float(loss.detach())
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}     # read BEFORE any optimiser
+    opt.step()
+    params = {n: p.detach().clone() for n, p in model.named_parameters()}
+    return total, grads, params
+
+
 def step(model, x, us, objective, average):
     from VAESNe import _noise
     from VAESNe.losses import elbo, m_iwae
     from VAESNe.optim import FusedAdamW
+    if objective == "accumulate":
+        return step_torch_optimizer_accumulating(model, x, us)
     opt = FusedAdamW(model.parameters(), lr=1e-2, grad_average=average)
     _noise.clear()
     if objective == "elbo":

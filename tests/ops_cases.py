@@ -174,8 +174,26 @@ def attn_reference(q, k, v, mask_full, dO):
 
 
 def make_attn_inputs(c, device, scale=1.0):
+    """`scale` is one factor for q, k and v, or a (q, k, v, dO) tuple of factors (operand-range tests)."""
     g = _g(zlib.crc32(c["id"].encode()) % 10000)
     N, Lq, Lk = c["N"], c["Lq"], c["Lk"]
+    if isinstance(scale, tuple):
+        sq, sk, sv, sg = scale
+        cols = torch.cat([torch.full((32,), float(f)) for f in (sq, sk, sv)])
+        if c["packed"] == "qkv":
+            qkv = torch.randn(N, Lq, 96, generator=g) * cols
+            q, k, v = qkv[..., :32], qkv[..., 32:64], qkv[..., 64:]
+            bufs = (qkv.to(device),)
+            qd, kd, vd = bufs[0][..., :32], bufs[0][..., 32:64], bufs[0][..., 64:]
+        else:
+            qb = torch.randn(N, Lq, 32, generator=g) * sq
+            kv = torch.randn(N, Lk, 64, generator=g) * cols[32:]
+            q, k, v = qb, kv[..., :32], kv[..., 32:]
+            bufs = (qb.to(device), kv.to(device))
+            qd, kd, vd = bufs[0], bufs[1][..., :32], bufs[1][..., 32:]
+        mask, mask_full = _attn_mask(c, g)
+        dO = torch.randn(N, Lq, 32, generator=g) * sg
+        return (q, k, v, mask, mask_full, dO), (qd, kd, vd)
     if c["packed"] == "qkv":
         qkv = torch.randn(N, Lq, 96, generator=g) * scale
         q, k, v = qkv[..., :32], qkv[..., 32:64], qkv[..., 64:]
@@ -187,6 +205,13 @@ def make_attn_inputs(c, device, scale=1.0):
         q, k, v = qb, kv[..., :32], kv[..., 32:]
         bufs = (qb.to(device), kv.to(device))
         qd, kd, vd = bufs[0], bufs[1][..., :32], bufs[1][..., 32:]
+    mask, mask_full = _attn_mask(c, g)
+    dO = torch.randn(N, Lq, 32, generator=g)
+    return (q, k, v, mask, mask_full, dO), (qd, kd, vd)
+
+
+def _attn_mask(c, g):
+    N, Lk = c["N"], c["Lk"]
     mask = mask_full = None
     if c.get("mask"):
         rows = c.get("mask_rows", N)
@@ -195,8 +220,7 @@ def make_attn_inputs(c, device, scale=1.0):
         mask[:, 0] = False
         mask_full = torch.zeros(N, Lk, dtype=torch.bool)
         mask_full[:, :mlen] = mask[torch.arange(N) % rows]
-    dO = torch.randn(N, Lq, 32, generator=g)
-    return (q, k, v, mask, mask_full, dO), (qd, kd, vd)
+    return mask, mask_full
 
 
 def run_attn_case(c, device, fwd=None, bwd=None, tol=TOL, scale=1.0):

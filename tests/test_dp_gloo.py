@@ -21,7 +21,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("objective", ["m_iwae", "elbo", "contrast"])
+@pytest.mark.parametrize("objective", ["m_iwae", "elbo", "contrast", "accumulate"])
 def test_two_ranks_match_one(emu, tmp_path, objective):
     out = str(tmp_path / "dp.pt")
     port = _free_port()

@@ -1,4 +1,4 @@
-"""Parity of the tcgen05 attention kernels (attn_tc.cu: forward, dQ pass, dK/dV pass) on the B200, through
+"""Parity of the tcgen05 attention kernels (attn_tc.cu: four-warpgroup forward, fused backward) on the B200, through
 the C ABI.  Tolerance: rel 1e-3 (north_star's fp32/TF32 bound) on max|err|/max|ref| per tensor; the
 measured errors are ~2e-4 (P and dS enter the second product as tf32).  Dropout: the kernels' mask is
 restated bit-exactly in numpy (tests/attn_tc_ref.py) and fed to an fp64 reference."""
@@ -35,6 +35,18 @@ def _grads(c, dev):
 @pytest.mark.parametrize("case", CASES, ids=lambda c: c["id"])
 def test_tc_attention_matches_fp64(case, scale):
     OC.run_attn_case(case, "cuda", tol=TC_TOL, scale=scale)
+
+
+# fp16 operands of the tcgen05 kernels (V in the forward; Q, K, V, dO in the fused backward) are range-managed by exact
+# powers of two, so magnitudes far outside fp16's 6e-5 .. 65504 must not change the accuracy.  (q, k, v, dO) factors; the
+# q*k product is kept moderate so the softmax stays non-degenerate.
+RANGE_SCALES = [(300.0, 1.0 / 300.0, 1e5, 1.0), (1e-4, 1e4, 1e-6, 1e6), (3e5, 1e-5 / 3.0, 30.0, 1e-7), (1.0, 1.0, 7e4, 3e4)]
+
+
+@pytest.mark.parametrize("scales", RANGE_SCALES, ids=lambda s: "q%g_k%g_v%g_g%g" % s)
+@pytest.mark.parametrize("case", [CASES[0], CASES[3]], ids=lambda c: c["id"])
+def test_tc_attention_operand_range(case, scales):
+    OC.run_attn_case(case, "cuda", tol=TC_TOL, scale=scales)
 
 
 @pytest.mark.parametrize("case", CASES[:2] + CASES[-2:], ids=lambda c: c["id"])

@@ -16,6 +16,25 @@ from . import _stacks as S
 from . import parallel
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def dev_guard(device):
+    """The kernels are enqueued on torch's current stream OF THE TENSORS' DEVICE; a model that lives on a device other than the
+    process's current one (device='cuda:1' without torch.cuda.set_device) therefore runs under a device guard."""
+    if device.type == "cuda" and device.index is not None and device.index != torch.cuda.current_device():
+        return torch.cuda.device(device)
+    return _NO_GUARD
+
+
 def _prep(t: Optional[torch.Tensor], dtype=None):
     if t is None:
         return None
@@ -35,42 +54,54 @@ class _StackFn(torch.autograd.Function):
         data, params = args[:n_data], args[n_data:]
         need = any(ctx.needs_input_grad)
         dev = params[0].device
-        tape = S.Tape(need, drop_p, dev)
-        pv = S.PView(names, [p.detach() for p in params])
-        out = runner(tape, pv, *[d.detach() if isinstance(d, torch.Tensor) else d for d in data])
+        with dev_guard(dev):
+            tape = S.Tape(need, drop_p, dev)
+            pv = S.PView(names, [p.detach() for p in params])
+            out = runner(tape, pv, *[d.detach() if isinstance(d, torch.Tensor) else d for d in data])
         ctx.tape, ctx.names, ctx.n_data = tape, names, n_data
         ctx.data = data
+        ctx.params = params if need else None
         ctx.pshapes = [tuple(p.shape) for p in params]
         ctx.pdev = dev
-        ctx.out_ref = out
-        return out
+        # only the identity of the output is kept (keeping the tensor would tie out.grad_fn -> ctx -> out into a cycle that
+        # holds the whole tape of a forward that is never back-propagated until the cyclic GC runs)
+        ctx.out_key, ctx.out_shape = S._Bwd.key(out), tuple(out.shape)
+        return out.view(out.shape) if need else out          # the tape's closures hold `out` itself: hand autograd an alias
 
     @staticmethod
     def backward(ctx, dout):
         n_data, names = ctx.n_data, ctx.names
         need = ctx.needs_input_grad[4:]
-        sizes = [int(torch.Size(s).numel()) for s in ctx.pshapes]
-        flat = torch.zeros(sum(sizes), device=ctx.pdev, dtype=torch.float32)
-        pg, views, off = {}, [], 0
-        for i, (name, shp, n) in enumerate(zip(names, ctx.pshapes, sizes)):
-            v = flat[off:off + n].view(shp)
-            off += n
-            views.append(v)
-            pg[name] = v if need[n_data + i] else None
-        bw = S._Bwd(pg)
-        bw.seed(ctx.out_ref, _prep(dout))
-        ctx.tape.backward(bw)
-        parallel.bucket_ready(flat)
-        dgrads = []
-        for i, d in enumerate(ctx.data):
-            if isinstance(d, torch.Tensor) and need[i]:
-                g = bw.take(d.detach())
-                dgrads.append(g if g is not None else torch.zeros_like(d))
-            else:
-                dgrads.append(None)
-        pgrads = [v if need[n_data + i] else None for i, v in enumerate(views)]
+        with dev_guard(ctx.pdev):
+            sizes = [int(torch.Size(s).numel()) for s in ctx.pshapes]
+            flat = torch.zeros(sum(sizes), device=ctx.pdev, dtype=torch.float32)
+            pg, views, off = {}, [], 0
+            for i, (name, shp, n) in enumerate(zip(names, ctx.pshapes, sizes)):
+                v = flat[off:off + n].view(shp)
+                off += n
+                views.append(v)
+                pg[name] = v if need[n_data + i] else None
+            bw = S._Bwd(pg)
+            dout = _prep(dout)
+            bw.seed_key(ctx.out_key, dout if tuple(dout.shape) == ctx.out_shape else dout.view(ctx.out_shape))
+            ctx.tape.backward(bw)
+            if parallel.enabled():
+                # the bucket may travel asynchronously only if autograd ADOPTS its views as .grad: parameters that already hold
+                # a gradient (accumulation, zero_grad(set_to_none=False)) or a stack that already produced a bucket in this
+                # backward pass (its views get summed in place) need the reduced values before autograd touches them
+                params = ctx.params or ()
+                first = not any(p.grad is not None for p in params) and parallel.first_bucket_of(params)
+                parallel.bucket_ready(flat, blocking=not first)
+            dgrads = []
+            for i, d in enumerate(ctx.data):
+                if isinstance(d, torch.Tensor) and need[i]:
+                    g = bw.take(d.detach())
+                    dgrads.append(g if g is not None else torch.zeros_like(d))
+                else:
+                    dgrads.append(None)
+            pgrads = [v if need[n_data + i] else None for i, v in enumerate(views)]
         ctx.tape = None
-        ctx.out_ref = None
+        ctx.params = None
         return (None, None, None, None, *dgrads, *pgrads)
 
 
@@ -101,7 +132,26 @@ def model_dim_of(module: torch.nn.Module) -> int:
     return int(d)
 
 
+def check_geometry(module: torch.nn.Module) -> None:
+    """The fused kernels compute model_dim 32 with 4 heads of head_dim 8 (what every reference script builds).  The number of
+    heads is NOT visible in any parameter shape (in_proj_weight is [3D, D] whatever it is), so it is checked on the
+    nn.MultiheadAttention containers themselves — also for modules unpickled from a reference checkpoint — and anything else
+    raises instead of silently computing with 4 heads (TransformerBlock ctor, util_layers.py:265-271)."""
+    ok = module.__dict__.get("_geom_ok")
+    if ok is None:
+        ok = True
+        for name, sub in module.named_modules():
+            if isinstance(sub, torch.nn.MultiheadAttention) and (sub.embed_dim != 32 or sub.num_heads != 4):
+                ok = (f"{name or type(module).__name__}: embed_dim={sub.embed_dim}, num_heads={sub.num_heads}")
+                break
+        module.__dict__["_geom_ok"] = ok
+    if ok is not True:
+        raise NotImplementedError(
+            f"VAESNe-B200 kernels support model_dim=32 with num_heads=4 (head_dim 8), the geometry of every reference script; got {ok}")
+
+
 def run_stack(module: torch.nn.Module, runner: Callable, data: Sequence):
+    check_geometry(module)
     names, params = zip(*module.named_parameters())
     drop_p = drop_p_of(module) if module.training else 0.0
     return _StackFn.apply(runner, names, len(data), drop_p, *data, *params)
@@ -116,7 +166,8 @@ class _LatentFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, fams, T, fam_prior, pz_mu, pz_s, want_lat, noises, *botts):
         M = len(botts)
-        z, mus, ss, lat, pi = P.latent_fwd([b.detach() for b in botts], noises, fams, T, fam_prior, pz_mu, pz_s, want_lat)
+        with dev_guard(botts[0].device):
+            z, mus, ss, lat, pi = P.latent_fwd([b.detach() for b in botts], noises, fams, T, fam_prior, pz_mu, pz_s, want_lat)
         ctx.cfg = (fams, T, fam_prior, pz_mu, pz_s, want_lat, noises, pi)
         ctx.botts = [b.detach() for b in botts]
         if lat is None:
@@ -132,10 +183,11 @@ class _LatentFn(torch.autograd.Function):
         M = len(ctx.botts)
         dmu = [_prep(g) for g in dms[:M]]
         ds = [_prep(g) for g in dms[M:]]
-        dbotts = P.latent_bwd(ctx.botts, noises, fams, T, fam_prior, pz_mu, pz_s, _prep(dz),
-                              _prep(dlat) if (want_lat and dlat is not None) else None, pi,
-                              dmu if any(g is not None for g in dmu) else None,
-                              ds if any(g is not None for g in ds) else None)
+        with dev_guard(ctx.botts[0].device):
+            dbotts = P.latent_bwd(ctx.botts, noises, fams, T, fam_prior, pz_mu, pz_s, _prep(dz),
+                                  _prep(dlat) if (want_lat and dlat is not None) else None, pi,
+                                  dmu if any(g is not None for g in dmu) else None,
+                                  ds if any(g is not None for g in ds) else None)
         return (None, None, None, None, None, None, None, *dbotts)
 
 

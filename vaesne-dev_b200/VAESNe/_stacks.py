@@ -58,6 +58,10 @@ class _Bwd:
     def seed(self, t: torch.Tensor, grad: torch.Tensor):
         self.g[self.key(t)] = grad
 
+    def seed_key(self, key: tuple, grad: torch.Tensor):
+        assert key not in self.g and key[1] > 0, "ambiguous activation identity (zero-sized or aliased stack output)"
+        self.g[key] = grad
+
     def peek(self, t: torch.Tensor) -> Optional[torch.Tensor]:
         g = self.g.get(self.key(t))
         return None if g is None else self._as(g, t)

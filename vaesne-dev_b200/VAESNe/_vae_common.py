@@ -43,10 +43,19 @@ class FusedVAEMixin:
         scale = masked_scale_tensor(x[3], self._big, loc[0])
         return self.px_z(loc, scale.unsqueeze(0).expand(loc.shape))
 
+    def _posterior_params(self, x):
+        """(mu, scale) of q(z|x) without drawing a sample: neither the global RNG nor an injected noise tensor is consumed
+        (the reference's encode() does not sample, PhotometricVAE.py:179-186)."""
+        bott = self._bottleneck(x)
+        fq = P.FAMILY[_noise.family_of(self.qz_x)]
+        zero = torch.zeros(1, bott.shape[0], self.latent_len, bott.shape[2], device=bott.device)
+        _, _, mus, ss = latent_step([bott], [zero], [fq], self.latent_len)
+        return mus[0], ss[0]
+
     def encode(self, x, mean=True):
         self.eval()
         with torch.no_grad():
-            _, mu, s = self._sample(x, 1)
+            mu, s = self._posterior_params(x)
             qz_x = self.qz_x(mu, s)
         return qz_x.mean if mean else qz_x
 

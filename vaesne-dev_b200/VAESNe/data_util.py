@@ -53,7 +53,9 @@ class ResidentLoader:
         self.generator, self.rank, self.world = generator, int(rank), int(world)
 
     def _local_count(self):
-        return len(range(self.rank, self.n, self.world))
+        # every rank serves the SAME number of samples (the n % world leftovers of an epoch's permutation are dropped): ranks
+        # with different step counts, or different last-batch sizes, would dead-lock in / skew the gradient all-reduce
+        return self.n // self.world
 
     def __len__(self):
         m = self._local_count()
@@ -66,8 +68,21 @@ class ResidentLoader:
             perm = torch.randperm(self.n, device=self.device, generator=g)
         else:
             perm = torch.arange(self.n, device=self.device)
-        perm = perm[self.rank::self.world]
+        perm = perm[:(self.n // self.world) * self.world][self.rank::self.world]
         for i in range(len(self)):
             idx = perm[i * self.batch_size:(i + 1) * self.batch_size]
             batch = [tuple(t.index_select(0, idx) for t in mod) for mod in self.mods]
             yield batch if self.multimodal else batch[0]
+
+
+def _image_dataset_stub(name):
+    class _Stub(Dataset):
+        def __init__(self, *args, **kwargs):
+            raise NotImplementedError(f"VAESNe-B200: data_util.{name} (host-galaxy image datasets, reference data_util.py:23-73) is outside "
+                                      "the accelerated photometry/spectra path and is not provided")
+    _Stub.__name__ = name
+    return _Stub
+
+
+ImagePathDataset = _image_dataset_stub("ImagePathDataset")
+ImagePathDatasetAug = _image_dataset_stub("ImagePathDatasetAug")

@@ -37,6 +37,12 @@ def elbo(model, x, K=1, debug=False):
     return (lpx_z.sum(-1) - kld.sum((-1, -2))[None, :]).mean()
 
 
+def m_elbo(model, x, K=1):
+    """The reference's m_elbo (losses.py:27-44) is dead code that cannot run (it drops K and sums over dimension -3.0); it is
+    outside the accelerated path and is not emulated."""
+    raise NotImplementedError("VAESNe-B200: losses.m_elbo is dead/broken code in the reference (losses.py:27-44) and is not provided; use m_iwae")
+
+
 def _m_iwae(model, x, K=1):
     """Stratified mixture-of-experts IWAE log-weights, [M*K, B] (generic torch.distributions form)."""
     qz_xs, px_zs, zss = model(x, K)

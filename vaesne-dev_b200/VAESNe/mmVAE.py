@@ -13,6 +13,14 @@ from . import _ops as P
 from ._functions import latent_step
 
 
+class MMVAE(nn.Module):
+    """Generic base of the reference (mmVAE.py:17-67): unused by every script and inconsistent with the decoder signatures
+    (its off-diagonal `vae.dec(zs)` call, :47); outside the accelerated path."""
+
+    def __init__(self, *args, **kwargs):
+        raise NotImplementedError("VAESNe-B200: the generic MMVAE base (reference mmVAE.py:17-67) is not provided; use photospecMMVAE")
+
+
 class photospecMMVAE(nn.Module):
     def __init__(self, vaes, prior_dist=dist.Laplace, beta=1., length_ratio=982 / 60):
         super().__init__()

@@ -73,6 +73,44 @@ class FusedAdamW(torch.optim.Optimizer):
             i = j
         return ranges
 
+    # ---- checkpointing: the moments and the step counter live in the flat buffers; they are exposed in (and restored from)
+    # torch.optim.AdamW's own state layout, so optimizer.state_dict() files are interchangeable with the reference's optimiser
+    def _mirror_state(self):
+        for st in self._flat:
+            if st is None:
+                continue
+            for p, off, n in zip(st["ps"], st["offs"], st["sizes"]):
+                self.state[p] = {"step": st["step"].to(torch.float32).reshape(()).clone(),
+                                 "exp_avg": st["m"][off:off + n].view(p.shape), "exp_avg_sq": st["v"][off:off + n].view(p.shape)}
+
+    def state_dict(self):
+        self._mirror_state()
+        return super().state_dict()
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        for st in self._flat:
+            if st is None:
+                continue
+            steps = []
+            for p, off, n in zip(st["ps"], st["offs"], st["sizes"]):
+                s = self.state.get(p)
+                if not s:
+                    continue
+                st["m"][off:off + n].copy_(s["exp_avg"].reshape(-1))
+                st["v"][off:off + n].copy_(s["exp_avg_sq"].reshape(-1))
+                steps.append(int(float(s["step"])))
+            if steps:
+                if len(set(steps)) != 1:
+                    raise ValueError("FusedAdamW keeps one step counter per parameter group; the loaded state has several")
+                st["step"].fill_(steps[0])
+        self._mirror_state()
+
+    def hyper_signature(self):
+        """What a captured CUDA graph of step() has baked in as host scalars (training_util re-captures when it changes)."""
+        return tuple((float(g["lr"]), tuple(float(b) for b in g["betas"]), float(g["eps"]), float(g["weight_decay"])) for g in self.param_groups)
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None

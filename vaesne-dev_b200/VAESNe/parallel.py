@@ -49,14 +49,52 @@ def world_size() -> int:
     return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
 
 
-def bucket_ready(flat: torch.Tensor) -> None:
-    """Called by a stack's backward when its flat gradient bucket is final."""
-    if _enabled:
+_seen_this_pass: set = set()
+_callback_queued = False
+
+
+def _end_of_backward() -> None:
+    """Runs when the autograd engine has finished the backward pass: every bucket is reduced before ANY optimiser
+    (torch.optim.AdamW as in the reference scripts, or the fused one) can read a gradient."""
+    global _callback_queued
+    _callback_queued = False
+    _seen_this_pass.clear()
+    wait_all()
+
+
+def first_bucket_of(params) -> bool:
+    """True the first time a stack (identified by its first parameter) reports a bucket in the current backward pass."""
+    if not params:
+        return True
+    key = params[0].data_ptr()
+    if key in _seen_this_pass:
+        return False
+    _seen_this_pass.add(key)
+    return True
+
+
+def bucket_ready(flat: torch.Tensor, blocking: bool = False) -> None:
+    """Called by a stack's backward when its flat gradient bucket is final.  Asynchronous by default (the bucket travels while
+    the remaining backward runs); `blocking` reduces it — and everything still in flight — before returning, for buckets whose
+    views autograd is going to ADD to existing gradients instead of adopting them."""
+    global _callback_queued
+    if not _enabled:
+        return
+    if not _callback_queued:
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(_end_of_backward)
+            _callback_queued = True
+        except RuntimeError:          # not inside a backward pass (a direct call): the caller waits explicitly
+            pass
+    if blocking:
+        wait_all()
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    else:
         _pending.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True))
 
 
 def wait_all() -> None:
-    """Called by the optimiser before it reads gradients."""
+    """Idempotent: called at the end of every backward pass and again by the fused optimiser before it reads gradients."""
     while _pending:
         _pending.pop().wait()
 

@@ -74,7 +74,11 @@ class GraphedStep:
     def __call__(self, x, device):
         from . import parallel
         leaves = _leaves(x, self.multimodal)
-        sig = tuple((tuple(t.shape), t.dtype) for t in leaves)
+        # learning rate / betas / eps / weight decay enter the captured kernels as host scalars: a scheduler or a param_group
+        # edit therefore selects (captures) another graph instead of silently replaying the old values
+        hyper = tuple((float(g.get("lr", 0.0)), float(g.get("weight_decay", 0.0)), tuple(g.get("betas", ())), float(g.get("eps", 0.0)))
+                      for g in self.optimizer.param_groups)
+        sig = tuple((tuple(t.shape), t.dtype) for t in leaves) + (hyper,)
         e = self.entries.setdefault(sig, dict(seen=0))
         if e.get("eager") or device.type != "cuda" or parallel.enabled():
             return self._eager(x, device)

@@ -49,10 +49,6 @@ constexpr int NTHREADS = 320;       // 8 softmax warps (2 warpgroups) + 1 MMA-is
 constexpr float kScale = 0.35355339059327373f;             // sqrt(1/8)
 constexpr float kQScale = kScale * 1.4426950408889634f;    // ... * log2(e)
 constexpr float kLazy = 8.f;        // rescale O only when the row max grows by more than 2^8
-#ifndef VAESNE_TC_SPLIT_T
-#define VAESNE_TC_SPLIT_T 1
-#endif
-constexpr bool kSplitT = VAESNE_TC_SPLIT_T != 0;   // dP = dO V^T with hi/lo-split operands (3 MMAs) or rounded operands (1 MMA)
 constexpr int RPT = (MAXL + NTHREADS - 1) / NTHREADS;   // staged rows per thread
 constexpr int TILE_F = MAXL * 8;    // floats of one staged operand array (32 KB)
 
@@ -150,6 +146,20 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 __device__ __forceinline__ float pow2_normaliser(float amax) {
   const uint32_t e = (__float_as_uint(amax) >> 23) & 255u;
   return (e == 0u || e >= 254u) ? 1.f : __uint_as_float((254u - e) << 23);
+}
+// range management of the fp16 operands: an exact power of two (clamped to 2^+-40 so that products of two normalisers stay
+// finite) that brings the largest magnitude of a row set into [1, 2); non-finite maxima leave the data alone (the results are
+// then non-finite as in fp32 arithmetic)
+__device__ __forceinline__ float pow2_normaliser_c(float amax) {
+  uint32_t e = (__float_as_uint(amax) >> 23) & 255u;
+  if (e == 0u || e >= 254u) return 1.f;
+  e = e < 87u ? 87u : (e > 167u ? 167u : e);
+  return __uint_as_float((254u - e) << 23);
+}
+__device__ __forceinline__ uint32_t absmax8_bits(const float* x, uint32_t m) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) m = max(m, __float_as_uint(fabsf(x[c])));     // non-negative floats order like their bit patterns; NaN/inf sort last
+  return m;
 }
 __device__ __forceinline__ void split8(const float* x, float* hi, float* lo) {
 #pragma unroll
@@ -250,7 +260,7 @@ __device__ __forceinline__ void load_key_rows(const AttnArgs& a, int n, int h, i
 template <int NT>
 __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, int n, int h, int tid, int LkC, int tile,
                                            float* Khi, float* Klo, float* V1hi, float* V1lo, __half* V2h, __half* K2h,
-                                           const TcDrop& dc, const KeyRowsT<NT>& kr) {
+                                           const TcDrop& dc, const KeyRowsT<NT>& kr, float vscale = 1.f) {
   const int Lpad = ((LkC + tile - 1) / tile) * tile;
   float z[8];
 #pragma unroll
@@ -274,8 +284,24 @@ __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, i
     if (K2h) put_l2h(K2h, c, kr.kk[u]);
     split8(kr.vv[u], hi, lo);
     if (V1hi) { put_l1(V1hi, c, hi); put_l1(V1lo, c, lo); }
-    if (V2h) put_l2h(V2h, c, kr.vv[u]);
+    if (V2h) {
+      float vs[8];
+#pragma unroll
+      for (int c2 = 0; c2 < 8; ++c2) vs[c2] = kr.vv[u][c2] * vscale;
+      put_l2h(V2h, c, vs);
+    }
   }
+}
+// largest |v| over the rows a CTA holds in registers -> s.pre[33] (cleared before compact_keys); returns after a barrier
+template <int NT>
+__device__ __forceinline__ float v_normaliser(const TcSmem& s, const KeyRowsT<NT>& kr, int lane) {
+  uint32_t m = 0u;
+#pragma unroll
+  for (int u = 0; u < KeyRowsT<NT>::R; ++u) m = absmax8_bits(kr.vv[u], m);
+  m = __reduce_max_sync(0xffffffffu, m);
+  if (lane == 0) atomicMax(&s.pre[33], m);
+  __syncthreads();
+  return pow2_normaliser_c(__uint_as_float(s.pre[33]));
 }
 
 // =================================================================================================
@@ -341,169 +367,6 @@ struct WgPhase {
 __device__ __forceinline__ void signal_in_free(uint64_t* b) { fence_before(); mbar_arrive(&b[B_F]); }
 
 // =================================================================================================
-// forward
-// =================================================================================================
-constexpr size_t FWD_SMEM = tc_smem_bytes(3, false);
-
-__global__ void __launch_bounds__(NTHREADS, 1) attn_tc_fwd_kernel(AttnArgs a) {
-  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-  const TcSmem s = carve(tc_smem_raw, 3, false);
-  float* Khi = s.arr[0]; float* Klo = s.arr[1]; __half* V2h = reinterpret_cast<__half*>(s.arr[2]);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
-  const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
-
-  KeyRows kr;
-  load_key_rows(a, n, h, tid, kr);
-  init_pipeline(s, tid, warp);
-  const int LkC = compact_keys(a, s, n, tid, warp, lane);
-  stage_keys(a, s, n, h, tid, LkC, FK, Khi, Klo, nullptr, nullptr, V2h, nullptr, dc, kr);
-  fence_async_smem();
-  fence_before();
-  __syncthreads();
-  fence_after();
-  const uint32_t tb = *s.tmem;
-  const int T = (LkC + FK - 1) / FK;
-  const int nQT = (a.Lq + TCQ - 1) / TCQ;
-  // per warpgroup: IN = S (128 columns) ; OUT = P as fp16 pairs (64) ; ACC = O hi (8) | O lo (8) ; X = Q hi (8) | Q lo (8)
-
-  if (warp >= 8) {
-    const int w = warp - 8;
-    const uint32_t idQK = idesc_tf32(128, FK), idPV = idesc_f16(128, 16);
-    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV2 = smem_u32(V2h);
-    const uint32_t tw = tb + (uint32_t)(w * C_WG);
-    auto issue_qk = [&](int j) {
-      const uint32_t d = tw + C_IN, q = tw + C_X;
-      const uint64_t dKhi = smem_desc(aKhi + j * (FK * 32), 128, 256), dKlo = smem_desc(aKlo + j * (FK * 32), 128, 256);
-      mma_ts(d, q, dKhi, idQK, 0);
-      mma_ts(d, q + 8, dKhi, idQK, 1);
-      mma_ts(d, q, dKlo, idQK, 1);
-    };
-    auto issue_pv = [&](int j) {
-      const int nsteps = (min(FK, LkC - j * FK) + 15) >> 4;      // 16 keys per kind::f16 MMA
-      for (int t = 0; t < nsteps; ++t) {
-        const uint32_t v = aV2 + (uint32_t)(j * (FK / 16) + t) * 256;
-        mma_ts_f16(tw + C_ACC, tw + C_OUT + (uint32_t)t * 8, smem_desc(v, 128, HALF_ARR * 2), idPV, (j > 0 || t > 0) ? 1u : 0u);   // [Vhi | Vlo]
-      }
-    };
-    mma_issuer(s.bars + w * B_PER_WG, w, nQT, T, issue_qk, issue_pv);
-  } else {
-    const int wg = warp >> 2, r = tid & 127;
-    uint64_t* bars = s.bars + wg * B_PER_WG;
-    const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * C_WG);
-    const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tO = tw + C_ACC, tQ = tw + C_X;
-    WgPhase ph = {0, 0};
-    int it = 0;
-    for (int qt = wg; qt < nQT; qt += 2, ++it) {
-      const int i = qt * TCQ + r;
-      const bool valid = i < a.Lq;
-      if (T == 0) {       // every key masked: softmax of an empty set (the reference yields NaN)
-        if (valid) {
-          float* op = a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8;
-          for (int c = 0; c < 8; ++c) op[c] = __int_as_float(0x7fc00000);
-          a.LSE[(long long)nh * a.Lq + i] = -INFINITY;
-        }
-        continue;
-      }
-      {   // Q row -> TMEM (scaled, hi/lo split)
-        float q[8], hi[8], lo[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) q[c] = 0.f;
-        if (valid) {
-          ld8g(q, a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) q[c] *= kQScale;
-        }
-        split8(q, hi, lo);
-        tmem_put8(tQ, hi); tmem_put8(tQ + 8, lo);
-        tmem_wait_st();
-        fence_before();
-        mbar_arrive(&bars[B_X]);
-      }
-      const uint32_t rw = dc.on ? drop_row_word(dc, nh, a.Lq, valid ? i : 0) : 1u;
-      float m_used = -1e30f, lsum = 0.f;
-      for (int j = 0; j < T; ++j) {
-        ph.wait_s(bars);
-        const int nvalid = min(FK, LkC - j * FK);
-        uint32_t sr[128];
-        tmem_ld32(tIN, sr); tmem_ld32(tIN + 32, sr + 32); tmem_ld32(tIN + 64, sr + 64); tmem_ld32(tIN + 96, sr + 96);
-        tmem_wait_ld();
-        if (j + 1 < T) signal_in_free(bars);          // QK^T of the next tile runs under this tile's softmax
-        float mt = -1e30f;
-        if (nvalid == FK) {
-#pragma unroll
-          for (int c = 0; c < 128; c += 2) mt = max3(mt, __uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));      // FMNMX3: half the issue slots
-        } else {
-#pragma unroll
-          for (int c = 0; c < 128; ++c) { if (c >= nvalid) sr[c] = 0xff800000u; mt = fmaxf(mt, __uint_as_float(sr[c])); }
-        }
-        const float m_new = fmaxf(m_used, mt);
-        const bool resc = __any_sync(0xffffffffu, m_new > m_used + kLazy);    // warp-uniform: TMEM ld/st are warp-collective
-        float alpha = 1.f;
-        if (resc) { alpha = ex2(m_used - m_new); lsum *= alpha; m_used = m_new; }   // first tile: 2^(-1e30 - m) = 0
-        // the row sum stays in fp32 registers (it defines LSE, which the backward exponentiates); the MMA operand is P
-        // rounded to nearest fp16 (11 significant bits, like tf32; P <= 2^8 by the lazy rescale): 64 TMEM columns
-        uint32_t pk[64];
-        if (!dc.on) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const float p0 = ex2(__uint_as_float(sr[2 * c]) - m_used), p1 = ex2(__uint_as_float(sr[2 * c + 1]) - m_used);
-            lsum += p0 + p1;
-            pk[c] = pack_h2(p0, p1);
-          }
-        } else {
-          const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * FK);
-#pragma unroll
-          for (int cc = 0; cc < 32; ++cc) {
-            const uint4 bq = bw[cc];
-            const uint32_t bb[4] = {bq.x, bq.y, bq.z, bq.w};
-            float pp[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float p = ex2(__uint_as_float(sr[cc * 4 + e]) - m_used);
-              lsum += p;
-              pp[e] = (rw * bb[e] >= dc.thr) ? p : 0.f;
-            }
-            pk[cc * 2] = pack_h2(pp[0], pp[1]); pk[cc * 2 + 1] = pack_h2(pp[2], pp[3]);
-          }
-        }
-        if (j > 0) {
-          ph.wait_out_free(bars);                    // PV of tile j-1 has consumed OUT and updated O
-          if (resc) {
-            uint32_t o[16];
-            tmem_ld16(tO, o); tmem_wait_ld();
-#pragma unroll
-            for (int c = 0; c < 16; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-            tmem_st16(tO, o);
-          }
-        }
-        tmem_st32(tOUT, pk); tmem_st32(tOUT + 32, pk + 32);
-        tmem_wait_st();
-        fence_before();
-        mbar_arrive(&bars[B_P]);
-      }
-      // epilogue: (O_hi + O_lo) / l
-      mbar_wait(&bars[B_O], it & 1);
-      fence_after();
-      uint32_t o[16];
-      tmem_ld16(tO, o); tmem_wait_ld();
-      if (valid) {
-        const float inv = dc.scale / lsum;
-        float out[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) out[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * inv;
-        st8g(a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8, out);
-        a.LSE[(long long)nh * a.Lq + i] = (m_used + log2f(lsum)) * kLn2;
-      }
-      fence_before();
-    }
-  }
-  fence_before();
-  __syncthreads();
-  if (warp == 8) { fence_after(); tmem_dealloc<512>(tb); }
-}
-
-// =================================================================================================
 // forward, four warpgroups (default): same arithmetic and pipeline as attn_tc_fwd_kernel with 64-key tiles, so that a
 // warpgroup needs 128 TMEM columns (IN 64 | OUT 32 | ACC 16 | X 16) and FOUR query tiles are in flight per CTA.
 // The exponentiation loop is a dependent chain per thread (subtract, MUFU, accumulate, convert) and with two warps per
@@ -543,8 +406,11 @@ __global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 16) tmem_alloc<512>(s.tmem);
+  if (tid == 0) s.pre[33] = 0u;
   const int LkC = compact_keys<F4_THREADS>(a, s, n, tid, warp, lane);
-  stage_keys<F4_THREADS>(a, s, n, h, tid, LkC, F4_FK, Khi, Klo, nullptr, nullptr, V2h, nullptr, dc, kr);
+  // V is an fp16 [hi | lo] operand: normalised per (row, head) by an exact power of two, undone in the epilogue
+  const float vnorm = v_normaliser<F4_THREADS>(s, kr, lane);
+  stage_keys<F4_THREADS>(a, s, n, h, tid, LkC, F4_FK, Khi, Klo, nullptr, nullptr, V2h, nullptr, dc, kr, vnorm);
   fence_async_smem();
   fence_before();
   __syncthreads();
@@ -674,7 +540,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a)
       uint32_t o[16];
       tmem_ld16(tO, o); tmem_wait_ld();
       if (valid) {
-        const float inv = dc.scale / lsum;
+        const float inv = dc.scale / (lsum * vnorm);
         float out[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) out[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * inv;
@@ -690,384 +556,6 @@ __global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a)
 }
 
 // =================================================================================================
-// backward, pass 1: rows = queries.  delta = dO.O ; dQ = scale * sum_j dS_ij K_j
-// =================================================================================================
-constexpr size_t DQ_SMEM = tc_smem_bytes(5, false);
-
-__global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dq_kernel(AttnArgs a) {
-  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-  const TcSmem s = carve(tc_smem_raw, 5, false);
-  float* Khi = s.arr[0]; float* Klo = s.arr[1]; float* V1 = s.arr[2]; float* V1lo = s.arr[3]; __half* K2h = reinterpret_cast<__half*>(s.arr[4]);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
-  const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
-
-  KeyRows kr;
-  load_key_rows(a, n, h, tid, kr);
-  init_pipeline(s, tid, warp);
-  const int LkC = compact_keys(a, s, n, tid, warp, lane);
-  stage_keys(a, s, n, h, tid, LkC, BK, Khi, Klo, V1, V1lo, nullptr, K2h, dc, kr);
-  fence_async_smem();
-  fence_before();
-  __syncthreads();
-  fence_after();
-  const uint32_t tb = *s.tmem;
-  const int T = (LkC + BK - 1) / BK;
-  const int nQT = (a.Lq + TCQ - 1) / TCQ;
-  // per warpgroup: IN = S (64) | T (64) ; OUT = dS as fp16 pairs (32) ; ACC = dQ hi (8) | lo (8) ; X = Qhi | Qlo | dOhi | dOlo
-
-  if (warp >= 8) {
-    const int w = warp - 8;
-    const uint32_t idS = idesc_tf32(128, BK), idA = idesc_f16(128, 16);
-    const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV1 = smem_u32(V1), aV1lo = smem_u32(V1lo), aK2 = smem_u32(K2h);
-    const uint32_t tw = tb + (uint32_t)(w * C_WG);
-    auto issue_st = [&](int j) {
-      const uint32_t d = tw + C_IN, x = tw + C_X;
-      const uint64_t dKhi = smem_desc(aKhi + j * (BK * 32), 128, 256), dKlo = smem_desc(aKlo + j * (BK * 32), 128, 256);
-      mma_ts(d, x, dKhi, idS, 0);
-      mma_ts(d, x + 8, dKhi, idS, 1);
-      mma_ts(d, x, dKlo, idS, 1);
-      const uint64_t dVhi = smem_desc(aV1 + j * (BK * 32), 128, 256), dVlo = smem_desc(aV1lo + j * (BK * 32), 128, 256);
-      mma_ts(d + 64, x + 16, dVhi, idS, 0);
-      if (kSplitT) { mma_ts(d + 64, x + 24, dVhi, idS, 1); mma_ts(d + 64, x + 16, dVlo, idS, 1); }
-    };
-    auto issue_acc = [&](int j) {
-      const int nsteps = (min(BK, LkC - j * BK) + 15) >> 4;
-      for (int t = 0; t < nsteps; ++t) {
-        const uint32_t k2 = aK2 + (uint32_t)(j * (BK / 16) + t) * 256;
-        mma_ts_f16(tw + C_ACC, tw + C_OUT + (uint32_t)t * 8, smem_desc(k2, 128, HALF_ARR * 2), idA, (j > 0 || t > 0) ? 1u : 0u);   // [Khi | Klo]
-      }
-    };
-    mma_issuer(s.bars + w * B_PER_WG, w, nQT, T, issue_st, issue_acc);
-  } else {
-    const int wg = warp >> 2, r = tid & 127;
-    uint64_t* bars = s.bars + wg * B_PER_WG;
-    const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * C_WG);
-    const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
-    WgPhase ph = {0, 0};
-    int it = 0;
-    for (int qt = wg; qt < nQT; qt += 2, ++it) {
-      const int i = qt * TCQ + r;
-      const bool valid = i < a.Lq;
-      float q[8], g[8], hi[8], lo[8];
-      float lse2 = INFINITY, delta = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { q[c] = 0.f; g[c] = 0.f; }
-      if (valid) {
-        float o[8];
-        ld8g(q, a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
-        ld8g(g, a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
-        ld8g(o, a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8);
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { q[c] *= kQScale; delta = fmaf(g[c], o[c], delta); }
-        lse2 = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
-        a.delta[(long long)nh * a.Lq + i] = delta;
-      }
-      if (T == 0) {       // every key masked: the reference's gradients are NaN
-        if (valid) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) q[c] = __int_as_float(0x7fc00000);
-          st8g(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, q);
-        }
-        continue;
-      }
-      // dS leaves as fp16: this row's dO (hence dP, delta, dS, dQ: all linear in it) is scaled by a power of two into [1, 2)
-      float gmax = 0.f;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) gmax = fmaxf(gmax, fabsf(g[c]));
-      const float rs = pow2_normaliser(gmax);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) g[c] *= rs * dc.scale;      // dropout scale folded in: dP = (dO * scale) . V
-      delta *= rs;
-      split8(q, hi, lo);
-      tmem_put8(tX, hi); tmem_put8(tX + 8, lo);
-      split8(g, hi, lo);
-      tmem_put8(tX + 16, hi); tmem_put8(tX + 24, lo);
-      tmem_wait_st();
-      fence_before();
-      mbar_arrive(&bars[B_X]);
-      const uint32_t rw = dc.on ? drop_row_word(dc, nh, a.Lq, valid ? i : 0) : 1u;
-      for (int j = 0; j < T; ++j) {
-        ph.wait_s(bars);
-        const int nvalid = min(BK, LkC - j * BK);
-        uint32_t pk[32];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t sr[32], tr[32];
-          tmem_ld32(tIN + half * 32, sr); tmem_ld32(tIN + 64 + half * 32, tr);
-          tmem_wait_ld();
-          if (half == 1 && j + 1 < T) signal_in_free(bars);       // the next tile's first product runs under this one's exponentials
-          float ds[32];
-          const f32x2 nl = pk2(-lse2, -lse2), nd = pk2(-delta, -delta);
-          const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            const int c = cc * 4;
-            float x0, x1, x2, x3;
-            upk2(add2(pk2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), nl), x0, x1);
-            upk2(add2(pk2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])), nl), x2, x3);
-            const f32x2 pa = pk2(ex2(x0), ex2(x1)), pb = pk2(ex2(x2), ex2(x3));
-            float t0 = __uint_as_float(tr[c]), t1 = __uint_as_float(tr[c + 1]), t2 = __uint_as_float(tr[c + 2]), t3 = __uint_as_float(tr[c + 3]);
-            if (dc.on) {        // the dropout scale is folded into the dO row operand: dP arrives scaled
-              const uint4 bq = bw[cc];
-              t0 = (rw * bq.x >= dc.thr) ? t0 : 0.f; t1 = (rw * bq.y >= dc.thr) ? t1 : 0.f;
-              t2 = (rw * bq.z >= dc.thr) ? t2 : 0.f; t3 = (rw * bq.w >= dc.thr) ? t3 : 0.f;
-            }
-            upk2(mul2(pa, add2(pk2(t0, t1), nd)), ds[c], ds[c + 1]);
-            upk2(mul2(pb, add2(pk2(t2, t3), nd)), ds[c + 2], ds[c + 3]);
-          }
-          if (nvalid < BK) {      // padded key slots: exactly zero (2^(-lse) may overflow and inf * 0 would poison the row)
-#pragma unroll
-            for (int c = 0; c < 32; ++c) if (half * 32 + c >= nvalid) ds[c] = 0.f;
-          }
-#pragma unroll
-          for (int c = 0; c < 16; ++c) pk[half * 16 + c] = pack_h2(ds[2 * c], ds[2 * c + 1]);
-        }
-        if (j > 0) ph.wait_out_free(bars);
-        tmem_st32(tOUT, pk);
-        tmem_wait_st();
-        fence_before();
-        mbar_arrive(&bars[B_P]);
-      }
-      mbar_wait(&bars[B_O], it & 1);
-      fence_after();
-      uint32_t o[16];
-      tmem_ld16(tA, o); tmem_wait_ld();
-      if (valid) {
-        float out[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) out[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * (kScale / rs);
-        st8g(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, out);
-      }
-      fence_before();
-    }
-  }
-  fence_before();
-  __syncthreads();
-  if (warp == 8) { fence_after(); tmem_dealloc<512>(tb); }
-}
-
-// =================================================================================================
-// backward, pass 2: rows = (unmasked) keys.  dV = sum_i Pd_ij dO_i ; dK = scale * sum_i dS_ij Q_i
-// =================================================================================================
-constexpr size_t DKV_SMEM = tc_smem_bytes(6, true);
-
-__global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
-  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-  const TcSmem s = carve(tc_smem_raw, 6, true);
-  float* Qhi = s.arr[0]; float* Qlo = s.arr[1]; float* G1 = s.arr[2]; float* G1lo = s.arr[3];
-  __half* Q2h = reinterpret_cast<__half*>(s.arr[4]); __half* G2h = reinterpret_cast<__half*>(s.arr[5]);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
-  const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
-#ifdef VAESNE_TC_PROFILE
-  const long long tk0 = clock64();
-#endif
-
-  init_pipeline(s, tid, warp);
-  const int LkC = compact_keys(a, s, n, tid, warp, lane);
-  // slot -> key index, zero gradients of the masked keys
-  for (int j = tid; j < a.Lk; j += NTHREADS) {
-    const int c = key_slot(s, j);
-    if (c >= 0) { s.idx[c] = (uint16_t)j; continue; }
-    float z[8];
-#pragma unroll
-    for (int c2 = 0; c2 < 8; ++c2) z[c2] = 0.f;
-    st8g(a.dk + ((long long)n * a.Lk + j) * a.lddk + h * 8, z);
-    st8g(a.dv + ((long long)n * a.Lk + j) * a.lddv + h * 8, z);
-  }
-  // P^T and dS^T leave as fp16: dO of this (row, head) is scaled by ONE power of two that brings its largest entry into
-  // [1, 2) (dP, delta, dS, dK, dV are linear in it; entries 2^14 below the largest one lose relative accuracy only).
-  // Query side: every thread owns up to RPT queries; all their loads are issued up front (one latency round trip),
-  // the block-wide max|dO| is reduced, then Q (scaled; L1 hi/lo + L2h), dO (L1 hi/lo + L2h), lse2, delta and the
-  // dropout row words are staged from registers.
-  const int NQ = (a.Lq + BK - 1) / BK;
-  {
-    float q[RPT][8], g[RPT][8], lse2[RPT], delta[RPT];
-    float gm = 0.f;
-#pragma unroll
-    for (int u = 0; u < RPT; ++u) {
-      const int i = tid + u * NTHREADS;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { q[u][c] = 0.f; g[u][c] = 0.f; }
-      lse2[u] = INFINITY; delta[u] = 0.f;
-      if (i < a.Lq) {
-        ld8g(q[u], a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
-        ld8g(g[u], a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
-        lse2[u] = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
-        delta[u] = a.delta[(long long)nh * a.Lq + i];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < RPT; ++u)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) gm = fmaxf(gm, fabsf(g[u][c]));
-    gm = isfinite(gm) ? gm : 0.f;
-    if (tid == 0) s.pre[33] = 0u;
-    __syncthreads();
-    atomicMax(&s.pre[33], __float_as_uint(gm));      // non-negative floats order like their bit patterns
-    __syncthreads();
-    const float sc = pow2_normaliser(__uint_as_float(s.pre[33]));
-#pragma unroll
-    for (int u = 0; u < RPT; ++u) {
-      const int i = tid + u * NTHREADS;
-      if (i >= NQ * BK) continue;
-      float hi[8], lo[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { q[u][c] *= kQScale; g[u][c] *= sc; }
-      split8(q[u], hi, lo);
-      put_l1(Qhi, i, hi); put_l1(Qlo, i, lo); put_l2h(Q2h, i, q[u]);
-      split8(g[u], hi, lo);
-      put_l1(G1, i, hi); put_l1(G1lo, i, lo); put_l2h(G2h, i, g[u]);
-      s.f0[i] = -lse2[u]; s.f1[i] = -delta[u] * sc;          // negated: the loop adds
-      s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
-    }
-  }
-  const float cs_scale = pow2_normaliser(__uint_as_float(s.pre[33]));
-  fence_async_smem();
-  fence_before();
-  __syncthreads();
-  fence_after();
-  const uint32_t tb = *s.tmem;
-  const int nKT = (LkC + TCQ - 1) / TCQ;
-  // per warpgroup: IN = S^T (64) | T^T (64) ; OUT = P^T (32) | dS^T (32) as fp16 pairs ; ACC = dK hi|lo (16) | dV hi|lo (16) ; X = Khi | Klo | Vhi | Vlo
-
-  if (warp >= 8) {
-    const int w = warp - 8;
-    const uint32_t idS = idesc_tf32(128, BK), idA = idesc_f16(128, 16);
-    const uint32_t aQhi = smem_u32(Qhi), aQlo = smem_u32(Qlo), aG1 = smem_u32(G1), aG1lo = smem_u32(G1lo), aQ2 = smem_u32(Q2h), aG2 = smem_u32(G2h);
-    const uint32_t tw = tb + (uint32_t)(w * C_WG);
-    auto issue_st = [&](int j) {
-      const uint32_t d = tw + C_IN, x = tw + C_X;
-      const uint64_t dQhi = smem_desc(aQhi + j * (BK * 32), 128, 256), dQlo = smem_desc(aQlo + j * (BK * 32), 128, 256);
-      mma_ts(d, x, dQhi, idS, 0);
-      mma_ts(d, x + 8, dQhi, idS, 1);
-      mma_ts(d, x, dQlo, idS, 1);
-      const uint64_t dGhi = smem_desc(aG1 + j * (BK * 32), 128, 256), dGlo = smem_desc(aG1lo + j * (BK * 32), 128, 256);
-      mma_ts(d + 64, x + 16, dGhi, idS, 0);
-      if (kSplitT) { mma_ts(d + 64, x + 24, dGhi, idS, 1); mma_ts(d + 64, x + 16, dGlo, idS, 1); }
-    };
-    auto issue_acc = [&](int j) {
-      if (g_tc_dbg & 1) return;
-      const int nsteps = (min(BK, a.Lq - j * BK) + 15) >> 4;
-      const uint32_t dK = tw + C_ACC, dV = dK + 16;
-      for (int t = 0; t < nsteps; ++t) {
-        const uint32_t off = (uint32_t)(j * (BK / 16) + t) * 256;
-        const uint32_t acc = (j > 0 || t > 0) ? 1u : 0u;
-        mma_ts_f16(dV, tw + C_OUT + (uint32_t)t * 8, smem_desc(aG2 + off, 128, HALF_ARR * 2), idA, acc);        // P^T [dOhi | dOlo]
-        mma_ts_f16(dK, tw + C_OUT + 32 + (uint32_t)t * 8, smem_desc(aQ2 + off, 128, HALF_ARR * 2), idA, acc);   // dS^T [Qhi | Qlo]
-      }
-    };
-    mma_issuer(s.bars + w * B_PER_WG, w, nKT, NQ, issue_st, issue_acc);
-  } else {
-    const int wg = warp >> 2, r = tid & 127;
-    uint64_t* bars = s.bars + wg * B_PER_WG;
-    const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * C_WG);
-    const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
-#ifdef VAESNE_TC_PROFILE
-    long long prof[16] = {0}; const long long tstart = clock64(); prof[6] = tstart - tk0;
-#endif
-    WgPhase ph = {0, 0};
-    int it = 0;
-    for (int kt = wg; kt < nKT; kt += 2, ++it) {
-      const int cs = kt * TCQ + r;
-      const bool valid = cs < LkC;
-      const int jk = valid ? (int)s.idx[cs] : 0;
-      float k[8], v[8], hi[8], lo[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) { k[c] = 0.f; v[c] = 0.f; }
-      if (valid) {
-        ld8g(k, a.k + ((long long)n * a.Lk + jk) * a.ldk + h * 8);
-        ld8g(v, a.v + ((long long)n * a.Lk + jk) * a.ldv + h * 8);
-      }
-      split8(k, hi, lo);
-      tmem_put8(tX, hi); tmem_put8(tX + 8, lo);
-      split8(v, hi, lo);
-      tmem_put8(tX + 16, hi); tmem_put8(tX + 24, lo);
-      tmem_wait_st();
-      fence_before();
-      mbar_arrive(&bars[B_X]);
-      const uint32_t cw = dc.on ? drop_col_word(dc, nh, cs) : 1u;
-      for (int j = 0; j < NQ; ++j) {
-        TPROF(0, ph.wait_s(bars));
-#ifdef VAESNE_TC_PROFILE
-        const long long tc0 = clock64();
-#endif
-        uint32_t pk[32], dk2[32];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t sr[32], tr[32];
-          tmem_ld32(tIN + half * 32, sr); tmem_ld32(tIN + 64 + half * 32, tr);
-          tmem_wait_ld();
-          if (half == 1 && j + 1 < NQ) signal_in_free(bars);      // the next tile's first product runs under this one's exponentials
-          const float4* l4 = reinterpret_cast<const float4*>(s.f0 + j * BK + half * 32);
-          const float4* d4 = reinterpret_cast<const float4*>(s.f1 + j * BK + half * 32);
-          const uint4* w4 = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
-          if (!(g_tc_dbg & 2))
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            const float4 lv = l4[cc], dv = d4[cc];          // -lse2, -delta of 4 queries
-            float pp[4], ss[4];
-            const int c = cc * 4;
-            // x = s - lse2 (2 lanes per FADD2), p = 2^x
-            float x0, x1, x2, x3;
-            upk2(add2(pk2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), pk2(lv.x, lv.y)), x0, x1);
-            upk2(add2(pk2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])), pk2(lv.z, lv.w)), x2, x3);
-            const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);
-            const f32x2 pa = pk2(p0, p1), pb = pk2(p2, p3);
-            const f32x2 ta = pk2(__uint_as_float(tr[c]), __uint_as_float(tr[c + 1])), tb2 = pk2(__uint_as_float(tr[c + 2]), __uint_as_float(tr[c + 3]));
-            if (!dc.on) {
-              pp[0] = p0; pp[1] = p1; pp[2] = p2; pp[3] = p3;
-              upk2(mul2(pa, add2(ta, pk2(dv.x, dv.y))), ss[0], ss[1]);
-              upk2(mul2(pb, add2(tb2, pk2(dv.z, dv.w))), ss[2], ss[3]);
-            } else {
-              const uint4 wv = w4[cc];
-              const float m0 = (wv.x * cw >= dc.thr) ? dc.scale : 0.f, m1 = (wv.y * cw >= dc.thr) ? dc.scale : 0.f;
-              const float m2 = (wv.z * cw >= dc.thr) ? dc.scale : 0.f, m3 = (wv.w * cw >= dc.thr) ? dc.scale : 0.f;
-              const f32x2 ma = pk2(m0, m1), mb = pk2(m2, m3);
-              upk2(mul2(pa, ma), pp[0], pp[1]);
-              upk2(mul2(pb, mb), pp[2], pp[3]);
-              upk2(mul2(pa, fma2(ta, ma, pk2(dv.x, dv.y))), ss[0], ss[1]);
-              upk2(mul2(pb, fma2(tb2, mb, pk2(dv.z, dv.w))), ss[2], ss[3]);
-            }
-            pk[half * 16 + cc * 2] = pack_h2(pp[0], pp[1]); pk[half * 16 + cc * 2 + 1] = pack_h2(pp[2], pp[3]);
-            dk2[half * 16 + cc * 2] = pack_h2(ss[0], ss[1]); dk2[half * 16 + cc * 2 + 1] = pack_h2(ss[2], ss[3]);
-          }
-        }
-        TPROF_ADD(1, clock64() - tc0);
-        if (j > 0) TPROF(5, ph.wait_out_free(bars));
-        tmem_st32(tOUT, pk); tmem_st32(tOUT + 32, dk2);
-        TPROF(2, tmem_wait_st());
-        fence_before();
-        mbar_arrive(&bars[B_P]);
-      }
-      TPROF(3, mbar_wait(&bars[B_O], it & 1));
-      fence_after();
-      uint32_t o[32];
-      tmem_ld32(tA, o); tmem_wait_ld();
-      if (valid) {
-        float dk[8], dv[8];
-        const float inv = 1.f / cs_scale;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {      // hi + lo parts; Q carried log2(e)
-          dk[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * (kLn2 * inv);
-          dv[c] = (__uint_as_float(o[16 + c]) + __uint_as_float(o[24 + c])) * inv;
-        }
-        st8g(a.dk + ((long long)n * a.Lk + jk) * a.lddk + h * 8, dk);
-        st8g(a.dv + ((long long)n * a.Lk + jk) * a.lddv + h * 8, dv);
-      }
-      fence_before();
-    }
-#ifdef VAESNE_TC_PROFILE
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { prof[4] = clock64() - tstart; for (int q = 0; q < 7; ++q) g_tc_prof[q] = prof[q]; }
-#endif
-  }
-  fence_before();
-  __syncthreads();
-  if (warp == 8) { fence_after(); tmem_dealloc<512>(tb); }
-}
-
-// =================================================================================================
 // backward, fused single pass (default): the key-major pass above extended by dQ, so S, P, dP and dS are computed ONCE.
 // dQ = scale * sum_keys dS[query, key] K[key] contracts over the TMEM-lane index of dS^T, which no TMEM operand can do;
 // the warpgroup therefore also writes dS^T (the fp16 pairs it stores to TMEM anyway) to shared memory as an MN-major
@@ -1076,12 +564,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_dkv_kernel(AttnArgs a) {
 // contribution in 8 TMEM columns (row m -> lane m).  One CTA owns all of dq[n, :, h], so the contributions of its key tiles are summed
 // with vector reductions into the zero-initialised output — no second pass, no extra exponentials.
 // TMEM is full (IN 128 | OUT 64 | ACC 32 | X 32 per warpgroup), so the dV product takes dO as fp16 hi only and dQ takes K as
-// fp16 hi only (their accumulators are 8 columns instead of 16).  fp16 operands assume |q|, |k|, |v| < 65504 (they are
-// projections of LayerNorm outputs); dO is normalised per (row, head) by an exact power of two.
+// fp16 hi only (their accumulators are 8 columns instead of 16).  every fp16 operand is range-managed by exact powers of two:
+// dO and q per (row, head), k and v per key tile (undone by the exponent's fma, the dropout multiplier and the output scales).
 // =================================================================================================
 constexpr int C_DQ = 216;                    // per warpgroup: ACC = dK hi|lo (192..207) | dV (208..215) | dQ tile (216..223)
 constexpr int DS_BYTES = 128 * 128 * 2, KB_BYTES = 8 * 128 * 2;      // dS^T of a tile pair (128 queries x 128 keys fp16), K rows
-constexpr size_t BWD_SMEM = (size_t)2 * TILE_F * 4 + 2 * DS_BYTES + 2 * KB_BYTES + 3 * MAXL * 4 + MAXL * 2 + 32 * 4 + 36 * 4 + 16 * 8 + 16;
+constexpr size_t BWD_SMEM = (size_t)2 * TILE_F * 4 + 2 * DS_BYTES + 2 * KB_BYTES + 3 * MAXL * 4 + MAXL * 2 + 32 * 4 + 36 * 4 + 16 * 8 + 16 + 32 * 4;
 static_assert(BWD_SMEM <= 232448, "fused backward does not fit the 227 KB shared-memory window");
 
 __device__ __forceinline__ void red_add8(float* p, const float* v) {
@@ -1118,6 +606,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     s.bars = (uint64_t*)(s.pre + 36);
     s.tmem = (uint32_t*)(s.bars + 16);
   }
+  uint32_t* const nrm = s.tmem + 4;        // [2 warpgroups][8 key-tile iterations][k, v]: largest magnitudes of a key tile
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
@@ -1142,7 +631,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     }
   }
   init_pipeline(s, tid, warp);
-  if (tid == 0) { mbar_init(&s.bars[12], 1); mbar_init(&s.bars[13], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); s.pre[33] = 0u; }
+  if (tid == 0) { mbar_init(&s.bars[12], 1); mbar_init(&s.bars[13], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); s.pre[33] = 0u; s.pre[34] = 0u; }
+  if (tid < 32) nrm[tid] = 0u;
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
   const int nKT = (LkC + TCQ - 1) / TCQ;
   // Key tiles go to the two warpgroups in pairs; an odd last tile is SHARED: each warpgroup takes half of its query tiles
@@ -1163,6 +653,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
   {
     float delta[RPT];
     float gm = 0.f;
+    uint32_t qmb = 0u;
     const float init = LkC > 0 ? 0.f : __int_as_float(0x7fc00000);
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
@@ -1171,24 +662,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) { d = fmaf(g[u][c], o[u][c], d); o[u][c] = init; gm = fmaxf(gm, fabsf(g[u][c])); }
       delta[u] = d;
+      qmb = absmax8_bits(q[u], qmb);
       if (i < a.Lq) st8g(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, o[u]);
     }
     gm = isfinite(gm) ? gm : 0.f;
-    atomicMax(&s.pre[33], __float_as_uint(gm));       // pre[33] was cleared before the barriers of compact_keys
+    const uint32_t gmb = __reduce_max_sync(0xffffffffu, __float_as_uint(gm));
+    qmb = __reduce_max_sync(0xffffffffu, qmb);
+    if (lane == 0) { atomicMax(&s.pre[33], gmb); atomicMax(&s.pre[34], qmb); }       // cleared before the barriers of compact_keys
     __syncthreads();
     const float sc = pow2_normaliser(__uint_as_float(s.pre[33]));
+    const float qs = kQScale * pow2_normaliser_c(__uint_as_float(s.pre[34]));
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
       const int i = tid + u * NTHREADS;
       if (i >= NQ * BK) continue;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) { q[u][c] *= kQScale; g[u][c] *= sc; }
+      for (int c = 0; c < 8; ++c) { q[u][c] *= qs; g[u][c] *= sc; }
       put_l2h(Q2h, i, q[u]); put_l2h(G2h, i, g[u]);
       s.f0[i] = -lse2[u]; s.f1[i] = -delta[u] * sc;
       s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
     }
   }
   const float cs_scale = pow2_normaliser(__uint_as_float(s.pre[33]));
+  const float q_norm = pow2_normaliser_c(__uint_as_float(s.pre[34]));       // Q2h holds q * sqrt(1/8) * log2(e) * q_norm
   fence_async_smem();
   fence_before();
   __syncthreads();
@@ -1263,7 +759,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
     unsigned char* const ds_row = dsb + wg * DS_BYTES + (r & 7) * 16 + (r >> 3) * 128;      // this key's 16-byte slot in each query group
     unsigned char* const kb_row = kbb + wg * KB_BYTES + (r & 7) * 16 + (r >> 3) * 128;
-    const float dq_scale = kScale / cs_scale;
+    float dq_scale = kScale / cs_scale;          // times 1 / (this key tile's K normaliser), set per tile
     WgPhase ph = {0, 0};
     uint32_t cdq = 0;
     int it = 0;
@@ -1296,6 +792,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
         ld8g(k, a.k + ((long long)n * a.Lk + jk) * a.ldk + h * 8);
         ld8g(v, a.v + ((long long)n * a.Lk + jk) * a.ldv + h * 8);
       }
+      // K and V rows are fp16 operands ([hi | lo] in TMEM, hi in the dQ product): normalised per key tile by exact powers of
+      // two, which the exponent (an fma instead of an add), the dropout multiplier and the output scales undo for free
+      float k_norm, v_norm;
+      {
+        const uint32_t kmb = __reduce_max_sync(0xffffffffu, absmax8_bits(k, 0u)), vmb = __reduce_max_sync(0xffffffffu, absmax8_bits(v, 0u));
+        uint32_t* slot = nrm + (wg * 8 + it) * 2;
+        if (lane == 0) { atomicMax(slot, kmb); atomicMax(slot + 1, vmb); }
+        asm volatile("bar.sync %0, 128;" :: "r"(wg + 1) : "memory");
+        k_norm = pow2_normaliser_c(__uint_as_float(slot[0])); v_norm = pow2_normaliser_c(__uint_as_float(slot[1]));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { k[c] *= k_norm; v[c] *= v_norm; }
+      }
+      const float inv_qk = 1.f / (q_norm * k_norm), inv_v = 1.f / v_norm;
+      const f32x2 iqk2 = pk2(inv_qk, inv_qk), iv2 = pk2(inv_v, inv_v);
+      const float drop_mul = dc.scale * inv_v;
+      dq_scale = kScale / (cs_scale * k_norm);
       *reinterpret_cast<uint4*>(kb_row) = make_uint4(pack_h2(k[0], k[1]), pack_h2(k[2], k[3]), pack_h2(k[4], k[5]), pack_h2(k[6], k[7]));
       {                // A operands: columns 0-3 = hi pairs, 4-7 = lo pairs (K index 0-7 hi, 8-15 lo); second operand: [hi | 0]
         uint32_t xa[8], xb[8];
@@ -1339,19 +851,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
             float pp[4], ss[4];
             const int c = cc * 4;
             float x0, x1, x2, x3;
-            upk2(add2(pk2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), pk2(lv.x, lv.y)), x0, x1);
-            upk2(add2(pk2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])), pk2(lv.z, lv.w)), x2, x3);
+            upk2(fma2(pk2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), iqk2, pk2(lv.x, lv.y)), x0, x1);
+            upk2(fma2(pk2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])), iqk2, pk2(lv.z, lv.w)), x2, x3);
             const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);
             const f32x2 pa = pk2(p0, p1), pb = pk2(p2, p3);
             const f32x2 ta = pk2(__uint_as_float(tr[c]), __uint_as_float(tr[c + 1])), tb2 = pk2(__uint_as_float(tr[c + 2]), __uint_as_float(tr[c + 3]));
             if (!dc.on) {
               pp[0] = p0; pp[1] = p1; pp[2] = p2; pp[3] = p3;
-              upk2(mul2(pa, add2(ta, pk2(dv.x, dv.y))), ss[0], ss[1]);
-              upk2(mul2(pb, add2(tb2, pk2(dv.z, dv.w))), ss[2], ss[3]);
+              upk2(mul2(pa, fma2(ta, iv2, pk2(dv.x, dv.y))), ss[0], ss[1]);
+              upk2(mul2(pb, fma2(tb2, iv2, pk2(dv.z, dv.w))), ss[2], ss[3]);
             } else {
               const uint4 wv = w4[cc];
-              const float m0 = (wv.x * cw >= dc.thr) ? dc.scale : 0.f, m1 = (wv.y * cw >= dc.thr) ? dc.scale : 0.f;
-              const float m2 = (wv.z * cw >= dc.thr) ? dc.scale : 0.f, m3 = (wv.w * cw >= dc.thr) ? dc.scale : 0.f;
+              const float m0 = (wv.x * cw >= dc.thr) ? drop_mul : 0.f, m1 = (wv.y * cw >= dc.thr) ? drop_mul : 0.f;
+              const float m2 = (wv.z * cw >= dc.thr) ? drop_mul : 0.f, m3 = (wv.w * cw >= dc.thr) ? drop_mul : 0.f;
               const f32x2 ma = pk2(m0, m1), mb = pk2(m2, m3);
               upk2(mul2(pa, ma), pp[0], pp[1]);
               upk2(mul2(pb, mb), pp[2], pp[3]);
@@ -1392,10 +904,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
       if (valid) {
         float dk[8], dv[8];
         const float inv = 1.f / cs_scale;
+        const float ck = kLn2 * inv / q_norm;                  // hi + lo parts; Q carried log2(e) and its normaliser
+        const float cv = dc.on ? inv * v_norm : inv;           // with dropout the P^T operand carries 1 / v_norm (drop_mul)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          dk[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * (kLn2 * inv);      // hi + lo parts; Q carried log2(e)
-          dv[c] = __uint_as_float(o[16 + c]) * inv;
+          dk[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * ck;
+          dv[c] = __uint_as_float(o[16 + c]) * cv;
         }
         float* pk_ = a.dk + ((long long)n * a.Lk + jk) * a.lddk + h * 8;
         float* pv_ = a.dv + ((long long)n * a.Lk + jk) * a.lddv + h * 8;
@@ -1431,36 +945,31 @@ static int tc_configure(K k, size_t bytes, const char* what) {
   return V_OK;
 }
 
+// The per-device opt-in to the large dynamic shared-memory window is applied once per device ordinal (a process may drive
+// several GPUs from one thread).
+template <typename K>
+static int tc_configure_dev(K k, size_t bytes, const char* what) {
+  static int done[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (done[dev]) return V_OK;
+  const int rc = tc_configure(k, bytes, what);
+  if (rc == V_OK) done[dev] = 1;
+  return rc;
+}
+
 int attn_tc_fwd(const AttnArgs& a, cudaStream_t st) {
-  static const bool two_wg = env_flag("VAESNE_TC_FWD2");      // the two-warpgroup forward (128-key tiles), kept for comparison
-  if (!two_wg) {
-    static int cfg4 = tc_configure(attn_tc_fwd4_kernel, FWD4_SMEM, "attn_tc_fwd4");
-    if (cfg4) return cfg4;
-    attn_tc_fwd4_kernel<<<dim3(kH, a.N), dim3(F4_THREADS), FWD4_SMEM, st>>>(a);
-    return check_launch("attn_tc_fwd4");
-  }
-  static int cfg = tc_configure(attn_tc_fwd_kernel, FWD_SMEM, "attn_tc_fwd");
+  const int cfg = tc_configure_dev(attn_tc_fwd4_kernel, FWD4_SMEM, "attn_tc_fwd4");
   if (cfg) return cfg;
-  attn_tc_fwd_kernel<<<dim3(kH, a.N), dim3(NTHREADS), FWD_SMEM, st>>>(a);
-  return check_launch("attn_tc_fwd");
+  attn_tc_fwd4_kernel<<<dim3(kH, a.N), dim3(F4_THREADS), FWD4_SMEM, st>>>(a);
+  return check_launch("attn_tc_fwd4");
 }
 
 int attn_tc_bwd(const AttnArgs& a, cudaStream_t st) {
-  static const bool split = env_flag("VAESNE_TC_BWD_SPLIT");      // the two-pass backward (dq kernel + key-major kernel), kept for comparison
-  if (!split) {
-    static int cfg = tc_configure(attn_tc_bwd_kernel, BWD_SMEM, "attn_tc_bwd");
-    if (cfg) return cfg;
-    attn_tc_bwd_kernel<<<dim3(kH, a.N), dim3(NTHREADS), BWD_SMEM, st>>>(a);
-    return check_launch("attn_tc_bwd");
-  }
-  static int cfg1 = tc_configure(attn_tc_dq_kernel, DQ_SMEM, "attn_tc_dq");
-  static int cfg2 = tc_configure(attn_tc_dkv_kernel, DKV_SMEM, "attn_tc_dkv");
-  if (cfg1) return cfg1;
-  if (cfg2) return cfg2;
-  attn_tc_dq_kernel<<<dim3(kH, a.N), dim3(NTHREADS), DQ_SMEM, st>>>(a);
-  int rc = check_launch("attn_tc_dq"); if (rc) return rc;
-  attn_tc_dkv_kernel<<<dim3(kH, a.N), dim3(NTHREADS), DKV_SMEM, st>>>(a);
-  return check_launch("attn_tc_dkv");
+  const int cfg = tc_configure_dev(attn_tc_bwd_kernel, BWD_SMEM, "attn_tc_bwd");
+  if (cfg) return cfg;
+  attn_tc_bwd_kernel<<<dim3(kH, a.N), dim3(NTHREADS), BWD_SMEM, st>>>(a);
+  return check_launch("attn_tc_bwd");
 }
 
 }  // namespace vaesne

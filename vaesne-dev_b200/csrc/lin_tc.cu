@@ -632,11 +632,14 @@ bool lin_tc_bwd_eligible(const LinBwd& a) {
 
 // Persistent grid: exactly as many CTAs as can be co-resident (a partial second wave would double the run time),
 // never more than there are tiles.  The occupancy of each kernel instantiation is queried once.
-struct TcKernelInfo { const void* fn; int ctas_per_sm; int sms; };
+struct TcKernelInfo { const void* fn; int ctas_per_sm; int sms; int dev; };
 template <typename K>
 static int tc_prepare(K k, size_t smem, const char* what, TcKernelInfo& out, int threads = LT) {
-  static thread_local TcKernelInfo cache[16] = {};
-  for (auto& e : cache) if (e.fn == (const void*)k) { out = e; return V_OK; }
+  // keyed by (kernel, device ordinal): cudaFuncSetAttribute opt-ins are per device, and one thread may drive several GPUs
+  static thread_local TcKernelInfo cache[64] = {};
+  int cur = 0;
+  if (cudaGetDevice(&cur) != cudaSuccess) cur = 0;
+  for (auto& e : cache) if (e.fn == (const void*)k && e.dev == cur) { out = e; return V_OK; }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("%s: cannot reserve %zu B of shared memory: %s", what, smem, cudaGetErrorString(e)); return V_ECUDA; }
   // ask for the full shared-memory carve-out, otherwise the occupancy (and residency) is computed for a small default
@@ -644,11 +647,11 @@ static int tc_prepare(K k, size_t smem, const char* what, TcKernelInfo& out, int
   // Residency from the kernel's own resources.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for
   // kernels that allocate tensor memory, whatever they allocate; the block scheduler itself only looks at
   // registers / shared memory / threads, and tcgen05.alloc waits for free columns.)
-  int dev = 0, sms = 148, smem_sm = 233472, regs_sm = 65536;
+  int dev = cur, sms = 148, smem_sm = 233472, regs_sm = 65536;
   cudaFuncAttributes fa;
   e = cudaFuncGetAttributes(&fa, k);
   if (e != cudaSuccess) { set_error("%s: cudaFuncGetAttributes failed: %s", what, cudaGetErrorString(e)); return V_ECUDA; }
-  if (cudaGetDevice(&dev) == cudaSuccess) {
+  {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
     cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
@@ -658,7 +661,7 @@ static int tc_prepare(K k, size_t smem, const char* what, TcKernelInfo& out, int
   const int by_smem = (int)((size_t)smem_sm / (smem + fa.sharedSizeBytes + 1024));
   int occ = by_regs < by_smem ? by_regs : by_smem;
   if (occ < 1) occ = 1;
-  out = TcKernelInfo{(const void*)k, occ, sms};
+  out = TcKernelInfo{(const void*)k, occ, sms, cur};
   if (getenv("VAESNE_DEBUG")) fprintf(stderr, "[vaesne] %s: %d CTAs/SM by occupancy, %d SMs, %zu B smem\n", what, occ, sms, smem);
   for (auto& c : cache) if (!c.fn) { c = out; break; }
   return V_OK;

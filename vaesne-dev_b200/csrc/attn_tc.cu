@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a)
 // with vector reductions into the zero-initialised output — no second pass, no extra exponentials.
 // TMEM is full (IN 128 | OUT 64 | ACC 32 | X 32 per warpgroup), so the dV product takes dO as fp16 hi only and dQ takes K as
 // fp16 hi only (their accumulators are 8 columns instead of 16).  every fp16 operand is range-managed by exact powers of two:
-// dO and q per (row, head), k and v per key tile (undone by the exponent's fma, the dropout multiplier and the output scales).
+// dO, q and v per (row, head), k per key tile (undone by the exponent's fma and the output scales).
 // =================================================================================================
 constexpr int C_DQ = 216;                    // per warpgroup: ACC = dK hi|lo (192..207) | dV (208..215) | dQ tile (216..223)
 constexpr int DS_BYTES = 128 * 128 * 2, KB_BYTES = 8 * 128 * 2;      // dS^T of a tile pair (128 queries x 128 keys fp16), K rows
@@ -606,7 +606,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     s.bars = (uint64_t*)(s.pre + 36);
     s.tmem = (uint32_t*)(s.bars + 16);
   }
-  uint32_t* const nrm = s.tmem + 4;        // [2 warpgroups][8 key-tile iterations][k, v]: largest magnitudes of a key tile
+  uint32_t* const nrm = s.tmem + 4;        // [2 warpgroups][8 key-tile iterations]: largest |k| of a key tile
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
@@ -616,6 +616,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
 
   // query side: every thread owns up to RPT queries; their loads are issued first so that the round trip overlaps the key
   // compaction below (the prologue is a chain of global-memory latencies and nothing else runs on the SM meanwhile)
+  // (first the largest |v| of the (row, head): V enters dP = dO V^T, whose scale the per-query delta must share, so its
+  // normaliser has to be known before the query-side tables are written; K's normaliser is per key tile, see below)
+  uint32_t vmb = 0u;
+#pragma unroll
+  for (int u = 0; u < RPT; ++u) {
+    const int j = tid + u * NTHREADS;
+    if (j < a.Lk) {
+      float vv[8];
+      ld8g(vv, a.v + ((long long)n * a.Lk + j) * a.ldv + h * 8);
+      vmb = absmax8_bits(vv, vmb);
+    }
+  }
   float q[RPT][8], g[RPT][8], o[RPT][8], lse2[RPT];
 #pragma unroll
   for (int u = 0; u < RPT; ++u) {
@@ -631,7 +643,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     }
   }
   init_pipeline(s, tid, warp);
-  if (tid == 0) { mbar_init(&s.bars[12], 1); mbar_init(&s.bars[13], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); s.pre[33] = 0u; s.pre[34] = 0u; }
+  if (tid == 0) { mbar_init(&s.bars[12], 1); mbar_init(&s.bars[13], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); s.pre[33] = 0u; s.pre[34] = 0u; s.pre[35] = 0u; }
   if (tid < 32) nrm[tid] = 0u;
   const int LkC = compact_keys(a, s, n, tid, warp, lane);
   const int nKT = (LkC + TCQ - 1) / TCQ;
@@ -668,9 +680,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     gm = isfinite(gm) ? gm : 0.f;
     const uint32_t gmb = __reduce_max_sync(0xffffffffu, __float_as_uint(gm));
     qmb = __reduce_max_sync(0xffffffffu, qmb);
-    if (lane == 0) { atomicMax(&s.pre[33], gmb); atomicMax(&s.pre[34], qmb); }       // cleared before the barriers of compact_keys
+    vmb = __reduce_max_sync(0xffffffffu, vmb);
+    if (lane == 0) { atomicMax(&s.pre[33], gmb); atomicMax(&s.pre[34], qmb); atomicMax(&s.pre[35], vmb); }       // cleared before the barriers of compact_keys
     __syncthreads();
     const float sc = pow2_normaliser(__uint_as_float(s.pre[33]));
+    const float dsc = sc * pow2_normaliser_c(__uint_as_float(s.pre[35]));       // delta shares the scale of dP = (dO sc) (V v_norm)^T
     const float qs = kQScale * pow2_normaliser_c(__uint_as_float(s.pre[34]));
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
@@ -679,12 +693,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
 #pragma unroll
       for (int c = 0; c < 8; ++c) { q[u][c] *= qs; g[u][c] *= sc; }
       put_l2h(Q2h, i, q[u]); put_l2h(G2h, i, g[u]);
-      s.f0[i] = -lse2[u]; s.f1[i] = -delta[u] * sc;
+      s.f0[i] = -lse2[u]; s.f1[i] = -delta[u] * dsc;
       s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
     }
   }
   const float cs_scale = pow2_normaliser(__uint_as_float(s.pre[33]));
   const float q_norm = pow2_normaliser_c(__uint_as_float(s.pre[34]));       // Q2h holds q * sqrt(1/8) * log2(e) * q_norm
+  const float v_norm = pow2_normaliser_c(__uint_as_float(s.pre[35]));       // V rows enter TMEM as v * v_norm: dS carries cs_scale * v_norm
   fence_async_smem();
   fence_before();
   __syncthreads();
@@ -759,7 +774,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
     unsigned char* const ds_row = dsb + wg * DS_BYTES + (r & 7) * 16 + (r >> 3) * 128;      // this key's 16-byte slot in each query group
     unsigned char* const kb_row = kbb + wg * KB_BYTES + (r & 7) * 16 + (r >> 3) * 128;
-    float dq_scale = kScale / cs_scale;          // times 1 / (this key tile's K normaliser), set per tile
+    const float ds_inv = 1.f / (cs_scale * v_norm);     // undoes the scale dS^T (and what is contracted with it) carries
+    float dq_scale = kScale * ds_inv;            // times 1 / (this key tile's K normaliser), set per tile
     WgPhase ph = {0, 0};
     uint32_t cdq = 0;
     int it = 0;
@@ -792,22 +808,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
         ld8g(k, a.k + ((long long)n * a.Lk + jk) * a.ldk + h * 8);
         ld8g(v, a.v + ((long long)n * a.Lk + jk) * a.ldv + h * 8);
       }
-      // K and V rows are fp16 operands ([hi | lo] in TMEM, hi in the dQ product): normalised per key tile by exact powers of
-      // two, which the exponent (an fma instead of an add), the dropout multiplier and the output scales undo for free
-      float k_norm, v_norm;
+      // K and V rows are fp16 operands ([hi | lo] in TMEM, hi in the dQ product), range-managed by exact powers of two: V per
+      // (row, head) (above), K per key tile — the exponent (an fma instead of an add) and the dQ drain undo it for free
+      float k_norm;
       {
-        const uint32_t kmb = __reduce_max_sync(0xffffffffu, absmax8_bits(k, 0u)), vmb = __reduce_max_sync(0xffffffffu, absmax8_bits(v, 0u));
-        uint32_t* slot = nrm + (wg * 8 + it) * 2;
-        if (lane == 0) { atomicMax(slot, kmb); atomicMax(slot + 1, vmb); }
+        const uint32_t kmb = __reduce_max_sync(0xffffffffu, absmax8_bits(k, 0u));
+        uint32_t* slot = nrm + wg * 8 + it;
+        if (lane == 0) atomicMax(slot, kmb);
         asm volatile("bar.sync %0, 128;" :: "r"(wg + 1) : "memory");
-        k_norm = pow2_normaliser_c(__uint_as_float(slot[0])); v_norm = pow2_normaliser_c(__uint_as_float(slot[1]));
+        k_norm = pow2_normaliser_c(__uint_as_float(slot[0]));
 #pragma unroll
         for (int c = 0; c < 8; ++c) { k[c] *= k_norm; v[c] *= v_norm; }
       }
-      const float inv_qk = 1.f / (q_norm * k_norm), inv_v = 1.f / v_norm;
-      const f32x2 iqk2 = pk2(inv_qk, inv_qk), iv2 = pk2(inv_v, inv_v);
-      const float drop_mul = dc.scale * inv_v;
-      dq_scale = kScale / (cs_scale * k_norm);
+      const float inv_qk = 1.f / (q_norm * k_norm);
+      const f32x2 iqk2 = pk2(inv_qk, inv_qk);
+      dq_scale = kScale * ds_inv / k_norm;
       *reinterpret_cast<uint4*>(kb_row) = make_uint4(pack_h2(k[0], k[1]), pack_h2(k[2], k[3]), pack_h2(k[4], k[5]), pack_h2(k[6], k[7]));
       {                // A operands: columns 0-3 = hi pairs, 4-7 = lo pairs (K index 0-7 hi, 8-15 lo); second operand: [hi | 0]
         uint32_t xa[8], xb[8];
@@ -858,12 +873,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
             const f32x2 ta = pk2(__uint_as_float(tr[c]), __uint_as_float(tr[c + 1])), tb2 = pk2(__uint_as_float(tr[c + 2]), __uint_as_float(tr[c + 3]));
             if (!dc.on) {
               pp[0] = p0; pp[1] = p1; pp[2] = p2; pp[3] = p3;
-              upk2(mul2(pa, fma2(ta, iv2, pk2(dv.x, dv.y))), ss[0], ss[1]);
-              upk2(mul2(pb, fma2(tb2, iv2, pk2(dv.z, dv.w))), ss[2], ss[3]);
+              upk2(mul2(pa, add2(ta, pk2(dv.x, dv.y))), ss[0], ss[1]);
+              upk2(mul2(pb, add2(tb2, pk2(dv.z, dv.w))), ss[2], ss[3]);
             } else {
               const uint4 wv = w4[cc];
-              const float m0 = (wv.x * cw >= dc.thr) ? drop_mul : 0.f, m1 = (wv.y * cw >= dc.thr) ? drop_mul : 0.f;
-              const float m2 = (wv.z * cw >= dc.thr) ? drop_mul : 0.f, m3 = (wv.w * cw >= dc.thr) ? drop_mul : 0.f;
+              const float m0 = (wv.x * cw >= dc.thr) ? dc.scale : 0.f, m1 = (wv.y * cw >= dc.thr) ? dc.scale : 0.f;
+              const float m2 = (wv.z * cw >= dc.thr) ? dc.scale : 0.f, m3 = (wv.w * cw >= dc.thr) ? dc.scale : 0.f;
               const f32x2 ma = pk2(m0, m1), mb = pk2(m2, m3);
               upk2(mul2(pa, ma), pp[0], pp[1]);
               upk2(mul2(pb, mb), pp[2], pp[3]);
@@ -903,9 +918,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
       tmem_ld16(tA, o); tmem_ld8(tA + 16, o + 16); tmem_wait_ld();
       if (valid) {
         float dk[8], dv[8];
-        const float inv = 1.f / cs_scale;
-        const float ck = kLn2 * inv / q_norm;                  // hi + lo parts; Q carried log2(e) and its normaliser
-        const float cv = dc.on ? inv * v_norm : inv;           // with dropout the P^T operand carries 1 / v_norm (drop_mul)
+        const float ck = kLn2 * ds_inv / q_norm;               // hi + lo parts; Q carried log2(e) and its normaliser
+        const float cv = 1.f / cs_scale;                       // dV = P^T (dO cs_scale)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           dk[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * ck;
@@ -945,16 +959,16 @@ static int tc_configure(K k, size_t bytes, const char* what) {
   return V_OK;
 }
 
-// The per-device opt-in to the large dynamic shared-memory window is applied once per device ordinal (a process may drive
-// several GPUs from one thread).
-template <typename K>
-static int tc_configure_dev(K k, size_t bytes, const char* what) {
-  static int done[64] = {0};
+// The per-device opt-in to the large dynamic shared-memory window is applied once per (kernel, device ordinal): a process may
+// drive several GPUs from one thread.  (Keyed by the function pointer: both kernels have the same C++ type.)
+static int tc_configure_dev(void (*k)(AttnArgs), size_t bytes, const char* what) {
+  struct Entry { const void* fn; int dev; };
+  static thread_local Entry done[32] = {};
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-  if (done[dev]) return V_OK;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  for (const Entry& e : done) if (e.fn == (const void*)k && e.dev == dev) return V_OK;
   const int rc = tc_configure(k, bytes, what);
-  if (rc == V_OK) done[dev] = 1;
+  if (rc == V_OK) for (Entry& e : done) if (!e.fn) { e.fn = (const void*)k; e.dev = dev; break; }
   return rc;
 }
 

@@ -2,7 +2,7 @@
 """bench.py — train samples/s of the VAESNe mmVAE step (fwd + bwd + IW-ELBO + AdamW) on B200.
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
-    python bench.py --impl reference --steps K --warmup W    (the reference algorithm on the host CPU cores)
+    python bench.py --impl reference --steps K --warmup W    (the UNMODIFIED reference on the host CPU cores)
 
 Workload (BASELINE.json configs[3], the one the metric is quoted on): the ZTF photometry+spectra
 mixture-of-experts VAE of cannon/ZTF_photospect.py:76-119 — 2 bands, latent 4x4, model_dim 32, 4 heads,
@@ -13,10 +13,18 @@ bins), weak scaling with a fixed per-GPU batch.
 One JSON line on stdout (rank 0).  `value` = samples/s with the batches resident in HBM; `e2e` = the same
 step through the public API (VAESNe.training_util.training_step) from pinned host batches with the loss
 read back every step.  `roofline` is for the dominant kernel (timed with CUDA events on the launching
-stream in an extra instrumented pass), `cpu_baseline` is the oracle port timed on the host cores."""
+stream in an extra instrumented pass).  Next to it, at N=1: `cpu_baseline` (the unmodified reference on the
+host cores), `eager_gpu_baseline` (the same unmodified reference as stock eager PyTorch on this GPU),
+`configs` (samples/s of BASELINE.json's other configurations), `batch_sweep` (per-GPU batch 16..512) and the
+encode / reconstruct rates; at N>1: `dp_check` (all-reduced buckets == sum over ranks of the local gradients).
+
+The reference arm runs baseline/_ref (pip-installed by baseline/install_ref.py from /root/reference, git-ignored,
+shipped to the GPU box) in a child interpreter through baseline/ref_arm.py; only if that copy is missing does it
+fall back to the oracle port (`cpu_baseline.kind` says which).  The product arm never imports oracle/."""
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import math
 import os
@@ -32,6 +40,8 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 import torch  # noqa: E402
+
+import bench_common as BC  # noqa: E402
 
 LP, LS = 60, 982
 KS = 8               # importance samples (ZTF_photospect.py:117)
@@ -62,21 +72,29 @@ def step_flops_per_sample(K):
 
 
 # ------------------------------------------------------------------------------------------------
-def synth_batch(B, seed, num_bands=2):
-    from oracle import vaesne_oracle as O
-    return [O.synth_photometry(B, LP, num_bands, seed=seed), O.synth_spectra(B, LS, seed=seed)]
+synth_batch = BC.synth_batch
 
 
 def build_model(device, dropout=0.1):
-    from VAESNe.PhotometricVAE import PhotometricVAE
-    from VAESNe.SpectraVAE import SpectraVAE
-    from VAESNe.mmVAE import photospecMMVAE
     torch.manual_seed(1)
-    pv = PhotometricVAE(num_bands=2, latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=4,
-                        dropout=dropout, selfattn=False, beta=0.5)
-    sv = SpectraVAE(latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=4,
-                    dropout=dropout, selfattn=True, beta=0.5)
-    return photospecMMVAE([pv, sv], beta=0.5).to(device)
+    model, _, _, _ = BC.build_config("mmvae_ztf", BC.Namespace(), dropout)
+    return model.to(device)
+
+
+def run_ref_arm(**kw):
+    """baseline/ref_arm.py in a child interpreter (the reference package shares the product package's name) -> dict or None."""
+    cmd = [sys.executable, os.path.join(ROOT, "baseline", "ref_arm.py")]
+    for k, v in kw.items():
+        cmd += ["--" + k.replace("_", "-"), str(v)]
+    env = {k: v for k, v in os.environ.items() if k not in ("PYTHONPATH", "RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"unavailable": (r.stderr or r.stdout)[-300:].replace("\n", " | ")}
+        return json.loads(line[-1])
+    except Exception as e:      # noqa: BLE001
+        return {"unavailable": repr(e)}
 
 
 class ClockSampler:
@@ -164,18 +182,24 @@ def run_reference_arm(args):
     if rank != 0:            # under torchrun only rank 0 runs the CPU arm; the other ranks exit without work
         return
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    t1 = time_cpu(1, 1, 1)                                   # calibrate: seconds per sample-step
-    budget = 150.0
-    B = int(max(1, min(16, budget / ((args.steps + args.warmup) * t1))))
-    t = time_cpu(B, args.steps, args.warmup)
-    v = B / t
+    ref = run_ref_arm(config="mmvae_ztf", device="cpu", batch=16, steps=args.steps, warmup=args.warmup, budget_s=150)
+    if ref and "samples_per_s" in ref:
+        B, t, v, kind = ref["batch"], ref["s_per_step"], ref["samples_per_s"], "reference"
+        sample = (f"{args.steps} steps of B={B} after {args.warmup} warm-up (unmodified reference package {ref['package']} through its own "
+                  f"training_step + torch.optim.AdamW, torch {ref['torch']} CPU fp32, {ref['threads']} threads, dropout 0.1)")
+    else:                    # baseline/_ref missing on this box: the oracle port of the same algorithm
+        torch.set_num_threads(cores)
+        t1 = time_cpu(1, 1, 1)
+        B = int(max(1, min(16, 150.0 / ((args.steps + args.warmup) * t1))))
+        t = time_cpu(B, args.steps, args.warmup)
+        v, kind = B / t, "port"
+        sample = f"{args.steps} steps of B={B} (oracle port of the reference, torch CPU fp32, dropout 0.1, AdamW); reference copy unavailable: {ref}"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(B), "per_step_batch": B, "K": KS},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps of B={B} (oracle port of the reference, torch CPU fp32, dropout 0.1, AdamW)"},
+            "config": {"workload": workload_name(B), "per_step_batch": B, "K": KS,
+                       "note": "same model / objective / optimiser as the product arm; the step is a bounded sample (smaller batch) of that workload"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -183,6 +207,103 @@ def run_reference_arm(args):
 def workload_name(B):
     return (f"ZTF_photospect mmVAE train step (2 bands, K={KS}, beta=0.5, spectra-encoder selfattn, dropout 0.1, AdamW lr 1e-3), "
             f"Lp={LP}, Ls={LS}, per-GPU batch {B}")
+
+
+# ------------------------------------------------------------------------------------------------
+def _time_train(model, opt, loss_fn, batches, multimodal, steps, warmup, graph=False):
+    """samples/s of training_step over device-resident batches (CUDA events on the launching stream)."""
+    from VAESNe.training_util import training_step
+    nb = len(batches)
+    B = (batches[0][0][0] if multimodal else batches[0][0]).shape[0]
+    training_step(model, opt, [batches[i % nb] for i in range(warmup)], loss_fn, multimodal=multimodal, cuda_graph=graph)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(); a.record()
+    training_step(model, opt, [batches[i % nb] for i in range(steps)], loss_fn, multimodal=multimodal, cuda_graph=graph)
+    b.record(); torch.cuda.synchronize()
+    return B * steps / (a.elapsed_time(b) * 1e-3)
+
+
+def _to_dev(x, dev, multimodal):
+    return [tuple(t.to(dev) for t in m) for m in x] if multimodal else tuple(t.to(dev) for t in x)
+
+
+def run_configs(dev):
+    """BASELINE.json configs 1, 2, 3, 5 through the product's public API: per-script batch (eager and as a replayed
+    CUDA graph — those batches are launch-bound) and a machine-filling batch."""
+    from VAESNe.optim import FusedAdamW
+    ns = BC.Namespace()
+    out = {}
+    big = {"photometry_elbo": 16384, "spectra_elbo": 1024, "mmvae_goldstein": 512, "contrastive": 2048, "photo_end2end": 16384}
+    for name in ("photometry_elbo", "spectra_elbo", "mmvae_goldstein", "contrastive", "photo_end2end"):
+        c = BC.CONFIGS[name]
+        torch.manual_seed(1)
+        model, loss_fn, make, mm = BC.build_config(name, ns, 0.1)
+        model = model.to(dev)
+        opt = FusedAdamW(model.parameters(), lr=c["lr"], grad_average=False)
+        rec = {"script": c["script"], "K": c["K"]}
+        for tag, B, steps, graph in (("script_batch", c["batch"], 20, False), ("script_batch_cuda_graph", c["batch"], 20, True),
+                                     ("large_batch", big[name], 5, False)):
+            batches = [_to_dev(make(B, 300 + i), dev, mm) for i in range(2)]
+            try:
+                rec[tag] = {"batch": B, "samples_per_s": _time_train(model, opt, loss_fn, batches, mm, steps, 4 if graph else 3, graph)}
+            except Exception as e:      # noqa: BLE001
+                rec[tag] = {"batch": B, "error": repr(e)[:200]}
+            del batches
+        out[name] = rec
+        del model, opt
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_batch_sweep(dev, headline):
+    """mmVAE ZTF step at per-GPU batch 16 / 64 / 256 (+ the headline batch): where the step stops being launch-bound."""
+    from VAESNe.losses import m_iwae
+    from VAESNe.optim import FusedAdamW
+    model = build_model(dev)
+    opt = FusedAdamW(model.parameters(), lr=1e-3)
+    loss_fn = lambda m, x: m_iwae(m, x, K=KS)      # noqa: E731
+    out = []
+    for B in (16, 64, 256):
+        batches = [_to_dev(synth_batch(B, 500 + i), dev, True) for i in range(2)]
+        rec = {"per_gpu_batch": B, "samples_per_s": _time_train(model, opt, loss_fn, batches, True, 8 if B < 256 else 5, 3)}
+        if B <= 64:
+            rec["samples_per_s_cuda_graph"] = _time_train(model, opt, loss_fn, batches, True, 8, 4, graph=True)
+        out.append(rec)
+        del batches
+    out.append({"per_gpu_batch": headline[0], "samples_per_s": headline[1]})
+    del model, opt
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_dp_check(model, loss_fn, x, dev, world):
+    """One backward with the data-parallel plumbing off (local gradients) and one with it on (per-stack buckets all-reduced
+    asynchronously over NCCL), same noise and dropout seeds; the reduced gradients must equal the sum over ranks of the local
+    ones (gathered and added in rank order in fp64).  Reported, not asserted: rel = max |a - b| / max |b| over all parameters."""
+    from VAESNe import _ops as P, parallel
+    import torch.distributed as dist
+
+    def grads(enabled):
+        parallel.enable(enabled)
+        P._SEED_CELLS.clear()                      # the dropout seed cell is re-drawn from torch's (re-seeded) generator
+        torch.manual_seed(4242 + dist.get_rank())
+        model.zero_grad(set_to_none=True)
+        (-loss_fn(model, x)).backward()
+        parallel.wait_all()
+        torch.cuda.synchronize()
+        return torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None]).clone()
+
+    local = grads(False)
+    reduced = grads(True)
+    parts = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(parts, local)
+    want = torch.stack([t.double() for t in parts]).sum(0)
+    err = (reduced.double() - want).abs().max().item()
+    ref = want.abs().max().item()
+    bitwise = bool(torch.equal(reduced, want.float()))
+    model.zero_grad(set_to_none=True)
+    return {"rel_err": err / max(ref, 1e-30), "max_abs_grad": ref, "n_params": int(local.numel()), "equals_fp64_sum_rounded": bitwise,
+            "what": "all-reduced per-stack buckets vs sum over ranks of the local gradients (same seeds), NCCL"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -195,6 +316,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs / batch_sweep / eager_gpu_baseline / encode")
     ap.add_argument("--cuda-graph", type=int, default=0, help="1: replay the captured step (training_step(cuda_graph=True))")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -284,11 +406,18 @@ def main():
         key, top = max(summ.items(), key=lambda kv: kv[1]["total_ms"])
         pk = peaks()
         name = key[0]
-        traffic_tab = {}
+        # measured DRAM traffic per batch row (ncu --set full of the SAME build: the table carries the library's hash and a
+        # mismatched table is refused, so the figure cannot go stale silently; profiles/make_traffic.py regenerates it)
+        traffic_tab, traffic_note = {}, None
         try:
-            traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
-        except Exception:
-            pass
+            tab = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
+            sha = hashlib.sha256(open(_native.LIB_PATH, "rb").read()).hexdigest()
+            if tab.get("lib_sha256") == sha:
+                traffic_tab = tab
+            else:
+                traffic_note = f"profiles/r2_traffic.json was measured on build {str(tab.get('lib_sha256'))[:12]}, this is {sha[:12]}: refused"
+        except Exception as e:      # noqa: BLE001
+            traffic_note = f"no traffic table: {e!r}"
         if name.startswith("attn"):
             Nb, Lq, Lk = key[1:]
             # algorithmic work per launch (the two attention matmuls, 2*8 FLOP each per score element;
@@ -305,6 +434,7 @@ def main():
                     "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                     "frac": ach / pk["tf_sust"],
                     "traffic": (lambda t: None if t is None else int(t * Nb))(traffic_tab.get("per_row", {}).get(f"{name}|{Lq}|{Lk}")),
+                    "traffic_note": traffic_note,
                     "peak_source": pk["src"] + " bf16 sustained (kernel timed inside the step)",
                     "share_of_step": top["total_ms"] / tot, "avg_ms": top["avg_ms"],
                     "binding_unit": {"name": "MUFU.EX2 (32 tensor FLOP per exponential at head_dim 8)", "floor_ms": ex2_floor_ms,
@@ -335,7 +465,7 @@ def main():
 
     # ---- encode latents/s (BASELINE.json's second metric; 1 GPU): VAE.encode on resident batches ------------
     enc = None
-    if world == 1:
+    if world == 1 and not args.no_extras:
         enc = {}
         # the encoders are launch-bound below a few thousand samples (photometry: ~60 kernels of ~20 us at batch 512), so the
         # headline figure uses batch 8192; batch 512 is reported next to it
@@ -369,19 +499,47 @@ def main():
         enc["reconstruct_batch"] = RB
         model.train()
 
+    # ---- N > 1: the all-reduced gradient buckets equal the sum over ranks of the local gradients (hardware NCCL path) -----
+    dp_check = None
+    if world > 1:
+        dp_check = run_dp_check(model, loss_fn, resident[0], dev, world)
+
+    # ---- BASELINE.json's other configurations and the per-GPU batch sweep (1 GPU) --------------------------------------
+    cfgs = sweep = None
+    if world == 1 and not args.no_extras:
+        del resident, pinned
+        torch.cuda.empty_cache()
+        cfgs = run_configs(dev)
+        sweep = run_batch_sweep(dev, headline=(B, value))
+
     if rank != 0:
         torch.distributed.destroy_process_group()
         return
 
-    # ---- CPU baseline (oracle port on the host cores), bounded sample -----------------------------
-    cpu = None
+    # ---- the unmodified reference: stock eager PyTorch on this GPU, and on the host cores (bounded samples) --------------
+    cpu = eager = None
+    if world == 1 and not args.no_extras:
+        del model, opt
+        torch.cuda.empty_cache()
+        r = run_ref_arm(config="mmvae_ztf", device="cuda", batch=16, steps=3, warmup=2)
+        eager = ({"value": r["samples_per_s"], "unit": UNIT, "batch": r["batch"], "ms_per_step": r["s_per_step"] * 1e3,
+                  "peak_mem_gib": r["peak_mem_gib"], "kind": "reference",
+                  "what": f"unmodified reference ({r['package']}) on cuda: its own training_step + torch.optim.AdamW, fp32 eager, dropout 0.1; "
+                          "batch 16 is the script's own (it materialises every 982x982 probability tensor: ~2.6 GB per sample)"}
+                 if r and "samples_per_s" in r else {"unavailable": r})
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        t1 = time_cpu(1, 1, 1)
-        Bc = int(max(1, min(8, 12.0 / t1)))
-        t = time_cpu(Bc, 1, 0)
-        cpu = {"value": Bc / t, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"1 step of B={Bc} after a B=1 warm-up (oracle port of the reference algorithm, torch CPU fp32, dropout 0.1, AdamW)"}
+        r = run_ref_arm(config="mmvae_ztf", device="cpu", batch=8, steps=2, warmup=1, budget_s=30)
+        if r and "samples_per_s" in r:
+            cpu = {"value": r["samples_per_s"], "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"{r['steps']} steps of B={r['batch']} after a warm-up step (unmodified reference {r['package']}, its own training_step + "
+                             f"torch.optim.AdamW, torch CPU fp32, {r['threads']} threads, dropout 0.1)"}
+        else:
+            t1 = time_cpu(1, 1, 1)
+            Bc = int(max(1, min(8, 12.0 / t1)))
+            t = time_cpu(Bc, 1, 0)
+            cpu = {"value": Bc / t, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"1 step of B={Bc} after a B=1 warm-up (oracle port; reference copy unavailable: {r})"}
 
     fl = step_flops_per_sample(KS)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -393,7 +551,8 @@ def main():
             "achieved_tflops_step": value * fl / 1e12,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,
                     "last_loss": last.get("loss")},
-            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "encode": enc}
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "eager_gpu_baseline": eager,
+            "configs": cfgs, "batch_sweep": sweep, "dp_check": dp_check, "encode": enc}
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

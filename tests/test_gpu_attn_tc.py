@@ -49,6 +49,27 @@ def test_tc_attention_operand_range(case, scales):
     OC.run_attn_case(case, "cuda", tol=TC_TOL, scale=scales)
 
 
+def test_tc_backward_rows_with_underflowed_upstream_gradient_stay_finite():
+    """A sample whose importance weight underflowed hands the decoder a gradient of ~1e-38 (seen in training at K=8): its
+    row must come out finite (the normalisers are clamped; an unclamped 2^126 times another normaliser overflowed to inf and
+    inf * 0 poisoned the whole parameter gradient), and the other rows keep their accuracy."""
+    from VAESNe import _ops as P
+    case = CASES[0]
+    (q, k, v, mask, mask_full, dO), (qd, kd, vd) = OC.make_attn_inputs(case, "cuda")
+    dO = dO.clone()
+    dO[1] *= 1e-38
+    dO[3] = 0.0
+    o_ref, lse_ref, dq_ref, dk_ref, dv_ref = OC.attn_reference(q, k, v, mask_full, dO)
+    md = mask.to("cuda")
+    O, LSE = P.attn_fwd(qd, kd, vd, md)
+    dq, dk, dv = _grads(case, "cuda")
+    P.attn_bwd(qd, kd, vd, md, O, LSE, dO.to("cuda"), dq, dk, dv)
+    for name, got, ref in (("dq", dq, dq_ref), ("dk", dk, dk_ref), ("dv", dv, dv_ref)):
+        assert torch.isfinite(got).all(), name
+        assert rel_err(got.cpu()[[0, 2]], ref[[0, 2]]) < TC_TOL, (name, rel_err(got.cpu()[[0, 2]], ref[[0, 2]]))
+        assert got[[1, 3]].abs().max().item() < 1e-30, name
+
+
 @pytest.mark.parametrize("case", CASES[:2] + CASES[-2:], ids=lambda c: c["id"])
 def test_tc_attention_dropout_mask_is_the_restated_one(case):
     from VAESNe import _ops as P

@@ -60,6 +60,13 @@ class GraphedStep:
         static = _to_device(x, device, self.multimodal)
         static = [tuple(t.clone() for t in m) for m in static] if self.multimodal else tuple(t.clone() for t in static)
         self.optimizer.zero_grad(set_to_none=True)
+        # nothing of an earlier (eager) iteration's autograd graph may survive into the capture: its AccumulateGrad nodes live
+        # on another stream and the engine would synchronise with it (illegal while capturing).  The models park the last
+        # posterior parameters — tensors with a grad_fn — on themselves (base_vae.py:24-30 `_qz_x_params`); drop those.
+        for mod in self.network.modules():
+            if getattr(mod, "_qz_x_params", None) is not None:
+                mod._qz_x_params = None
+        gc.collect()
         graph = torch.cuda.CUDAGraph()
         torch.cuda.synchronize(device)
         from . import _native

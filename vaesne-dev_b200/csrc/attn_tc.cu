@@ -147,13 +147,14 @@ __device__ __forceinline__ float pow2_normaliser(float amax) {
   const uint32_t e = (__float_as_uint(amax) >> 23) & 255u;
   return (e == 0u || e >= 254u) ? 1.f : __uint_as_float((254u - e) << 23);
 }
-// range management of the fp16 operands: an exact power of two (clamped to 2^+-40 so that products of two normalisers stay
-// finite) that brings the largest magnitude of a row set into [1, 2); non-finite maxima leave the data alone (the results are
-// then non-finite as in fp32 arithmetic)
+// range management of the fp16 operands: an exact power of two (clamped to 2^+-30 so that products and quotients of three
+// normalisers stay finite and normal) that brings the largest magnitude of a row set into [1, 2); non-finite maxima leave the
+// data alone (the results are then non-finite as in fp32 arithmetic).  Rows whose magnitudes lie below 2^-30 of ... 1 keep a
+// proportionally smaller operand — a gradient row of 1e-38 (an importance weight that underflowed) rounds to zero.
 __device__ __forceinline__ float pow2_normaliser_c(float amax) {
   uint32_t e = (__float_as_uint(amax) >> 23) & 255u;
   if (e == 0u || e >= 254u) return 1.f;
-  e = e < 87u ? 87u : (e > 167u ? 167u : e);
+  e = e < 97u ? 97u : (e > 157u ? 157u : e);
   return __uint_as_float((254u - e) << 23);
 }
 __device__ __forceinline__ uint32_t absmax8_bits(const float* x, uint32_t m) {
@@ -683,7 +684,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     vmb = __reduce_max_sync(0xffffffffu, vmb);
     if (lane == 0) { atomicMax(&s.pre[33], gmb); atomicMax(&s.pre[34], qmb); atomicMax(&s.pre[35], vmb); }       // cleared before the barriers of compact_keys
     __syncthreads();
-    const float sc = pow2_normaliser(__uint_as_float(s.pre[33]));
+    const float sc = pow2_normaliser_c(__uint_as_float(s.pre[33]));
     const float dsc = sc * pow2_normaliser_c(__uint_as_float(s.pre[35]));       // delta shares the scale of dP = (dO sc) (V v_norm)^T
     const float qs = kQScale * pow2_normaliser_c(__uint_as_float(s.pre[34]));
 #pragma unroll
@@ -697,7 +698,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
       s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
     }
   }
-  const float cs_scale = pow2_normaliser(__uint_as_float(s.pre[33]));
+  const float cs_scale = pow2_normaliser_c(__uint_as_float(s.pre[33]));
   const float q_norm = pow2_normaliser_c(__uint_as_float(s.pre[34]));       // Q2h holds q * sqrt(1/8) * log2(e) * q_norm
   const float v_norm = pow2_normaliser_c(__uint_as_float(s.pre[35]));       // V rows enter TMEM as v * v_norm: dS carries cs_scale * v_norm
   fence_async_smem();

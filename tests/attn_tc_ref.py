@@ -31,10 +31,24 @@ def hash_ctr(s0, s1, stream, ctr):
 
 
 def drop_threshold(p):
-    t = float(np.float32(p)) * 4294967296.0      # the C ABI carries p as a float
-    thr = 0xFFFFFFFF if t >= 4294967295.0 else int(t)
-    scale = np.float32(1.0 / (1.0 - thr / 4294967296.0))
+    """(threshold fp16 bit pattern, scale): the number of dropped 16-bit patterns is round(p * 65536), see make_tcdrop."""
+    n = int(float(np.float32(p)) * 65536.0 + 0.5)         # the C ABI carries p as a float
+    n = min(max(n, 1), 63490)
+    if n <= 31744:
+        thr = 0x7C01 - n
+    else:
+        n = max(n, 31746)
+        thr = 0x8000 | (n - 31746)
+    scale = np.float32(1.0 / (1.0 - n / 65536.0))
     return thr, float(scale)
+
+
+def dropped(r16, thr):
+    """r16 (uint16 array) read as fp16 compares >= the threshold pattern (NaN patterns: False)."""
+    r = np.asarray(r16, dtype=np.uint16).view(np.float16)
+    t = np.array([thr], dtype=np.uint16).view(np.float16)[0]
+    with np.errstate(invalid="ignore"):
+        return r >= t
 
 
 def keep_mask(seed, stream, p, N, H, Lq, key_mask_full, Lk):
@@ -48,10 +62,10 @@ def keep_mask(seed, stream, p, N, H, Lq, key_mask_full, Lk):
         slots = np.arange(len(kept), dtype=np.uint64)
         for h in range(H):
             nh = n * H + h
-            A = hash_ctr(s0, s1, stream, np.uint64(nh) * np.uint64(Lq) + np.arange(Lq, dtype=np.uint64)) | np.uint64(1)
-            B = hash_ctr(s1, s0, (stream ^ 0x5bd1e995) & 0xFFFFFFFF, (np.uint64(nh) << np.uint64(32)) | slots)
-            prod = _u32(A[:, None] * B[None, :])
-            out[n, h][:, kept] = prod >= np.uint64(thr)
+            A = hash_ctr(s0, s1, stream, np.uint64(nh) * np.uint64(Lq) + np.arange(Lq, dtype=np.uint64)) & np.uint64(0xFFFF)
+            B = hash_ctr(s1, s0, (stream ^ 0x5bd1e995) & 0xFFFFFFFF, (np.uint64(nh) << np.uint64(32)) | slots) & np.uint64(0xFFFF)
+            r = (A[:, None] ^ B[None, :]).astype(np.uint16)
+            out[n, h][:, kept] = ~dropped(r, thr)
     return out
 
 

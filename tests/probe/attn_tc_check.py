@@ -69,6 +69,6 @@ if os.environ.get('TC_PROF'):
     lib = ctypes.CDLL(os.path.join(ROOT, 'vaesne-dev_b200', 'lib', 'libvaesne_b200.so'))
     buf = (ctypes.c_longlong * 16)()
     torch.cuda.synchronize(); lib.vaesne_debug_tc_prof(buf)
-    names = ["warp0 wait s_ready", "warp0 ld+compute (incl. in_free signal)", "warp0 wait::st", "warp0 wait o_ready", "warp0 total (after staging)", "warp0 wait out_free", "staging prologue", "warp0 wait dq product", "warp0 drain dq"]
+    names = ["warp0 wait s_ready", "warp0 ld+compute (incl. in_free signal)", "warp0 wait::st", "warp0 wait o_ready", "warp0 total (after staging)", "warp0 wait out_free", "staging prologue", "warp0 wait dq product", "warp0 drain dq", "warp0 key-tile setup (to x_ready)", "warp0 key-tile tail (after o_ready)"]
     for n_, v in zip(names, buf):
         if n_: print(f"  bwd CTA(0,0) {n_:28s} {v:10d} clk")

@@ -35,15 +35,25 @@ def _keep_chunk(seed, stream, p, n0, n1, H, Lq, Lk, key_mask):
     n = torch.arange(n0, n1, device=dev, dtype=torch.int64)
     nh = n[:, None] * H + torch.arange(H, device=dev, dtype=torch.int64)[None, :]                      # [n, H]
     ctr = nh[:, :, None] * Lq + torch.arange(Lq, device=dev, dtype=torch.int64)[None, None, :]         # [n, H, Lq]
-    A = _hash_ctr(s0, s1, stream, ctr & M32, ctr >> 32) | 1
+    A = _hash_ctr(s0, s1, stream, ctr & M32, ctr >> 32) & 0xFFFF
     if key_mask is None:
         slot = torch.arange(Lk, device=dev, dtype=torch.int64)[None, :].expand(n1 - n0, Lk)
     else:
         km = key_mask[n % key_mask.shape[0]]
         slot = torch.cumsum((~km).to(torch.int64), 1) - 1                                                # compacted key slot
-    B = _hash_ctr(s1, s0, (stream ^ 0x5bd1e995) & M32, slot[:, None, :].expand(n1 - n0, H, Lk), nh[:, :, None].expand(n1 - n0, H, Lk))
-    prod = (A[:, :, :, None] * B[:, :, None, :]) & M32
-    return prod >= thr
+    B = _hash_ctr(s1, s0, (stream ^ 0x5bd1e995) & M32, slot[:, None, :].expand(n1 - n0, H, Lk), nh[:, :, None].expand(n1 - n0, H, Lk)) & 0xFFFF
+    r = A[:, :, :, None] ^ B[:, :, None, :]                  # 16-bit words, read as fp16 bit patterns
+    return ~_dropped(r, thr)
+
+
+def _dropped(r, thr):
+    """fp16 ordered compare r >= thr on integer bit patterns (NaN patterns: False; -0 == +0)."""
+    def key(x):                                              # monotone integer key of a non-NaN fp16 pattern
+        mag = x & 0x7FFF
+        return torch.where((x & 0x8000) != 0, -mag, mag)
+    nan = (r & 0x7FFF) > 0x7C00
+    t = torch.tensor(thr, device=r.device, dtype=torch.int64)
+    return (key(r) >= key(t)) & ~nan
 
 
 def _check(N, p, chunk=32):

@@ -25,9 +25,10 @@
 //   * one extra warp per warpgroup issues its MMAs from ONE ELECTED lane (elect.sync: without it ptxas wraps every
 //     UTCMMA in a divergence loop, 103 instead of 24 clk per issue — tests/probe/tc_rates.cu) and tracks completion
 //     with tcgen05.commit -> mbarrier.
-//   * dropout keeps element (query i, key slot c) iff  A_i * B_c >= p * 2^32  (A_i odd per-query hash word,
-//     B_c per-slot hash word): two integer ops per element in either orientation, so the row-major forward and
-//     the key-major backward regenerate identical masks.  tests/attn_tc_ref.py restates it in numpy.
+//   * dropout: element (query i, key slot c) carries the 16-bit word a_i ^ b_c (per-query / per-slot hash halves) and is
+//     dropped iff that word, read as an fp16 pattern, compares >= a threshold pattern — one LOP3 + one packed-half
+//     compare per TWO elements in either orientation, so the row-major forward and the key-major backward regenerate
+//     identical masks.  tests/attn_tc_ref.py restates it in numpy.
 //
 // At head_dim 8 the kernels are bound by MUFU.EX2 and instruction issue, not by tensor math (32 tensor FLOP per
 // exponential); see DESIGN.md §4.
@@ -61,22 +62,43 @@ __device__ long long g_tc_prof[16];   // probe build (-DVAESNE_TC_PROFILE): per-
 #define TPROF_ADD(slot, v) (void)0
 #endif
 __constant__ int g_tc_dbg = 0;      // timing experiments only (tests/probe): 1 = no second-product MMAs, 2 = no exponentials
-struct TcDrop { uint32_t s0, s1, stream, thr; float scale; bool on; };
+// Dropout rule of the tcgen05 kernels: element (query i, key slot c) carries the 16-bit word r = a_i ^ b_c (a_i: low half of a
+// per-query hash, b_c: low half of a per-slot hash) and is DROPPED iff r, read as an fp16 bit pattern, compares >= the pattern
+// `thr` (NaN patterns compare false: kept).  Counting patterns makes the rate exact to 1/65536: a positive thr T drops the
+// 0x7C01 - T patterns T..+inf; thr = 0x8000 | M drops every non-negative pattern, -0 and the M negative ones of smallest
+// magnitude (31746 + M).  Why this shape: the xor of two PACKED 16-bit pairs is one LOP3, the compare one HSET2 / HSETP2 for two
+// elements — 1.5 (forward, mask applied to the packed fp16 P) or 2 (backward) issue slots per element instead of 3 for a 32-bit
+// multiply + compare + select — and it reads the same in the row-major forward (pairs of key slots) and the key-major
+// backward (pairs of queries).  tests/attn_tc_ref.py restates it in numpy.
+struct TcDrop { uint32_t s0, s1, stream, thr2; float scale; bool on; };      // thr2: the threshold pattern in both halves
 __device__ __forceinline__ TcDrop make_tcdrop(float p, const uint64_t* seed, uint32_t stream) {
-  TcDrop d; d.on = (p > 0.f) && seed != nullptr; d.s0 = d.s1 = 0; d.stream = stream; d.thr = 0; d.scale = 1.f;
+  TcDrop d; d.on = (p > 0.f) && seed != nullptr; d.s0 = d.s1 = 0; d.stream = stream; d.thr2 = 0x7C017C01u; d.scale = 1.f;
   if (d.on) {
     uint64_t s = *seed; d.s0 = (uint32_t)s; d.s1 = (uint32_t)(s >> 32);
-    const double t = (double)p * 4294967296.0;
-    d.thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
-    d.scale = (float)(1.0 / (1.0 - (double)d.thr * (1.0 / 4294967296.0)));
+    int n = (int)((double)p * 65536.0 + 0.5);                 // patterns to drop
+    n = n < 1 ? 1 : (n > 63490 ? 63490 : n);
+    uint32_t t;
+    if (n <= 31744) t = 0x7C01u - (uint32_t)n;
+    else { if (n < 31746) n = 31746; t = 0x8000u | (uint32_t)(n - 31746); }
+    d.thr2 = t | (t << 16);
+    d.scale = (float)(1.0 / (1.0 - (double)n * (1.0 / 65536.0)));
   }
   return d;
 }
-__device__ __forceinline__ uint32_t drop_row_word(const TcDrop& d, int nh, int Lq, int i) {
-  return hash_ctr(d.s0, d.s1, d.stream, (uint64_t)nh * (uint64_t)Lq + (uint64_t)i) | 1u;
+__device__ __forceinline__ uint32_t drop_row_word(const TcDrop& d, int nh, int Lq, int i) {      // a_i (low 16 bits used)
+  return hash_ctr(d.s0, d.s1, d.stream, (uint64_t)nh * (uint64_t)Lq + (uint64_t)i) & 0xffffu;
 }
-__device__ __forceinline__ uint32_t drop_col_word(const TcDrop& d, int nh, int c) {
-  return hash_ctr(d.s1, d.s0, d.stream ^ 0x5bd1e995u, ((uint64_t)nh << 32) | (uint64_t)c);
+__device__ __forceinline__ uint32_t drop_col_word(const TcDrop& d, int nh, int c) {               // b_c
+  return hash_ctr(d.s1, d.s0, d.stream ^ 0x5bd1e995u, ((uint64_t)nh << 32) | (uint64_t)c) & 0xffffu;
+}
+// 0xffff in each half of the result whose r-half is KEPT (less-than-or-unordered against the threshold pattern)
+__device__ __forceinline__ uint32_t drop_keep_mask2(uint32_t r2, uint32_t thr2) {
+  return __hltu2_mask(*reinterpret_cast<const __half2*>(&r2), *reinterpret_cast<const __half2*>(&thr2));
+}
+// fp32 multipliers (mul or 0) of the two elements packed in r2
+__device__ __forceinline__ void drop_mult2(uint32_t r2, uint32_t thr2, float mul, float& m0, float& m1) {
+  asm("{\n\t.reg .pred p, q;\n\tsetp.ltu.f16x2 p|q, %2, %3;\n\tselp.f32 %0, %4, 0f00000000, p;\n\tselp.f32 %1, %4, 0f00000000, q;\n\t}\n"
+      : "=f"(m0), "=f"(m1) : "r"(r2), "r"(thr2), "f"(mul));
 }
 
 // packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2): two lanes per issue slot — the exponentiation loops are bound by
@@ -273,7 +295,7 @@ __device__ __forceinline__ void stage_keys(const AttnArgs& a, const TcSmem& s, i
     if (K2h) put_l2h(K2h, c, z);
   }
   const int nh = n * kH + h;
-  if (dc.on) for (int c = tid; c < Lpad; c += NT) s.w0[c] = drop_col_word(dc, nh, c);
+  if (dc.on) for (int c = tid; c < Lpad; c += NT) reinterpret_cast<uint16_t*>(s.w0)[c] = (uint16_t)drop_col_word(dc, nh, c);   // b_c, packed pairs
 #pragma unroll
   for (int u = 0; u < KeyRowsT<NT>::R; ++u) {
     const int j = tid + u * NT;
@@ -375,11 +397,19 @@ __device__ __forceinline__ void signal_in_free(uint64_t* b) { fence_before(); mb
 // scheduler hide them.  Tile MMAs get smaller (N=64), which the tensor pipe has room for in the forward (< 25 % busy).
 // =================================================================================================
 constexpr int F4_THREADS = 640;          // 16 softmax warps + 4 issuer warps (one per warpgroup)
+constexpr int F2_THREADS = 384;          // the two-warpgroup variant: two CTAs share an SM
 constexpr int F4_FK = 64;
 constexpr int F4_IN = 0, F4_OUT = 64, F4_ACC = 96, F4_X = 112, F4_CW = 128;
 constexpr size_t FWD4_SMEM = (size_t)3 * TILE_F * 4 + MAXL * 4 + 32 * 4 + 36 * 4 + 24 * 8 + 16;
 
-__global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a) {
+// NWG = 4: one CTA per SM.  NWG = 2: two CTAs per SM (101 KB of shared memory and 256 TMEM columns each) — the same sixteen
+// softmax warps per SM, but the staging prologue of one (row, head) runs under the key loop of the other instead of
+// leaving the SM idle.
+template <int NWG>
+__global__ void __launch_bounds__(NWG * 128 + 128, NWG == 4 ? 1 : 2) attn_tc_fwdN_kernel(AttnArgs a) {
+  // the issuers always form a FULL warpgroup (setmaxnreg is a warpgroup-wide instruction); with NWG = 2 its last two warps
+  // only help staging
+  constexpr int NT = NWG * 128 + 128, CW = NWG * 4;          // threads ; first issuer warp
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
   TcSmem s;
   float* const fb = reinterpret_cast<float*>(tc_smem_raw);
@@ -397,21 +427,21 @@ __global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a)
   const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
   const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
 
-  KeyRowsT<F4_THREADS> kr;
-  load_key_rows<F4_THREADS>(a, n, h, tid, kr);
+  KeyRowsT<NT> kr;
+  load_key_rows<NT>(a, n, h, tid, kr);
   if (tid == 0) {
-    for (int w = 0; w < 4; ++w) {
+    for (int w = 0; w < NWG; ++w) {
       uint64_t* b = s.bars + w * B_PER_WG;
       mbar_init(&b[B_X], 128); mbar_init(&b[B_S], 1); mbar_init(&b[B_F], 128); mbar_init(&b[B_P], 128); mbar_init(&b[B_OF], 1); mbar_init(&b[B_O], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 16) tmem_alloc<512>(s.tmem);
+  if (warp == CW) tmem_alloc<NWG * 128>(s.tmem);
   if (tid == 0) s.pre[33] = 0u;
-  const int LkC = compact_keys<F4_THREADS>(a, s, n, tid, warp, lane);
+  const int LkC = compact_keys<NT>(a, s, n, tid, warp, lane);
   // V is an fp16 [hi | lo] operand: normalised per (row, head) by an exact power of two, undone in the epilogue
-  const float vnorm = v_normaliser<F4_THREADS>(s, kr, lane);
-  stage_keys<F4_THREADS>(a, s, n, h, tid, LkC, F4_FK, Khi, Klo, nullptr, nullptr, V2h, nullptr, dc, kr, vnorm);
+  const float vnorm = v_normaliser<NT>(s, kr, lane);
+  stage_keys<NT>(a, s, n, h, tid, LkC, F4_FK, Khi, Klo, nullptr, nullptr, V2h, nullptr, dc, kr, vnorm);
   fence_async_smem();
   fence_before();
   __syncthreads();
@@ -420,9 +450,11 @@ __global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a)
   const int T = (LkC + F4_FK - 1) / F4_FK;
   const int nQT = (a.Lq + TCQ - 1) / TCQ;
 
-  if (warp >= 16) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");       // the issuer warpgroup hands its registers to the softmax warpgroups
-    const int w = warp - 16;
+  if (warp >= CW) {
+    if constexpr (NWG == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");       // the issuer warpgroup hands its registers to the softmax warpgroups
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    const int w = warp - CW;
+    if (w < NWG) {
     const uint32_t idQK = idesc_tf32(128, F4_FK), idPV = idesc_f16(128, 16);
     const uint32_t aKhi = smem_u32(Khi), aKlo = smem_u32(Klo), aV2 = smem_u32(V2h);
     const uint32_t tw = tb + (uint32_t)(w * F4_CW);
@@ -440,16 +472,18 @@ __global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a)
         mma_ts_f16(tw + F4_ACC, tw + F4_OUT + (uint32_t)t * 8, smem_desc(v, 128, HALF_ARR * 2), idPV, (j > 0 || t > 0) ? 1u : 0u);   // [Vhi | Vlo]
       }
     };
-    mma_issuer<4>(s.bars + w * B_PER_WG, w, nQT, T, issue_qk, issue_pv);
+    mma_issuer<NWG>(s.bars + w * B_PER_WG, w, nQT, T, issue_qk, issue_pv);
+    }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    if constexpr (NWG == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    else asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int wg = warp >> 2, r = tid & 127;
     uint64_t* bars = s.bars + wg * B_PER_WG;
     const uint32_t tw = tb + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(wg * F4_CW);
     const uint32_t tIN = tw + F4_IN, tOUT = tw + F4_OUT, tO = tw + F4_ACC, tQ = tw + F4_X;
     WgPhase ph = {0, 0};
     int it = 0;
-    for (int qt = wg; qt < nQT; qt += 4, ++it) {
+    for (int qt = wg; qt < nQT; qt += NWG, ++it) {
       const int i = qt * TCQ + r;
       const bool valid = i < a.Lq;
       if (T == 0) {       // every key masked: softmax of an empty set (the reference yields NaN)
@@ -475,7 +509,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a)
         fence_before();
         mbar_arrive(&bars[B_X]);
       }
-      const uint32_t rw = dc.on ? drop_row_word(dc, nh, a.Lq, valid ? i : 0) : 1u;
+      const uint32_t rw2 = dc.on ? drop_row_word(dc, nh, a.Lq, valid ? i : 0) * 0x00010001u : 0u;      // a_i in both halves
       float m_used = -1e30f, lsum = 0.f;
       for (int j = 0; j < T; ++j) {
         ph.wait_s(bars);
@@ -486,8 +520,14 @@ __global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a)
         if (j + 1 < T) signal_in_free(bars);          // QK^T of the next tile runs under this tile's softmax
         float mt = -1e30f;
         if (nvalid == F4_FK) {
+          // four independent chains (a single chain of 32 dependent FMNMX3 is ~150 clk of exposed latency per tile)
+          float m4[4] = {-1e30f, -1e30f, -1e30f, -1e30f};
 #pragma unroll
-          for (int c = 0; c < 64; c += 2) mt = max3(mt, __uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
+          for (int c = 0; c < 64; c += 8) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) m4[u] = max3(m4[u], __uint_as_float(sr[c + 2 * u]), __uint_as_float(sr[c + 2 * u + 1]));
+          }
+          mt = fmaxf(max3(m4[0], m4[1], m4[2]), m4[3]);
         } else {
 #pragma unroll
           for (int c = 0; c < 64; ++c) { if (c >= nvalid) sr[c] = 0xff800000u; mt = fmaxf(mt, __uint_as_float(sr[c])); }
@@ -506,18 +546,18 @@ __global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a)
             pk[c] = pack_h2(p0, p1);
           }
         } else {
-          const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * F4_FK);
+          const uint4* bw = reinterpret_cast<const uint4*>(s.w0 + j * (F4_FK / 2));       // 16-bit words: 8 key slots per uint4
 #pragma unroll
-          for (int cc = 0; cc < 16; ++cc) {
+          for (int cc = 0; cc < 8; ++cc) {
             const uint4 bq = bw[cc];
             const uint32_t bb[4] = {bq.x, bq.y, bq.z, bq.w};
-            float pp[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) pp[e] = ex2(__uint_as_float(sr[cc * 4 + e]) - m_used);
-            l0 += pp[0] + pp[2]; l1 += pp[1] + pp[3];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) pp[e] = (rw * bb[e] >= dc.thr) ? pp[e] : 0.f;
-            pk[cc * 2] = pack_h2(pp[0], pp[1]); pk[cc * 2 + 1] = pack_h2(pp[2], pp[3]);
+            for (int e = 0; e < 4; ++e) {
+              const int c = cc * 8 + e * 2;
+              const float p0 = ex2(__uint_as_float(sr[c]) - m_used), p1 = ex2(__uint_as_float(sr[c + 1]) - m_used);
+              l0 += p0; l1 += p1;
+              pk[cc * 4 + e] = pack_h2(p0, p1) & drop_keep_mask2(rw2 ^ bb[e], dc.thr2);
+            }
           }
         }
         lsum += l0 + l1;
@@ -553,7 +593,7 @@ __global__ void __launch_bounds__(F4_THREADS, 1) attn_tc_fwd4_kernel(AttnArgs a)
   }
   fence_before();
   __syncthreads();
-  if (warp == 16) { fence_after(); tmem_dealloc<512>(tb); }
+  if (warp == CW) { fence_after(); tmem_dealloc<NWG * 128>(tb); }
 }
 
 // =================================================================================================
@@ -695,7 +735,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
       for (int c = 0; c < 8; ++c) { q[u][c] *= qs; g[u][c] *= sc; }
       put_l2h(Q2h, i, q[u]); put_l2h(G2h, i, g[u]);
       s.f0[i] = -lse2[u]; s.f1[i] = -delta[u] * dsc;
-      s.w0[i] = dc.on ? drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : 1u;
+      reinterpret_cast<uint16_t*>(s.w0)[i] = dc.on ? (uint16_t)drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : (uint16_t)0;   // a_i, packed pairs
     }
   }
   const float cs_scale = pow2_normaliser_c(__uint_as_float(s.pre[33]));
@@ -801,6 +841,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
       const int jb = (shared && wg) ? NQ / 2 : 0, je = (shared && !wg) ? NQ / 2 : NQ;
       const int cs = kt * TCQ + r;
       const bool valid = cs < LkC;
+#ifdef VAESNE_TC_PROFILE
+      const long long tset0 = clock64();
+#endif
       const int jk = valid ? (int)s.idx[cs] : 0;
       float k[8], v[8];
 #pragma unroll
@@ -845,7 +888,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
       tmem_wait_st();
       fence_before();
       mbar_arrive(&bars[B_X]);
-      const uint32_t cw = dc.on ? drop_col_word(dc, nh, cs) : 1u;
+      TPROF_ADD(9, clock64() - tset0);
+      const uint32_t cw2 = dc.on ? drop_col_word(dc, nh, cs) * 0x00010001u : 0u;      // b_c in both halves
       for (int j = jb; j < je; ++j) {
         TPROF(0, ph.wait_s(bars));
 #ifdef VAESNE_TC_PROFILE
@@ -860,7 +904,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
           if (half == 1 && j + 1 < je) signal_in_free(bars);
           const float4* l4 = reinterpret_cast<const float4*>(s.f0 + j * BK + half * 32);
           const float4* d4 = reinterpret_cast<const float4*>(s.f1 + j * BK + half * 32);
-          const uint4* w4 = reinterpret_cast<const uint4*>(s.w0 + j * BK + half * 32);
+          const uint2* w4 = reinterpret_cast<const uint2*>(s.w0 + (j * BK + half * 32) / 2);      // 16-bit words: 4 queries per uint2
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
             const float4 lv = l4[cc], dv = d4[cc];
@@ -877,9 +921,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
               upk2(mul2(pa, add2(ta, pk2(dv.x, dv.y))), ss[0], ss[1]);
               upk2(mul2(pb, add2(tb2, pk2(dv.z, dv.w))), ss[2], ss[3]);
             } else {
-              const uint4 wv = w4[cc];
-              const float m0 = (wv.x * cw >= dc.thr) ? dc.scale : 0.f, m1 = (wv.y * cw >= dc.thr) ? dc.scale : 0.f;
-              const float m2 = (wv.z * cw >= dc.thr) ? dc.scale : 0.f, m3 = (wv.w * cw >= dc.thr) ? dc.scale : 0.f;
+              const uint2 wv = w4[cc];
+              float m0, m1, m2, m3;
+              drop_mult2(wv.x ^ cw2, dc.thr2, dc.scale, m0, m1);
+              drop_mult2(wv.y ^ cw2, dc.thr2, dc.scale, m2, m3);
               const f32x2 ma = pk2(m0, m1), mb = pk2(m2, m3);
               upk2(mul2(pa, ma), pp[0], pp[1]);
               upk2(mul2(pb, mb), pp[2], pp[3]);
@@ -913,6 +958,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
         TPROF_ADD(2, clock64() - ts0);
       }
       TPROF(3, mbar_wait(&bars[B_O], it & 1));
+#ifdef VAESNE_TC_PROFILE
+      const long long ttail0 = clock64();
+#endif
       fence_after();
       if ((je - jb) & 1) drain_dq(je - 1, BK); else drain_dq(je - 2, 2 * BK);     // an odd last tile sits alone in rows 0..63
       uint32_t o[24];
@@ -932,14 +980,332 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
         else { st8g(pk_, dk); st8g(pv_, dv); }
       }
       fence_before();
+      TPROF_ADD(10, clock64() - ttail0);
     }
 #ifdef VAESNE_TC_PROFILE
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { prof[4] = clock64() - tstart; for (int q = 0; q < 9; ++q) g_tc_prof[q] = prof[q]; }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) { prof[4] = clock64() - tstart; for (int q = 0; q < 11; ++q) g_tc_prof[q] = prof[q]; }
 #endif
   }
   fence_before();
   __syncthreads();
   if (warp == 8) { fence_after(); tmem_dealloc<512>(tb); }
+}
+
+// =================================================================================================
+// backward, ONE warpgroup per CTA and TWO CTAs per SM (default).  Same arithmetic, tiles, TMEM map and barrier protocol as the
+// two-warpgroup kernel above, but a CTA = 4 compute warps + 1 issuer warp that walks ALL key tiles of its (row, head):
+//   * two independent CTAs share an SM (113 KB of shared memory and 256 TMEM columns each), so the staging prologue and the
+//     per-key-tile pipeline drain / refill of one run under the exponentiation loop of the other — with two warpgroups in ONE
+//     CTA both sit in those phases together (measured in-kernel: 13 % + 12 % of the CTA's time with the SM idle);
+//   * no key tile is shared between warpgroups: dK / dV are plain stores, only dQ is accumulated with reductions;
+//   * 160 threads leave the register file for two such CTAs at 200 registers per thread.
+// The prologue runs in two passes over the query rows (the normalisers must be known before the operands are written): pass 1
+// only takes maxima, pass 2 re-reads the rows (L2 hits) and stages them.
+// =================================================================================================
+constexpr int B1_THREADS = 160;
+constexpr int B1_RPT = (MAXL + B1_THREADS - 1) / B1_THREADS;      // 7 rows per thread and pass
+constexpr size_t BWD1_SMEM = (size_t)2 * TILE_F * 4 + DS_BYTES + KB_BYTES + 2 * MAXL * 4 + MAXL * 2 + MAXL * 2 + 32 * 4 + 36 * 4 + 8 * 8 + 16 + 8 * 4;
+static_assert(2 * (BWD1_SMEM + 1024) <= 233472, "two one-warpgroup backward CTAs must fit one SM");
+
+__global__ void __launch_bounds__(B1_THREADS, 2) attn_tc_bwd1_kernel(AttnArgs a) {
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  TcSmem s;
+  float* const fb = reinterpret_cast<float*>(tc_smem_raw);
+  __half* Q2h = reinterpret_cast<__half*>(fb);                       // Q  hi | lo  ([d][query] fp16, 16 KB each)
+  __half* G2h = reinterpret_cast<__half*>(fb + TILE_F);              // dO hi | lo
+  unsigned char* const dsb = tc_smem_raw + (size_t)2 * TILE_F * 4;   // dS^T of a tile pair (A of the dQ product)
+  unsigned char* const kbb = dsb + DS_BYTES;                         // K rows (B of the dQ product)
+  uint16_t* w16;                                                     // [MAXL] per-query dropout halves a_i
+  {
+    float* f = reinterpret_cast<float*>(kbb + KB_BYTES);
+    for (int i = 0; i < 6; ++i) s.arr[i] = nullptr;
+    s.pad = nullptr; s.w0 = nullptr;
+    s.f0 = f; f += MAXL; s.f1 = f; f += MAXL;
+    w16 = (uint16_t*)f; f += MAXL / 2;
+    s.idx = (uint16_t*)f; f += MAXL / 2;
+    s.ballot = (uint32_t*)f; s.pre = s.ballot + 32;
+    s.bars = (uint64_t*)(s.pre + 36);
+    s.tmem = (uint32_t*)(s.bars + 8);
+  }
+  uint32_t* const nrm = s.tmem + 4;        // [8 key tiles]: largest |k| of a key tile
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int h = blockIdx.x, n = blockIdx.y, nh = n * kH + h;
+  const TcDrop dc = make_tcdrop(a.p_drop, a.seed, a.stream_id);
+
+  // ---- pass 1: largest |dO|, |q|, |v| of the (row, head) ----
+  uint32_t gmb = 0u, qmb = 0u, vmb = 0u;
+#pragma unroll
+  for (int u = 0; u < B1_RPT; ++u) {
+    const int i = tid + u * B1_THREADS;
+    float t[8];
+    if (i < a.Lk) { ld8g(t, a.v + ((long long)n * a.Lk + i) * a.ldv + h * 8); vmb = absmax8_bits(t, vmb); }
+    if (i < a.Lq) {
+      ld8g(t, a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8); qmb = absmax8_bits(t, qmb);
+      ld8g(t, a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8); gmb = absmax8_bits(t, gmb);
+    }
+  }
+  if (tid == 0) {
+    uint64_t* b = s.bars;
+    mbar_init(&b[B_X], 128); mbar_init(&b[B_S], 1); mbar_init(&b[B_F], 128); mbar_init(&b[B_P], 128); mbar_init(&b[B_OF], 1); mbar_init(&b[B_O], 1);
+    mbar_init(&b[6], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s.pre[33] = 0u; s.pre[34] = 0u; s.pre[35] = 0u;
+  }
+  if (warp == 4) tmem_alloc<256>(s.tmem);
+  if (tid < 8) nrm[tid] = 0u;
+  const int LkC = compact_keys<B1_THREADS>(a, s, n, tid, warp, lane);
+  const int nKT = (LkC + TCQ - 1) / TCQ;
+  gmb = __reduce_max_sync(0xffffffffu, gmb); qmb = __reduce_max_sync(0xffffffffu, qmb); vmb = __reduce_max_sync(0xffffffffu, vmb);
+  if (lane == 0) { atomicMax(&s.pre[33], gmb); atomicMax(&s.pre[34], qmb); atomicMax(&s.pre[35], vmb); }      // cleared before the barriers of compact_keys
+  for (int j = tid; j < a.Lk; j += B1_THREADS) {          // slot -> key index; masked keys get zero gradients
+    const int c = key_slot(s, j);
+    if (c >= 0) { s.idx[c] = (uint16_t)j; continue; }
+    float z[8];
+#pragma unroll
+    for (int c2 = 0; c2 < 8; ++c2) z[c2] = 0.f;
+    st8g(a.dk + ((long long)n * a.Lk + j) * a.lddk + h * 8, z);
+    st8g(a.dv + ((long long)n * a.Lk + j) * a.lddv + h * 8, z);
+  }
+  __syncthreads();
+  const float cs_scale = pow2_normaliser_c(__uint_as_float(s.pre[33]));
+  const float q_norm = pow2_normaliser_c(__uint_as_float(s.pre[34]));       // Q2h holds q * sqrt(1/8) * log2(e) * q_norm
+  const float v_norm = pow2_normaliser_c(__uint_as_float(s.pre[35]));       // V rows enter TMEM as v * v_norm: dS carries cs_scale * v_norm
+  // ---- pass 2: delta = rowsum(dO * O); dq starts at zero (NaN if every key is masked); operands and per-query tables ----
+  const int NQ = (a.Lq + BK - 1) / BK;
+  {
+    const float init = LkC > 0 ? 0.f : __int_as_float(0x7fc00000);
+    const float dsc = cs_scale * v_norm, qs = kQScale * q_norm;
+#pragma unroll
+    for (int u = 0; u < B1_RPT; ++u) {
+      const int i = tid + u * B1_THREADS;
+      if (i >= NQ * BK) continue;
+      float q[8], g[8], o[8], lse2 = INFINITY, d = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { q[c] = 0.f; g[c] = 0.f; o[c] = 0.f; }
+      if (i < a.Lq) {
+        ld8g(q, a.q + ((long long)n * a.Lq + i) * a.ldq + h * 8);
+        ld8g(g, a.dO + ((long long)n * a.Lq + i) * a.lddo + h * 8);
+        ld8g(o, a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8);
+        lse2 = a.LSE[(long long)nh * a.Lq + i] * kLog2e;
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { d = fmaf(g[c], o[c], d); o[c] = init; q[c] *= qs; g[c] *= cs_scale; }
+      if (i < a.Lq) st8g(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, o);
+      put_l2h(Q2h, i, q); put_l2h(G2h, i, g);
+      s.f0[i] = -lse2; s.f1[i] = -d * dsc;
+      w16[i] = dc.on ? (uint16_t)drop_row_word(dc, nh, a.Lq, i < a.Lq ? i : 0) : (uint16_t)0;
+    }
+  }
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = *s.tmem;
+  uint64_t* const bars = s.bars;
+  uint64_t* const bdq = s.bars + 6;
+  // TMEM: IN = S^T (64) | T^T (64) ; OUT = P^T (32) | dS^T (32) fp16 pairs ; ACC = dK hi|lo (16) | dV (8) | dQ tile (8) ; X = Khi | Klo | Vhi | Vlo
+
+  if (warp == 4) {
+    const uint32_t idK = idesc_f16(128, 16), idV = idesc_f16(128, 8), idQ = idesc_f16_mn(128, 8, true, true);
+    const uint32_t aQ2 = smem_u32(Q2h), aG2 = smem_u32(G2h);
+    const uint32_t aDS = smem_u32(dsb), aKB = smem_u32(kbb);
+    const uint32_t tw = tb;
+    const uint32_t idF = idesc_f16_mn(128, BK, false, true);
+    auto issue_st = [&](int j) {
+      const uint32_t d = tw + C_IN, x = tw + C_X;
+      const uint32_t off = (uint32_t)j * (BK / 8) * 128;
+      mma_ts_f16(d, x, smem_desc(aQ2 + off, 0, 128), idF, 0);                          // [Khi | Klo] x [Qhi | Qhi]
+      mma_ts_f16(d, x + 8, smem_desc(aQ2 + HALF_ARR * 2 + off, 0, 128), idF, 1);       // [Khi | 0  ] x [Qlo | Qlo]
+      mma_ts_f16(d + 64, x + 16, smem_desc(aG2 + off, 0, 128), idF, 0);                // [Vhi | Vlo] x [Ghi | Ghi]
+      mma_ts_f16(d + 64, x + 24, smem_desc(aG2 + HALF_ARR * 2 + off, 0, 128), idF, 1); // [Vhi | 0  ] x [Glo | Glo]
+    };
+    uint32_t cF = 0, cP = 0;
+    for (int kt = 0; kt < nKT; ++kt) {
+      const int ksteps = (min(TCQ, LkC - kt * TCQ) + 15) >> 4;
+      mbar_wait(&bars[B_X], kt & 1);
+      fence_after();
+      if (elect_one()) { issue_st(0); commit(&bars[B_S]); }
+      __syncwarp();
+      for (int j = 0; j < NQ; ++j) {
+        const bool last = j + 1 == NQ;
+        if (!last) {
+          mbar_wait(&bars[B_F], cF & 1); cF++;
+          fence_after();
+          if (elect_one()) { issue_st(j + 1); commit(&bars[B_S]); }
+          __syncwarp();
+        }
+        mbar_wait(&bars[B_P], cP & 1); cP++;
+        fence_after();
+        if (elect_one()) {
+          const int nsteps = (min(BK, a.Lq - j * BK) + 15) >> 4;
+          const uint32_t dK = tw + C_ACC, dV = dK + 16;
+          for (int t = 0; t < nsteps; ++t) {
+            const uint32_t off = (uint32_t)(j * (BK / 16) + t) * 256;
+            const uint32_t acc = (j > 0 || t > 0) ? 1u : 0u;
+            mma_ts_f16(dV, tw + C_OUT + (uint32_t)t * 8, smem_desc(aG2 + off, 128, 256), idV, acc);                   // P^T dO
+            mma_ts_f16(dK, tw + C_OUT + 32 + (uint32_t)t * 8, smem_desc(aQ2 + off, 128, HALF_ARR * 2), idK, acc);     // dS^T [Qhi | Qlo]
+          }
+          if (!last) commit(&bars[B_OF]);
+          if ((j & 1) || last) {                    // dS K -> dQ of the tile pair (M = 128: two 64-query tiles)
+            for (int t = 0; t < ksteps; ++t)
+              mma_ss_f16(tw + C_DQ, smem_desc(aDS + t * 256, 128, 2048), smem_desc(aKB + t * 256, 128, 2048), idQ, t > 0 ? 1u : 0u);
+            commit(last ? &bars[B_O] : bdq);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int r = tid;
+    const uint32_t tw = tb + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
+    unsigned char* const ds_row = dsb + (r & 7) * 16 + (r >> 3) * 128;      // this key's 16-byte slot in each query group
+    unsigned char* const kb_row = kbb + (r & 7) * 16 + (r >> 3) * 128;
+    const float ds_inv = 1.f / (cs_scale * v_norm);     // undoes the scale dS^T (and what is contracted with it) carries
+    float dq_scale = kScale * ds_inv;                   // times 1 / (this key tile's K normaliser), set per tile
+    WgPhase ph = {0, 0};
+    uint32_t cdq = 0;
+    // dQ contribution of the tile pair starting at query tile jq: accumulator row m (query jq*64 + m) sits in lane m
+    auto drain_dq = [&](int jq, int nrows) {
+      uint32_t v[8];
+      tmem_ld8(tw + C_DQ, v); tmem_wait_ld();
+      const int i = jq * BK + r;
+      if (r < nrows && i < a.Lq) {
+        float o[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o[c] = __uint_as_float(v[c]) * dq_scale;
+        red_add8(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, o);
+      }
+    };
+    for (int kt = 0; kt < nKT; ++kt) {
+      const int cs = kt * TCQ + r;
+      const bool valid = cs < LkC;
+      const int jk = valid ? (int)s.idx[cs] : 0;
+      float k[8], v[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { k[c] = 0.f; v[c] = 0.f; }
+      if (valid) {
+        ld8g(k, a.k + ((long long)n * a.Lk + jk) * a.ldk + h * 8);
+        ld8g(v, a.v + ((long long)n * a.Lk + jk) * a.ldv + h * 8);
+      }
+      // K and V rows are fp16 operands ([hi | lo] in TMEM, hi in the dQ product), range-managed by exact powers of two: V per
+      // (row, head) (pass 1), K per key tile — the exponent (an fma instead of an add) and the dQ drain undo it for free
+      float k_norm;
+      {
+        const uint32_t kmb = __reduce_max_sync(0xffffffffu, absmax8_bits(k, 0u));
+        if (lane == 0) atomicMax(&nrm[kt], kmb);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        k_norm = pow2_normaliser_c(__uint_as_float(nrm[kt]));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { k[c] *= k_norm; v[c] *= v_norm; }
+      }
+      const float inv_qk = 1.f / (q_norm * k_norm);
+      const f32x2 iqk2 = pk2(inv_qk, inv_qk);
+      dq_scale = kScale * ds_inv / k_norm;
+      *reinterpret_cast<uint4*>(kb_row) = make_uint4(pack_h2(k[0], k[1]), pack_h2(k[2], k[3]), pack_h2(k[4], k[5]), pack_h2(k[6], k[7]));
+      {                // A operands: columns 0-3 = hi pairs, 4-7 = lo pairs (K index 0-7 hi, 8-15 lo); second operand: [hi | 0]
+        uint32_t xa[8], xb[8];
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+          const float* src = pass ? v : k;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const __half2 h2 = __floats2half2_rn(src[2 * c], src[2 * c + 1]);
+            const float2 hf = __half22float2(h2);
+            xa[c] = *reinterpret_cast<const uint32_t*>(&h2);
+            xa[4 + c] = pack_h2(src[2 * c] - hf.x, src[2 * c + 1] - hf.y);
+            xb[c] = xa[c]; xb[4 + c] = 0u;
+          }
+          tmem_st8(tX + pass * 16, xa); tmem_st8(tX + pass * 16 + 8, xb);
+        }
+      }
+      fence_async_smem();
+      tmem_wait_st();
+      fence_before();
+      mbar_arrive(&bars[B_X]);
+      const uint32_t cw2 = dc.on ? drop_col_word(dc, nh, cs) * 0x00010001u : 0u;      // b_c in both halves
+      for (int j = 0; j < NQ; ++j) {
+        ph.wait_s(bars);
+        uint32_t pk[32], dk2[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t sr[32], tr[32];
+          tmem_ld32(tIN + half * 32, sr); tmem_ld32(tIN + 64 + half * 32, tr);
+          tmem_wait_ld();
+          if (half == 1 && j + 1 < NQ) signal_in_free(bars);
+          const float4* l4 = reinterpret_cast<const float4*>(s.f0 + j * BK + half * 32);
+          const float4* d4 = reinterpret_cast<const float4*>(s.f1 + j * BK + half * 32);
+          const uint2* w4 = reinterpret_cast<const uint2*>(w16 + j * BK + half * 32);      // 16-bit words: 4 queries per uint2
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            const float4 lv = l4[cc], dv = d4[cc];
+            float pp[4], ss[4];
+            const int c = cc * 4;
+            float x0, x1, x2, x3;
+            upk2(fma2(pk2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), iqk2, pk2(lv.x, lv.y)), x0, x1);
+            upk2(fma2(pk2(__uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3])), iqk2, pk2(lv.z, lv.w)), x2, x3);
+            const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);
+            const f32x2 pa = pk2(p0, p1), pb = pk2(p2, p3);
+            const f32x2 ta = pk2(__uint_as_float(tr[c]), __uint_as_float(tr[c + 1])), tb2 = pk2(__uint_as_float(tr[c + 2]), __uint_as_float(tr[c + 3]));
+            if (!dc.on) {
+              pp[0] = p0; pp[1] = p1; pp[2] = p2; pp[3] = p3;
+              upk2(mul2(pa, add2(ta, pk2(dv.x, dv.y))), ss[0], ss[1]);
+              upk2(mul2(pb, add2(tb2, pk2(dv.z, dv.w))), ss[2], ss[3]);
+            } else {
+              const uint2 wv = w4[cc];
+              float m0, m1, m2, m3;
+              drop_mult2(wv.x ^ cw2, dc.thr2, dc.scale, m0, m1);
+              drop_mult2(wv.y ^ cw2, dc.thr2, dc.scale, m2, m3);
+              const f32x2 ma = pk2(m0, m1), mb = pk2(m2, m3);
+              upk2(mul2(pa, ma), pp[0], pp[1]);
+              upk2(mul2(pb, mb), pp[2], pp[3]);
+              upk2(mul2(pa, fma2(ta, ma, pk2(dv.x, dv.y))), ss[0], ss[1]);
+              upk2(mul2(pb, fma2(tb2, mb, pk2(dv.z, dv.w))), ss[2], ss[3]);
+            }
+            pk[half * 16 + cc * 2] = pack_h2(pp[0], pp[1]); pk[half * 16 + cc * 2 + 1] = pack_h2(pp[2], pp[3]);
+            dk2[half * 16 + cc * 2] = pack_h2(ss[0], ss[1]); dk2[half * 16 + cc * 2 + 1] = pack_h2(ss[2], ss[3]);
+          }
+        }
+        const int par = j & 1;
+        if (j > 0) ph.wait_out_free(bars);
+        if (par == 0 && j > 0) {
+          mbar_wait(bdq, cdq & 1); cdq++;       // dQ product of the previous tile pair done: read its accumulator, reuse the dS^T buffer
+          fence_after();
+          drain_dq(j - 2, 2 * BK);
+        }
+        tmem_st32(tOUT, pk); tmem_st32(tOUT + 32, dk2);
+        // padded key rows (zero K, but P = 2^(-lse) may be huge) must contribute exact zeros to dQ
+#pragma unroll
+        for (int g8 = 0; g8 < 8; ++g8)
+          *reinterpret_cast<uint4*>(ds_row + (par * 8 + g8) * 2048) = valid ? make_uint4(dk2[g8 * 4], dk2[g8 * 4 + 1], dk2[g8 * 4 + 2], dk2[g8 * 4 + 3]) : make_uint4(0u, 0u, 0u, 0u);
+        fence_async_smem();
+        tmem_wait_st();
+        fence_before();
+        mbar_arrive(&bars[B_P]);
+      }
+      mbar_wait(&bars[B_O], kt & 1);
+      fence_after();
+      if (NQ & 1) drain_dq(NQ - 1, BK); else drain_dq(NQ - 2, 2 * BK);     // an odd last tile sits alone in rows 0..63
+      uint32_t o[24];
+      tmem_ld16(tA, o); tmem_ld8(tA + 16, o + 16); tmem_wait_ld();
+      if (valid) {
+        float dk[8], dv[8];
+        const float ck = kLn2 * ds_inv / q_norm;               // hi + lo parts; Q carried log2(e) and its normaliser
+        const float cv = 1.f / cs_scale;                       // dV = P^T (dO cs_scale)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          dk[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * ck;
+          dv[c] = __uint_as_float(o[16 + c]) * cv;
+        }
+        st8g(a.dk + ((long long)n * a.Lk + jk) * a.lddk + h * 8, dk);
+        st8g(a.dv + ((long long)n * a.Lk + jk) * a.lddv + h * 8, dv);
+      }
+      fence_before();
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 4) { fence_after(); tmem_dealloc<256>(tb); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -957,6 +1323,7 @@ template <typename K>
 static int tc_configure(K k, size_t bytes, const char* what) {
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
   if (e != cudaSuccess) { set_error("%s: cannot reserve %zu B of shared memory: %s", what, bytes, cudaGetErrorString(e)); return V_ECUDA; }
+  (void)cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);   // two CTAs per SM need the full window
   return V_OK;
 }
 
@@ -974,17 +1341,31 @@ static int tc_configure_dev(void (*k)(AttnArgs), size_t bytes, const char* what)
 }
 
 int attn_tc_fwd(const AttnArgs& a, cudaStream_t st) {
-  const int cfg = tc_configure_dev(attn_tc_fwd4_kernel, FWD4_SMEM, "attn_tc_fwd4");
+  static const bool one_cta = env_flag("VAESNE_TC_FWD4");      // the one-CTA-per-SM, four-warpgroup launch (comparison)
+  if (one_cta) {
+    const int cfg = tc_configure_dev(attn_tc_fwdN_kernel<4>, FWD4_SMEM, "attn_tc_fwd4");
+    if (cfg) return cfg;
+    attn_tc_fwdN_kernel<4><<<dim3(kH, a.N), dim3(F4_THREADS), FWD4_SMEM, st>>>(a);
+    return check_launch("attn_tc_fwd4");
+  }
+  const int cfg = tc_configure_dev(attn_tc_fwdN_kernel<2>, FWD4_SMEM, "attn_tc_fwd2x2");
   if (cfg) return cfg;
-  attn_tc_fwd4_kernel<<<dim3(kH, a.N), dim3(F4_THREADS), FWD4_SMEM, st>>>(a);
-  return check_launch("attn_tc_fwd4");
+  attn_tc_fwdN_kernel<2><<<dim3(kH, a.N), dim3(F2_THREADS), FWD4_SMEM, st>>>(a);
+  return check_launch("attn_tc_fwd2x2");
 }
 
 int attn_tc_bwd(const AttnArgs& a, cudaStream_t st) {
-  const int cfg = tc_configure_dev(attn_tc_bwd_kernel, BWD_SMEM, "attn_tc_bwd");
+  static const bool two_wg = env_flag("VAESNE_TC_BWD2");      // the two-warpgroup, one-CTA-per-SM launch (comparison)
+  if (two_wg) {
+    const int cfg = tc_configure_dev(attn_tc_bwd_kernel, BWD_SMEM, "attn_tc_bwd");
+    if (cfg) return cfg;
+    attn_tc_bwd_kernel<<<dim3(kH, a.N), dim3(NTHREADS), BWD_SMEM, st>>>(a);
+    return check_launch("attn_tc_bwd");
+  }
+  const int cfg = tc_configure_dev(attn_tc_bwd1_kernel, BWD1_SMEM, "attn_tc_bwd1");
   if (cfg) return cfg;
-  attn_tc_bwd_kernel<<<dim3(kH, a.N), dim3(NTHREADS), BWD_SMEM, st>>>(a);
-  return check_launch("attn_tc_bwd");
+  attn_tc_bwd1_kernel<<<dim3(kH, a.N), dim3(B1_THREADS), BWD1_SMEM, st>>>(a);
+  return check_launch("attn_tc_bwd1");
 }
 
 }  // namespace vaesne

@@ -143,6 +143,26 @@ int vaesne_step_advance(int* step, unsigned long long* seed, void* stream);
  * global Philox stream (util_layers.py:265-271,283); here every forward call takes one fresh 64-bit seed. */
 int vaesne_seed_next(unsigned long long* cell, unsigned long long* out, void* stream);
 
+/* ---- contrastive objective ------------------------------------------------------------------------
+ * negInfoNCE (losses.py:98-110): l2norm = F.normalize(z, dim=-1) (inv_norm [B] is saved for the backward);
+ * ce_rows: loss[i] = logsumexp_j(inv_tau * a_i . b_j) - inv_tau * a_i . b_{i + label_off}  over rows A [n,P], columns Bm [m,P]
+ * (the logits matrix is never materialised; P <= 64); bwd: dA / dB (+)= w * (*gptr) * d(sum_i loss[i]);
+ * sum_scale: out = scale * (sum a [+ sum b]). */
+int vaesne_l2norm_fwd(const float* x, int B, int P, float eps, float* y, float* inv_norm, void* stream);
+int vaesne_l2norm_bwd(const float* y, const float* inv_norm, const float* dy, int B, int P, float* dx, int accumulate, void* stream);
+int vaesne_ce_rows_fwd(const float* A, int n, const float* Bm, int m, int P, float inv_tau, int label_off, float* lse, float* loss, void* stream);
+int vaesne_ce_rows_bwd(const float* A, int n, const float* Bm, int m, int P, float inv_tau, int label_off, const float* lse,
+                       float w, const float* gptr /* device scalar, nullable */, float* dA, int dA_acc, float* dB, int dB_acc, void* stream);
+int vaesne_sum_scale(const float* a, const float* b /* nullable */, int n, float scale, float* out, void* stream);
+
+/* ---- device-side augmentation of a resident training set --------------------------------------------
+ * cannon/test_photospectra.py:45-47,75-78, cannon/ZTF_photospect.py:46-66: output row r reads source row r % B (the 10x
+ * repeat); x_out = x + sigma_elem * N(0,1) per element + sigma_row * N(0,1) per output row (the per-curve time shift);
+ * mask_out = mask | (U < mask_p).  x / x_out or mask / mask_out may be NULL (only the other is produced).
+ * Counter-based generator keyed by (*seed, stream_id, element): independent of the launch geometry. */
+int vaesne_augment(const float* x, const unsigned char* mask, long long R, long long B, int L, float sigma_elem, float sigma_row,
+                   float mask_p, const unsigned long long* seed, uint32_t stream_id, float* x_out, unsigned char* mask_out, void* stream);
+
 /* ---- probe hooks (tests/probe only; not part of the operator surface) ---------------------------
  * vaesne_debug_tc(flags): timing experiments on the tcgen05 attention key pass (1 = skip the second-product MMAs,
  * 2 = skip the exponentials; results are then meaningless).  vaesne_debug_tc_prof(out16): per-phase clocks of

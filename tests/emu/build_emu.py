@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "vaesne-dev_b200", "csrc")
 OUT = os.path.join(HERE, "libvaesne_emu.so")
 # tcgen05 / TMA kernels (attn_tc*.cu) are Blackwell-only and are not part of the emulated build
-PORTABLE = ["api.cu", "lin.cu", "attn.cu", "attn_small.cu", "attn_mid.cu", "misc.cu", "loss.cu"]
+PORTABLE = ["api.cu", "lin.cu", "attn.cu", "attn_small.cu", "attn_mid.cu", "misc.cu", "loss.cu", "extra.cu"]
 
 
 def build(force=False):

@@ -261,3 +261,83 @@ class _ElboFn(torch.autograd.Function):
 
 def elbo_objective(spec, fam_q, pz_mu, pz_s, loc, mu, s):
     return _ElboFn.apply(spec, fam_q, pz_mu, pz_s, loc, mu, s)
+
+
+# ------------------------------------------------------------------------------------------------
+class _InfoNCEFn(torch.autograd.Function):
+    """-(CE(z1n z2n^T / tau, arange) + CE(z2n z1n^T / tau, arange)) / 2 with zXn = F.normalize(zX)   losses.py:98-110
+    (single process: rows and columns are the same batch).  Every arithmetic step is a kernel of csrc/extra.cu."""
+
+    @staticmethod
+    def forward(ctx, z1, z2, temperature):
+        z1, z2 = _prep(z1.detach(), torch.float32), _prep(z2.detach(), torch.float32)
+        with dev_guard(z1.device):
+            n = z1.shape[0]
+            inv_tau = 1.0 / float(temperature)
+            y1, i1 = P.l2norm_fwd(z1)
+            y2, i2 = P.l2norm_fwd(z2)
+            l1, lse1 = P.ce_rows_fwd(y1, y2, inv_tau)
+            l2, lse2 = P.ce_rows_fwd(y2, y1, inv_tau)
+            out = P.sum_scale(l1, l2, -0.5 / n)
+        ctx.saved = (y1, i1, y2, i2, lse1, lse2, inv_tau, n)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        y1, i1, y2, i2, lse1, lse2, inv_tau, n = ctx.saved
+        g = _prep(g)
+        with dev_guard(y1.device):
+            w = -0.5 / n
+            dy1 = torch.empty_like(y1); dy2 = torch.empty_like(y2)
+            P.ce_rows_bwd(y1, y2, inv_tau, 0, lse1, w, g, dA=dy1, dB=dy2)                               # rows = z1, columns = z2
+            P.ce_rows_bwd(y2, y1, inv_tau, 0, lse2, w, g, dA=dy2, dA_acc=True, dB=dy1, dB_acc=True)     # rows = z2, columns = z1
+            return P.l2norm_bwd(y1, i1, dy1), P.l2norm_bwd(y2, i2, dy2), None
+
+
+def infonce_objective(z1, z2, temperature):
+    return _InfoNCEFn.apply(z1, z2, temperature)
+
+
+class _L2NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z):
+        z = _prep(z.detach(), torch.float32)
+        with dev_guard(z.device):
+            y, inv = P.l2norm_fwd(z)
+        ctx.saved = (y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved
+        with dev_guard(y.device):
+            return P.l2norm_bwd(y, inv, _prep(dy, torch.float32))
+
+
+class _CeRowsFn(torch.autograd.Function):
+    """sum_i [ logsumexp_j(A_i . B_j / tau) - A_i . B_{i + off} / tau ]: the data-parallel form (columns = the gathered batch)."""
+
+    @staticmethod
+    def forward(ctx, A, Bm, inv_tau, off):
+        A, Bm = _prep(A.detach(), torch.float32), _prep(Bm.detach(), torch.float32)
+        with dev_guard(A.device):
+            loss, lse = P.ce_rows_fwd(A, Bm, inv_tau, off)
+            out = P.sum_scale(loss, None, 1.0)
+        ctx.saved = (A, Bm, lse, inv_tau, off)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        A, Bm, lse, inv_tau, off = ctx.saved
+        with dev_guard(A.device):
+            dA, dB = torch.empty_like(A), torch.empty_like(Bm)
+            P.ce_rows_bwd(A, Bm, inv_tau, off, lse, 1.0, _prep(g), dA=dA, dB=dB)
+        return dA, dB, None, None
+
+
+def l2normalize(z):
+    return _L2NormFn.apply(z)
+
+
+def ce_rows_sum(A, Bm, inv_tau, off=0):
+    return _CeRowsFn.apply(A, Bm, inv_tau, off)

@@ -46,6 +46,12 @@ _SIGS = {
     "vaesne_adamw_flat": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _vp, _f, _vp],
     "vaesne_step_advance": [_vp, _vp, _vp],
     "vaesne_seed_next": [_vp, _vp, _vp],
+    "vaesne_l2norm_fwd": [_vp, _i, _i, _f, _vp, _vp, _vp],
+    "vaesne_l2norm_bwd": [_vp, _vp, _vp, _i, _i, _vp, _i, _vp],
+    "vaesne_ce_rows_fwd": [_vp, _i, _vp, _i, _i, _f, _i, _vp, _vp, _vp],
+    "vaesne_ce_rows_bwd": [_vp, _i, _vp, _i, _i, _f, _i, _vp, _f, _vp, _vp, _i, _vp, _i, _vp],
+    "vaesne_sum_scale": [_vp, _vp, _i, _f, _vp, _vp],
+    "vaesne_augment": [_vp, _vp, _ll, _ll, _i, _f, _f, _f, _vp, _u32, _vp, _vp, _vp],
 }
 EXPORTS = sorted(list(_SIGS) + ["vaesne_last_error", "vaesne_abi_version", "vaesne_is_emulated", "vaesne_launch_count",
                   "vaesne_debug_tc", "vaesne_debug_tc_prof"])      # the last two: probe hooks (tests/probe)

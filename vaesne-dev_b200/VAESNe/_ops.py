@@ -337,6 +337,64 @@ def step_advance(step, seed):
     N.check(N.lib().vaesne_step_advance(N.ptr(step), N.ptr(seed), N.stream_of(t)))
 
 
+# ------------------------------------------------------------------------------------------------
+def l2norm_fwd(x, eps=1e-12):
+    B, Pd = x.shape
+    y = torch.empty_like(x)
+    inv = torch.empty(B, device=x.device, dtype=torch.float32)
+    N.check(N.lib().vaesne_l2norm_fwd(_c(_f32(x, "x"), "x"), B, Pd, float(eps), y.data_ptr(), inv.data_ptr(), N.stream_of(x)))
+    return y, inv
+
+
+def l2norm_bwd(y, inv, dy, dx=None, accumulate=False):
+    B, Pd = y.shape
+    if dx is None:
+        dx = torch.empty_like(y)
+    N.check(N.lib().vaesne_l2norm_bwd(_c(y, "y"), _c(inv, "inv"), _c(_f32(dy, "dy"), "dy"), B, Pd, _c(dx, "dx"), int(accumulate), N.stream_of(y)))
+    return dx
+
+
+def ce_rows_fwd(A, Bm, inv_tau, label_off=0):
+    """loss[i] = logsumexp_j(inv_tau * A_i . Bm_j) - inv_tau * A_i . Bm_{i + label_off}; also returns lse (saved for the backward)."""
+    n, Pd = A.shape
+    m = Bm.shape[0]
+    lse = torch.empty(n, device=A.device, dtype=torch.float32)
+    loss = torch.empty(n, device=A.device, dtype=torch.float32)
+    N.check(N.lib().vaesne_ce_rows_fwd(_c(_f32(A, "A"), "A"), n, _c(_f32(Bm, "Bm"), "Bm"), m, Pd, float(inv_tau), int(label_off),
+                                       lse.data_ptr(), loss.data_ptr(), N.stream_of(A)))
+    return loss, lse
+
+
+def ce_rows_bwd(A, Bm, inv_tau, label_off, lse, w, gptr, dA=None, dA_acc=False, dB=None, dB_acc=False):
+    n, Pd = A.shape
+    m = Bm.shape[0]
+    N.check(N.lib().vaesne_ce_rows_bwd(_c(A, "A"), n, _c(Bm, "Bm"), m, Pd, float(inv_tau), int(label_off), _c(lse, "lse"), float(w), N.ptr(gptr),
+                                       N.ptr(dA), int(dA_acc), N.ptr(dB), int(dB_acc), N.stream_of(A)))
+
+
+def sum_scale(a, b, scale):
+    out = torch.empty((), device=a.device, dtype=torch.float32)
+    N.check(N.lib().vaesne_sum_scale(_c(a, "a"), N.ptr(b), a.numel(), float(scale), out.data_ptr(), N.stream_of(a)))
+    return out
+
+
+def augment(x, mask, copies, sigma_elem, sigma_row, mask_p, seed, stream_id):
+    """x [B, L] float32 (or None), mask [B, L] bool (or None) -> (x_out [copies*B, L] | None, mask_out [copies*B, L] bool | None)."""
+    ref = x if x is not None else mask
+    B, L = (ref.shape[0], ref.shape[1]) if ref.dim() == 2 else (ref.shape[0], 1)
+    R = B * int(copies)
+    shape = (R,) + tuple(ref.shape[1:])
+    xo = torch.empty(shape, device=ref.device, dtype=torch.float32) if x is not None else None
+    mo = torch.empty(shape, device=ref.device, dtype=torch.bool) if (mask is not None or (mask_p > 0 and x is None)) else None
+    if mask is None and mask_p > 0 and x is not None:
+        mo = torch.empty(shape, device=ref.device, dtype=torch.bool)
+    if mask is not None and (mask.dtype != torch.bool or not mask.is_contiguous()):
+        raise ValueError("augment: mask must be a contiguous torch.bool tensor")
+    N.check(N.lib().vaesne_augment(N.ptr(None if x is None else _f32(x, "x")), N.ptr(mask), R, B, L, float(sigma_elem), float(sigma_row), float(mask_p),
+                                   seed.data_ptr(), int(stream_id) & 0xFFFFFFFF, N.ptr(xo), N.ptr(mo), N.stream_of(ref)))
+    return xo, mo
+
+
 _SEED_CELLS = {}
 
 

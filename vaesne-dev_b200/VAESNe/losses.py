@@ -5,7 +5,6 @@ For the accelerated model classes the objectives run through the fused likelihoo
 log-sum-exp kernels; any other model object goes through the generic torch.distributions form."""
 import numpy as np
 import torch
-from torch.nn import functional as F
 
 from . import _noise
 from . import _ops as P
@@ -98,21 +97,21 @@ def m_iwae(model, x, K=1):
 
 
 def negInfoNCE(model, x, temperature=0.07):
-    """Symmetric InfoNCE on the two projected encodings (the only place samples of a batch interact)."""
-    z1, z2 = model(x)
-    z1 = F.normalize(z1, dim=-1)
-    z2 = F.normalize(z2, dim=-1)
+    """Symmetric InfoNCE on the two projected encodings (the only place samples of a batch interact): L2-normalise,
+    logits = z1 z2^T / tau, -(CE(logits, arange) + CE(logits^T, arange)) / 2 — fused kernels (csrc/extra.cu), the B x B logits
+    matrix is never materialised."""
     from . import parallel
+    from ._functions import ce_rows_sum, infonce_objective, l2normalize
+    z1, z2 = model(x)
     if parallel.enabled():
         # batch-sharded data parallelism: the negatives are the GLOBAL batch (the projections of all ranks are gathered, tiny
         # messages); each rank returns its rows' share of the global mean, so the ranks' losses — and, through the SUM
         # all-reduce of the gradient buckets, their gradients — add up to the single-process objective on the whole batch
+        z1, z2 = l2normalize(z1), l2normalize(z2)
         z1g, z2g = parallel.gather_batch(z1), parallel.gather_batch(z2)
         n, world = z1.size(0), parallel.world_size()
-        labels = torch.arange(n, device=z1.device) + parallel.rank() * n
-        rows = F.cross_entropy(z1 @ z2g.T / temperature, labels, reduction="sum")
-        cols = F.cross_entropy(z2 @ z1g.T / temperature, labels, reduction="sum")
+        off = parallel.rank() * n
+        rows = ce_rows_sum(z1, z2g, 1.0 / temperature, off)
+        cols = ce_rows_sum(z2, z1g, 1.0 / temperature, off)
         return -(rows + cols) / (2 * n * world)
-    logits = z1 @ z2.T / temperature
-    labels = torch.arange(z1.size(0), device=z1.device)
-    return -(F.cross_entropy(logits, labels) + F.cross_entropy(logits.T, labels)) / 2
+    return infonce_objective(z1, z2, temperature)

@@ -36,7 +36,8 @@ from VAESNe.SpectraVAE import SpectraVAE, BrightSpectraVAE  # noqa: E402
 from VAESNe.mmVAE import photospecMMVAE  # noqa: E402
 from VAESNe.losses import elbo, m_iwae, negInfoNCE  # noqa: E402
 from VAESNe.contrastiveNets import ContraPhotSpec  # noqa: E402
-from VAESNe.regression import photoend2endregression, specend2endregression, VAEregressionHead  # noqa: E402
+from VAESNe.regression import (photoend2endregression, specend2endregression, VAEregressionHead,  # noqa: E402
+                               contrasphotoregressionHead, contrasspecregressionHead)
 
 OUT = os.path.join(ROOT, "tests", "golden")
 os.makedirs(OUT, exist_ok=True)
@@ -236,7 +237,59 @@ def case_end2end():
          **pack_x("x", x2), **grads_of(m2))
 
 
+def case_contras_heads():
+    """regression.py:28-65: frozen ContraPhotSpec encoders (eval, no grad) -> flatten -> MLP; outputs + the heads' gradients."""
+    net = ContraPhotSpec(4, 4, 8, 6, 32, 4, 32, 2, 0.0, 32, 4, 2, 32, 0.0, False)
+    load_random(net, 51)
+    net_shapes = dict(_LAST_SHAPES)
+    x = [O.synth_photometry(3, 60, 6, seed=51), O.synth_spectra(3, 300, seed=51)]
+    out = {}
+    for tag, cls, xi, seed in (("photo", contrasphotoregressionHead, x[0], 52), ("spec", contrasspecregressionHead, x[1], 53)):
+        head = cls(net, 5, MLPlatent=[64, 64])
+        hshapes = {k: list(v.shape) for k, v in head.outfc.state_dict().items()}
+        head.outfc.load_state_dict(O.random_params(hshapes, seed))
+        tgt = torch.randn(3, 5, generator=torch.Generator().manual_seed(seed))
+        y = head(xi)
+        loss = torch.nn.functional.mse_loss(y, tgt)
+        head.zero_grad()
+        loss.backward()
+        out.update({f"{tag}.y": y.detach().numpy(), f"{tag}.target": tgt.numpy(), f"{tag}.loss": loss.item(), f"{tag}.seed": seed,
+                    f"{tag}.shapes": json.dumps(hshapes)})
+        out.update({f"{tag}.grad.{n}": q.grad.numpy().copy() for n, q in head.outfc.named_parameters()})
+        assert all(q.grad is None for q in net.parameters())          # frozen
+    np.savez(os.path.join(OUT, "contras_heads.npz"), seed=51, shapes=json.dumps(net_shapes), **out,
+             **pack_x("x0", x[0]), **pack_x("x1", x[1]))
+    print("contras_heads")
+
+
+def case_generate():
+    """photospecMMVAE.generate(N, x) (mmVAE.py:108-118) and SpectraVAE.generate(N, x) (SpectraVAE.py:198-206): prior samples
+    decoded on the data's positions.  The latents are drawn from torch's global RNG: they are recorded next to the outputs."""
+    pv = PhotometricVAE(num_bands=6, latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=2, dropout=0.0)
+    sv = SpectraVAE(latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=2, dropout=0.0)
+    m = photospecMMVAE([pv, sv], beta=1.0)
+    load_random(m, 61)
+    x = [O.synth_photometry(2, 60, 6, seed=61), O.synth_spectra(2, 300, seed=61)]
+    N = 3
+    torch.manual_seed(611)
+    latents = m.pz(*m.pz_params).rsample(torch.Size([N, 2]))
+    torch.manual_seed(611)
+    gen = m.generate(N, x)
+    torch.manual_seed(612)
+    lat_s = sv.pz(*sv.pz_params).rsample(torch.Size([N, 1]))
+    torch.manual_seed(612)
+    xs1 = tuple(t[:1] for t in x[1])
+    gen_s = sv.generate(N, xs1)
+    save("generate", seed=61, N=N, latents=latents.detach().numpy(), gen0=gen[0].numpy(), gen1=gen[1].numpy(),
+         lat_s=lat_s.detach().numpy(), gen_s=gen_s.numpy(), **pack_x("x0", x[0]), **pack_x("x1", x[1]))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1:          # regenerate selected cases only: python oracle/make_golden.py case_generate ...
+        torch.set_num_threads(8)
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     torch.set_num_threads(8)
     case_photo_elbo()
     case_spec_elbo()
@@ -247,3 +300,5 @@ if __name__ == "__main__":
     case_end2end()
     case_bright()
     case_noconcat()
+    case_contras_heads()
+    case_generate()

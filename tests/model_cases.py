@@ -2,6 +2,8 @@
 the GPU tests (test infrastructure).  Tolerances are stated per case; the goldens are fp32 reference
 outputs, so the bound is fp32 round-off amplified through 4 post-LN layers (never looser than the
 1e-3 the north star allows for the fp32/TF32 path)."""
+import os
+
 import torch
 import torch.distributions as dist
 
@@ -96,15 +98,21 @@ def run_bright_case(name, device):
     loss = elbo(m, x, K=K)
     loss.backward()
     assert abs(loss.item() - float(g["loss"])) < FWD_TOL * abs(float(g["loss"])), (loss.item(), float(g["loss"]))
-    # Tolerance.  fp32 kernels (the emulator; the GPU with VAESNE_NO_TC=1 measures 1.3e-5): the usual 1e-3.  With the
-    # tcgen05 attention (spectra, L >= 256) the second products take P / dS as 11-bit operands — the "TF32 path" of the
-    # north star.  The reconstruction still agrees to 4e-5, but the Laplace likelihood's gradient sign(loc - x) / s is
-    # discontinuous: an element with loc within round-off of x flips, which moves a parameter gradient by a fixed quantum
-    # (one of K*B*L elements), and the mean-centred Bright loss shrinks the decoder gradients that quantum is measured
-    # against.  tests/probe/bright_debug.py measures 2.6e-4 .. 2.4e-3 over parameter draws and lengths (plain SpectraVAE:
-    # 2e-5 .. 6e-4, the upper end being single sign flips), hence 5e-3 here.
-    tc_attention = str(device).startswith("cuda") and name == "bright_spec_elbo"
-    worst = _check_grads(m, g, tol=5e-3 if tc_attention else GRAD_TOL, scale_floor=0.1)
+    # Tolerance.  fp32 kernels (the emulator; the GPU with VAESNE_NO_TC=1, which tests/test_gpu_alt_paths.py runs: 1.3e-5):
+    # the contract's 1e-3 on every tensor's own scale.  With the tcgen05 attention (spectra, L >= 256) P and dS enter the
+    # second products as 11-bit operands — the "TF32 path" of the north star, relative error ~2.4e-4 per term.  The Bright
+    # reconstruction is MEAN-CENTRED, so every decoder gradient is a sum of such terms that cancels to ~1 % of their size
+    # (measured: decoder tensors are 1e-3 .. 2e-2 of the model's largest gradient): the rounding does not cancel with them
+    # and shows up as 1-4 % of those small tensors, i.e. <= 2.1e-4 of the model's gradient scale.  It is NOT Laplace sign
+    # flips (round 1's guess): the gate below counts them and finds none.  Hence two explicit bounds instead of a blanket:
+    # 1e-3 on the own scale of every tensor that is at least 3 % of the model's largest gradient, and 3e-4 of the largest
+    # gradient for every tensor.
+    tc_attention = str(device).startswith("cuda") and name == "bright_spec_elbo" and not os.environ.get("VAESNE_NO_TC")
+    if not tc_attention:
+        worst = _check_grads(m, g, tol=GRAD_TOL, scale_floor=0.1)
+    else:
+        worst = _bright_gate(m, g)
+        _bright_sign_flips_are_counted(m, g, x, u, K)
     _noise.inject([u])
     with torch.no_grad():
         qz, px, zs = m(x, K)
@@ -112,6 +120,107 @@ def run_bright_case(name, device):
     _noise.inject([u])
     assert rel_err(m.reconstruct(x, K).cpu(), g["loc"]) < FWD_TOL
     return loss.item(), worst
+
+
+def _bright_gate(m, g, own_tol=GRAD_TOL, model_tol=3e-4, big=0.03):
+    want = golden_grads(g)
+    gmax = max(float(v.abs().max()) for v in want.values())
+    worst_own, worst_model = (0.0, None), (0.0, None)
+    for n, p in m.named_parameters():
+        if not p.requires_grad:
+            continue
+        w = want[n]
+        err, own = float((p.grad.cpu() - w).abs().max()), float(w.abs().max())
+        if own >= big * gmax and err / own > worst_own[0]:
+            worst_own = (err / own, n)
+        if err / gmax > worst_model[0]:
+            worst_model = (err / gmax, n)
+    assert worst_own[0] < own_tol, ("own scale", worst_own)
+    assert worst_model[0] < model_tol, ("model scale", worst_model)
+    print(f"bright gate: worst {worst_own[0]:.2e} of its own scale ({worst_own[1]}), {worst_model[0]:.2e} of the model's largest gradient ({worst_model[1]})")
+    return worst_model
+
+
+def _bright_sign_flips_are_counted(m, g, x, u, K, delta=2e-3, max_flips=8):
+    """The Laplace likelihood's gradient is -sign(loc - x) / s per element: an element whose reconstruction sits within
+    round-off of the data would flip sign between two equally accurate forward passes and move every parameter gradient by a
+    fixed quantum.  Counted here so that it cannot be used as an excuse: the elements whose sign differs from the golden
+    reconstruction's must be FEW and genuinely tied (|loc_golden - x| < delta)."""
+    from VAESNe import _noise
+    _noise.clear(); _noise.inject([u])
+    with torch.no_grad():
+        _, px, _ = m(x, K)
+    gold = torch.from_numpy(g["loc"]).to(x[0].device)
+    live = ~x[3]
+    flips = (torch.sign(px.loc - x[0]) != torch.sign(gold - x[0])) & live
+    nflip = int(flips.sum())
+    margin = float((gold - x[0]).abs()[flips].max()) if nflip else 0.0
+    assert nflip <= max_flips and margin < delta, (nflip, margin)
+    print(f"bright gate: {nflip} sign-flip element(s) of {int(live.sum()) * px.loc.shape[0]} (margin {margin:.2e})")
+
+
+def run_contras_heads_case(device):
+    """contras{photo,spec}regressionHead (regression.py:28-65) against the live reference: outputs and the heads' gradients."""
+    import json
+    from oracle import vaesne_oracle as O
+    from VAESNe.contrastiveNets import ContraPhotSpec
+    from VAESNe.regression import contrasphotoregressionHead, contrasspecregressionHead
+    g = load_golden("contras_heads")
+    net = ContraPhotSpec(4, 4, 8, 6, 32, 4, 32, 2, 0.0, 32, 4, 2, 32, 0.0, False)
+    net.load_state_dict(golden_params(g))
+    net.to(device)
+    xs = {"photo": _to(golden_x(g, "x0"), device), "spec": _to(golden_x(g, "x1"), device)}
+    for tag, cls in (("photo", contrasphotoregressionHead), ("spec", contrasspecregressionHead)):
+        head = cls(net, 5, MLPlatent=[64, 64])
+        head.outfc.load_state_dict(O.random_params(json.loads(str(g[f"{tag}.shapes"])), int(g[f"{tag}.seed"])))
+        head.to(device)
+        y = head(xs[tag])
+        assert rel_err(y.detach().cpu(), g[f"{tag}.y"]) < FWD_TOL, (tag, rel_err(y.detach().cpu(), g[f"{tag}.y"]))
+        loss = torch.nn.functional.mse_loss(y, torch.from_numpy(g[f"{tag}.target"]).to(device))
+        assert abs(loss.item() - float(g[f"{tag}.loss"])) < FWD_TOL * abs(float(g[f"{tag}.loss"]))
+        loss.backward()
+        for n, p in head.outfc.named_parameters():
+            assert rel_err(p.grad.cpu(), g[f"{tag}.grad.{n}"]) < GRAD_TOL, (tag, n)
+        assert all(p.grad is None for p in net.parameters()) and not net.training            # frozen, left in eval mode
+
+
+def run_generate_case(device):
+    """photospecMMVAE.generate / SpectraVAE.generate (mmVAE.py:108-118, SpectraVAE.py:198-206) against the live reference.
+    The prior draws come from torch's global generator: on the CPU (emulator) the seeded draw IS the reference's and the whole
+    call is compared; on a CUDA device the draw differs, so the latents of the seeded call are captured and the golden
+    decoder is applied to them by the oracle... the recorded latents go through the same decode the call uses."""
+    from VAESNe.PhotometricVAE import PhotometricVAE
+    from VAESNe.SpectraVAE import SpectraVAE
+    from VAESNe.mmVAE import photospecMMVAE
+    g = load_golden("generate")
+    pv = PhotometricVAE(num_bands=6, latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=2, dropout=0.0)
+    sv = SpectraVAE(latent_len=4, latent_dim=4, model_dim=32, num_heads=4, ff_dim=32, num_layers=2, dropout=0.0)
+    m = photospecMMVAE([pv, sv], beta=1.0)
+    m.load_state_dict(golden_params(g))
+    m.to(device)
+    x = [_to(golden_x(g, "x0"), device), _to(golden_x(g, "x1"), device)]
+    N = int(g["N"])
+    lat = torch.from_numpy(g["latents"]).to(device)
+    # decode of the reference's latents on the data's positions == the reference's generations
+    for d, vae in enumerate(m.vaes):
+        assert rel_err(vae._decode_loc(lat, x[d]).detach().cpu(), g[f"gen{d}"]) < FWD_TOL, d
+    if str(device) == "cpu":                                   # same generator as the reference: the call itself reproduces it
+        torch.manual_seed(611)
+        gen = m.generate(N, x)
+        assert rel_err(gen[0].cpu(), g["gen0"]) < FWD_TOL and rel_err(gen[1].cpu(), g["gen1"]) < FWD_TOL
+        torch.manual_seed(612)
+        gs = sv.generate(N, tuple(t[:1] for t in x[1]))
+        assert tuple(gs.shape) == tuple(g["gen_s"].shape) and rel_err(gs.cpu(), g["gen_s"]) < FWD_TOL
+    else:                                                      # device generator: the call must equal the decode of ITS OWN draw
+        torch.manual_seed(7)
+        own = m.pz(*m.pz_params).rsample(torch.Size([N, x[0][0].shape[0]]))
+        torch.manual_seed(7)
+        gen = m.generate(N, x)
+        for d, vae in enumerate(m.vaes):
+            assert torch.equal(gen[d], vae._decode_loc(own, x[d]))
+        gs = sv.generate(N, tuple(t[:1] for t in x[1]))
+        assert tuple(gs.shape) == tuple(g["gen_s"].shape) and torch.isfinite(gs).all()
+    assert tuple(gen[0].shape) == (N, 2, 60) and tuple(gen[1].shape) == (N, 2, 300) and not m.training
 
 
 def run_noconcat_case(name, device):

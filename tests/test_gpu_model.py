@@ -35,6 +35,14 @@ def test_bright_variants(name):
     MC.run_bright_case(name, "cuda")
 
 
+def test_contras_regression_heads():
+    MC.run_contras_heads_case("cuda")
+
+
+def test_generate():
+    MC.run_generate_case("cuda")
+
+
 def test_script_flow():
     import script_flow
     script_flow.run("cuda", n=13, Lp=60, Ls=982, K=2)

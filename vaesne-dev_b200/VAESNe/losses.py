@@ -14,19 +14,27 @@ from .mmVAE import photospecMMVAE
 from .util_layers import kl_divergence, log_mean_exp
 
 
+def _same_family(model) -> bool:
+    try:
+        return _noise.family_of(model.pz) == _noise.family_of(model.qz_x)
+    except NotImplementedError:
+        return False
+
+
 def expand_first_dim(t, K):
     return t.unsqueeze(0).expand((K,) + t.shape)
 
 
 def elbo(model, x, K=1, debug=False):
     """E_{p(x)}[ELBO]: mean over K and batch of (sum_L log p(x|z)*llik_scaling - sum KL(q||p))."""
-    if isinstance(model, FusedVAEMixin) and not debug:
+    # the fused objective has the closed-form KL of a prior and posterior of the SAME family (Laplace | Normal); any other
+    # pairing takes the generic torch.distributions form below, whose kl_divergence falls back to the reference's K-sample
+    # Monte-Carlo estimate when no closed form is registered (util_layers.py:330-336) — on top of the same kernels
+    if isinstance(model, FusedVAEMixin) and not debug and _same_family(model):
         zs, mu, s = model._sample(x, K)
         model._qz_x_params = (mu, s)
         loc = model._decode_loc(zs, x)
         fq = P.FAMILY[_noise.family_of(model.qz_x)]
-        if _noise.family_of(model.pz) != _noise.family_of(model.qz_x):
-            raise NotImplementedError("fused ELBO needs prior and posterior of the same family")
         return elbo_objective(model.lik_spec(x), fq, model._pz_params[0], model._pz_params[1], loc, mu, s)
     qz_x, px_z, _ = model(x, K)
     lpx_z = px_z.log_prob(expand_first_dim(x[0], K)).reshape(*px_z.batch_shape[:2], -1) * model.llik_scaling

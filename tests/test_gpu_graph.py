@@ -47,3 +47,35 @@ def test_graphed_step_matches_eager():
     d = (pe - pg).abs()
     assert float(d.median()) < 1e-6 and float((d > 1e-4).float().mean()) < 0.02, (float(d.median()), float((d > 1e-4).float().mean()))
     assert float(d.max()) <= 2 * len(le) * 1e-3
+
+
+def test_graphed_encode_matches_eager_and_follows_parameter_updates():
+    """vae.graph_encode = True: the third encode() of a signature is captured, later ones replay; results equal the eager
+    path bit for bit, also after the parameters changed in place (the graph reads their storage) and after an optimiser
+    re-homed them (new storage -> new capture)."""
+    from VAESNe.optim import FusedAdamW
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    net = bench.build_model(dev, dropout=0.1)
+    for vae, mod in ((net.vaes[0], 0), (net.vaes[1], 1)):
+        xs = [tuple(t.to(dev) for t in bench.synth_batch(32, seed=40 + i)[mod]) for i in range(5)]
+        want = [vae.encode(x).clone() for x in xs]
+        vae.graph_encode = True
+        got = [vae.encode(x).clone() for x in xs]
+        assert all(torch.equal(a, b) for a, b in zip(want, got))
+        entry = [e for e in vae.__dict__["_encode_graphs"].values() if "graph" in e]
+        assert len(entry) == 1
+        with torch.no_grad():
+            for p in vae.enc.parameters():
+                p.mul_(1.01)
+        vae.graph_encode = False; w2 = vae.encode(xs[0]).clone()
+        vae.graph_encode = True; g2 = vae.encode(xs[0]).clone()
+        assert torch.equal(w2, g2) and not torch.equal(w2, want[0])
+    FusedAdamW(net.parameters(), lr=1e-3)                  # re-homes every parameter into one flat buffer
+    vae = net.vaes[0]
+    x = tuple(t.to(dev) for t in bench.synth_batch(32, seed=50)[0])
+    vae.graph_encode = False; w3 = vae.encode(x).clone()
+    vae.graph_encode = True
+    for _ in range(4):
+        g3 = vae.encode(x).clone()
+    assert torch.equal(w3, g3)

@@ -15,6 +15,16 @@ def masked_scale_tensor(mask, big: float, like: torch.Tensor):
     return torch.where(mask, one + torch.tensor(big, dtype=torch.float32, device=like.device), one)
 
 
+def _encode_graphs_enabled(model, x) -> bool:
+    import os
+    if not x[0].is_cuda:
+        return False
+    flag = model.__dict__.get("graph_encode")
+    if flag is None:
+        flag = os.environ.get("VAESNE_CUDA_GRAPH", "0") not in ("", "0")
+    return bool(flag) and not torch.cuda.is_current_stream_capturing()
+
+
 class FusedVAEMixin:
     """Expects: self.enc.inference_transformer, self.dec.generativetransformer, self.qz_x / px_z / pz,
     self.latent_len, self._big (1e8 | 1e10) and self._bottleneck(x)."""
@@ -55,9 +65,35 @@ class FusedVAEMixin:
     def encode(self, x, mean=True):
         self.eval()
         with torch.no_grad():
-            mu, s = self._posterior_params(x)
+            mu, s = self._graphed_posterior_params(x) if _encode_graphs_enabled(self, x) else self._posterior_params(x)
             qz_x = self.qz_x(mu, s)
         return qz_x.mean if mean else qz_x
+
+    # ---- CUDA-graph replay of the encode path (the "encode latents/s" metric) ------------------------------------------
+    # The photometry encoder is ~60 kernels of a few microseconds at the batch sizes the regression scripts use (32 .. 512):
+    # launch-bound.  Per input signature the third call captures the whole posterior-parameter computation into one graph over
+    # static input buffers; later calls copy the batch in and replay.  Opt-in (`vae.graph_encode = True` or VAESNE_CUDA_GRAPH=1);
+    # the capture is keyed on the parameters' storage, so an optimiser that re-homes them (FusedAdamW) or a load_state_dict
+    # into new storage re-captures instead of replaying stale pointers.
+    def _graphed_posterior_params(self, x):
+        cache = self.__dict__.setdefault("_encode_graphs", {})
+        sig = tuple((tuple(t.shape), t.dtype) for t in x) + (next(self.enc.parameters()).data_ptr(),)
+        e = cache.setdefault(sig, {"seen": 0})
+        if "graph" not in e:
+            if e["seen"] < 2:                       # ordinary calls: they also run every one-time host initialisation
+                e["seen"] += 1
+                return self._posterior_params(x)
+            static = tuple(t.clone() for t in x)
+            torch.cuda.synchronize(x[0].device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._posterior_params(static)
+            e.update(graph=graph, static=static, out=out)
+        else:
+            for st, t in zip(e["static"], x):
+                st.copy_(t, non_blocking=True)
+        e["graph"].replay()
+        return e["out"][0].clone(), e["out"][1].clone()
 
     def reconstruct(self, x, K=1):
         self.eval()

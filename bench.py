@@ -276,6 +276,24 @@ def run_batch_sweep(dev, headline):
     return out
 
 
+def run_dp_small_batch(model, opt, loss_fn, dev, rank, world, timed, B=16, steps=20):
+    """samples/s at per-GPU batch 16 (cannon/ZTF_photospect.py:77), eager and graph-replayed; max over ranks like the headline."""
+    from VAESNe.training_util import training_step
+    batches = [_to_dev(synth_batch(B, 7000 + 10 * rank + i), dev, True) for i in range(2)]
+    out = {"per_gpu_batch": B}
+    for tag, graph in (("samples_per_s", False), ("samples_per_s_cuda_graph", True)):
+        def run(n, graph=graph):
+            training_step(model, opt, [batches[i % 2] for i in range(n)], loss_fn, multimodal=True, cuda_graph=graph)
+        try:
+            run(4)
+            ms = timed(run, steps)
+            out[tag] = world * B * steps / (ms * 1e-3)
+        except Exception as e:      # noqa: BLE001
+            out[tag] = None
+            out[tag + "_error"] = repr(e)[:200]
+    return out
+
+
 def run_dp_check(model, loss_fn, x, dev, world):
     """One backward with the data-parallel plumbing off (local gradients) and one with it on (per-stack buckets all-reduced
     asynchronously over NCCL), same noise and dropout seeds; the reduced gradients must equal the sum over ranks of the local
@@ -284,8 +302,11 @@ def run_dp_check(model, loss_fn, x, dev, world):
     import torch.distributed as dist
 
     def grads(enabled):
+        import itertools
+        from VAESNe import _stacks
         parallel.enable(enabled)
         P._SEED_CELLS.clear()                      # the dropout seed cell is re-drawn from torch's (re-seeded) generator
+        _stacks._call_counter = itertools.count(1)  # ... and the dropout stream ids restart, so both passes draw the same masks
         torch.manual_seed(4242 + dist.get_rank())
         model.zero_grad(set_to_none=True)
         (-loss_fn(model, x)).backward()
@@ -514,6 +535,12 @@ def main():
     if world > 1:
         dp_check = run_dp_check(model, loss_fn, resident[0], dev, world)
 
+    # ---- N > 1: the reference scripts' own batch (16 per GPU) is launch-bound; eager vs the step replayed as ONE CUDA graph
+    #      with the NCCL bucket all-reduces captured inside it
+    dp_small = None
+    if world > 1 and not args.no_extras:
+        dp_small = run_dp_small_batch(model, opt, loss_fn, dev, rank, world, timed)
+
     # ---- BASELINE.json's other configurations and the per-GPU batch sweep (1 GPU) --------------------------------------
     cfgs = sweep = None
     if world == 1 and not args.no_extras:
@@ -523,7 +550,7 @@ def main():
         sweep = run_batch_sweep(dev, headline=(B, value))
 
     if rank != 0:
-        torch.distributed.destroy_process_group()
+        _finish(opt, world)
         return
 
     # ---- the unmodified reference: stock eager PyTorch on this GPU, and on the host cores (bounded samples) --------------
@@ -562,10 +589,22 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8, "ms_per_step": ms_e2e / args.steps,
                     "last_loss": last.get("loss")},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "eager_gpu_baseline": eager,
-            "configs": cfgs, "batch_sweep": sweep, "dp_check": dp_check, "encode": enc}
+            "configs": cfgs, "batch_sweep": sweep, "dp_check": dp_check, "dp_small_batch": dp_small, "encode": enc}
     print(json.dumps(line), flush=True)
+    _finish(None, world)
+
+
+def _finish(opt, world):
+    """Leave without tearing NCCL down: destroy_process_group() after a CUDA graph has captured NCCL launches blocks in the
+    watchdog (seen on the 2-GPU box: 'CudaEventDestroy hang'); everything is flushed, so the process simply exits."""
     if world > 1:
-        torch.distributed.destroy_process_group()
+        sys.stdout.flush(); sys.stderr.flush()
+        torch.cuda.synchronize()
+        try:
+            torch.distributed.barrier()
+        except Exception:      # noqa: BLE001
+            pass
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -87,7 +87,9 @@ class GraphedStep:
                       for g in self.optimizer.param_groups)
         sig = tuple((tuple(t.shape), t.dtype) for t in leaves) + (hyper,)
         e = self.entries.setdefault(sig, dict(seen=0))
-        if e.get("eager") or device.type != "cuda" or parallel.enabled():
+        # data-parallel runs are captured too: the per-stack bucket all-reduces are NCCL launches on NCCL's own stream, forked
+        # from / joined to the capturing stream by events, so they become nodes of the graph (VAESNE_DP_GRAPH=0 opts out)
+        if e.get("eager") or device.type != "cuda" or (parallel.enabled() and os.environ.get("VAESNE_DP_GRAPH", "1") in ("", "0")):
             return self._eager(x, device)
         if "graph" not in e:
             if e["seen"] < self.WARM:

@@ -71,8 +71,8 @@ int vaesne_lin_bwd(const float* dY, long long lddy, int T, int K, int N,
  * never masked (the appended phase token, SpectraLayers.py:129-131).  LSE is [N,4,Lq].
  * N = 0 returns VAESNE_OK without touching the (possibly null) pointers; N <= 65535 per call (the Python binding splits
  * larger batches, rows are independent).  A row whose keys are all masked yields NaN, as the reference does.
- * Four kernel families serve the call, chosen by shape only (forward and backward always agree): tcgen05 (256 <= Lq, Lk
- * <= 1024), few keys (Lk <= 8), short sequences (Lq, Lk <= 64), general. */
+ * Four kernel families serve the call, chosen by shape only (forward and backward always agree): tcgen05 (96 <= Lq, Lk
+ * <= 1024; TF32-class second products), few keys (Lk <= 8), one CTA per row (Lq, Lk <= 255 otherwise), general. */
 int vaesne_attn_fwd(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
                     int N, int Lq, int Lk, const unsigned char* mask, int mask_rows, int mask_len,
                     float p_drop, const uint64_t* seed, uint32_t stream_id,

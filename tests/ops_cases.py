@@ -15,6 +15,15 @@ from oracle import vaesne_oracle as O
 TOL = 2e-5
 
 
+def is_tc_shape(Lq, Lk, device):
+    """Shapes the tcgen05 attention kernels serve on a CUDA device (TF32-class second products: tolerance 1e-3)."""
+    import os
+    if not str(device).startswith("cuda") or os.environ.get("VAESNE_NO_TC"):
+        return False
+    lmin = int(os.environ.get("VAESNE_TC_MIN", "96"))
+    return lmin <= Lq <= 1024 and lmin <= Lk <= 1024
+
+
 def _g(seed):
     return torch.Generator().manual_seed(seed)
 

@@ -19,6 +19,9 @@ CASES = [c for c in OC.ATTN_CASES_FULL if c["Lq"] >= 256 and c["Lk"] >= 256] + [
     dict(id="self_1024_mask", N=2, Lq=1024, Lk=1024, mask=True, packed="qkv"),
     dict(id="self_257_mask", N=2, Lq=257, Lk=257, mask=True, packed="qkv"),
     dict(id="cross_640x385", N=2, Lq=640, Lk=385, mask=True, mask_len=300, packed="q+kv"),
+    dict(id="self_96_mask", N=3, Lq=96, Lk=96, mask=True, packed="qkv"),                     # the window's lower edge: one partial tile
+    dict(id="cross_130x100_mask", N=3, Lq=130, Lk=100, mask=True, packed="q+kv"),
+    dict(id="self_200_mask_rowmod", N=4, Lq=200, Lk=200, mask=True, mask_rows=2, packed="qkv"),
 ]
 
 

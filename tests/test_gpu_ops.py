@@ -15,8 +15,7 @@ def test_lin(case):
 @pytest.mark.parametrize("case", OC.ATTN_CASES_FULL, ids=lambda c: c["id"])
 def test_attn(case):
     # shapes served by the tcgen05 kernels carry tf32 second-product operands (see test_gpu_attn_tc.py)
-    tc = case["Lq"] >= 256 and case["Lk"] >= 256
-    OC.run_attn_case(case, "cuda", tol=1e-3 if tc else OC.TOL)
+    OC.run_attn_case(case, "cuda", tol=1e-3 if OC.is_tc_shape(case["Lq"], case["Lk"], "cuda") else OC.TOL)
 
 
 def test_misc():
@@ -56,3 +55,9 @@ def test_fully_masked_row_is_nan_like_the_reference(L):
 def test_boundary_lengths():
     import edge_cases
     edge_cases.run_boundary_lengths("cuda", edge_cases.BOUNDARY_SMALL + edge_cases.BOUNDARY_GPU)
+
+
+def test_no_cliff_between_the_attention_windows():
+    import edge_cases
+    t = edge_cases.run_window_timing("cuda")
+    print("ns per score element (fwd + bwd):", {k: round(v, 4) for k, v in t.items()})

@@ -1,7 +1,9 @@
-// Attention over short sequences (Lq, Lk <= 64): the photometry stacks' 60-point light curves — decoder self-attention
-// on K*M*B rows of 60 tokens, the encoder's 60 x 60 and 8 x 60 blocks (PhotometricLayers.py:48-67,117-143; core as in attn.cu).
-// Everything one batch row needs (K, V, and in the backward Q, dO, lse, delta) fits in 34 KB of shared memory, so ONE CTA
-// serves a batch row with all four heads: global memory is touched once, coalesced, and the score matrix never exists.
+// Attention over short and medium sequences (Lq, Lk <= 255): the photometry stacks' 60-point light curves — decoder
+// self-attention on K*M*B rows of 60 tokens, the encoder's 60 x 60 and 8 x 60 blocks (PhotometricLayers.py:48-67,117-143; core
+// as in attn.cu) — and anything up to where the tcgen05 kernels take over (256 tokens): real light curves with more than 64
+// points, short spectra.  Everything one batch row needs (K, V, and in the backward Q, dO, lse, delta) fits in shared memory
+// (34 KB at 64 tokens, 137 KB at 256), so ONE CTA serves a batch row with all four heads: global memory is touched once,
+// coalesced, and the score matrix never exists.  Three instantiations (64 / 128 / 256 tokens, 4 threads per token).
 //   forward : thread = (query, head); two sweeps over the keys in shared memory (row max, then exp / sum / PV).
 //   backward: the same CTA runs a query-major sweep (dQ) and a key-major sweep (dK, dV) over the staged operands — each
 //             gradient row is owned by one thread, so there are no atomics and no second launch.
@@ -13,7 +15,7 @@
 
 namespace vaesne {
 
-constexpr int ML = 64;                              // max tokens on either side
+constexpr int kMidMax = 256;                        // largest instantiation (exclusive upper bound of the window is 256)
 constexpr float kMScale = 0.35355339059327373f;     // sqrt(1/8)
 
 __device__ __forceinline__ void ld8m(float* d, const float* p) {
@@ -56,6 +58,7 @@ __device__ __forceinline__ void stage_rows(float (*dst)[32], const float* src, l
   reinterpret_cast<float4*>(&dst[i][h * 8])[0] = make_float4(x[0], x[1], x[2], x[3]);
   reinterpret_cast<float4*>(&dst[i][h * 8])[1] = make_float4(x[4], x[5], x[6], x[7]);
 }
+template <int ML>
 __device__ __forceinline__ void stage_bias(const AttnArgs& a, int n, float* sB, int tid) {
   if (tid < ML) {
     float b = 0.f;
@@ -65,15 +68,17 @@ __device__ __forceinline__ void stage_bias(const AttnArgs& a, int n, float* sB, 
   }
 }
 
-__global__ void __launch_bounds__(256) attn_mid_fwd_kernel(AttnArgs a) {
-  __shared__ __align__(16) float sK[ML][32];
-  __shared__ __align__(16) float sV[ML][32];
-  __shared__ float sB[ML];
+template <int ML>
+__global__ void __launch_bounds__(ML * 4) attn_mid_fwd_kernel(AttnArgs a) {
+  VDYNSMEM(float, smem);
+  float (*sK)[32] = reinterpret_cast<float (*)[32]>(smem);
+  float (*sV)[32] = reinterpret_cast<float (*)[32]>(smem + ML * 32);
+  float* sB = smem + 2 * ML * 32;
   const int tid = threadIdx.x, n = blockIdx.x;
   const int i = tid >> 2, h = tid & 3;
   stage_rows(sK, a.k + (long long)n * a.Lk * a.ldk, a.ldk, a.Lk, tid, 1.f);
   stage_rows(sV, a.v + (long long)n * a.Lk * a.ldv, a.ldv, a.Lk, tid, 1.f);
-  stage_bias(a, n, sB, tid);
+  stage_bias<ML>(a, n, sB, tid);
   float q[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) q[c] = 0.f;
@@ -113,20 +118,23 @@ __global__ void __launch_bounds__(256) attn_mid_fwd_kernel(AttnArgs a) {
   a.LSE[((long long)n * kH + h) * a.Lq + i] = (m + log2f(l)) * kLn2;
 }
 
-__global__ void __launch_bounds__(256) attn_mid_bwd_kernel(AttnArgs a) {
-  __shared__ __align__(16) float sQ[ML][32];      // scaled by sqrt(1/8) * log2(e)
-  __shared__ __align__(16) float sK[ML][32];
-  __shared__ __align__(16) float sV[ML][32];
-  __shared__ __align__(16) float sG[ML][32];      // dO
-  __shared__ float sL[kH][ML], sD[kH][ML];        // lse (log2 units), delta = rowsum(dO * O)
-  __shared__ float sB[ML];
+template <int ML>
+__global__ void __launch_bounds__(ML * 4) attn_mid_bwd_kernel(AttnArgs a) {
+  VDYNSMEM(float, smem);
+  float (*sQ)[32] = reinterpret_cast<float (*)[32]>(smem);                      // scaled by sqrt(1/8) * log2(e)
+  float (*sK)[32] = reinterpret_cast<float (*)[32]>(smem + ML * 32);
+  float (*sV)[32] = reinterpret_cast<float (*)[32]>(smem + 2 * ML * 32);
+  float (*sG)[32] = reinterpret_cast<float (*)[32]>(smem + 3 * ML * 32);       // dO
+  float (*sL)[ML] = reinterpret_cast<float (*)[ML]>(smem + 4 * ML * 32);       // lse (log2 units)
+  float (*sD)[ML] = reinterpret_cast<float (*)[ML]>(smem + 4 * ML * 32 + kH * ML);   // delta = rowsum(dO * O)
+  float* sB = smem + 4 * ML * 32 + 2 * kH * ML;
   const int tid = threadIdx.x, n = blockIdx.x;
   const int i = tid >> 2, h = tid & 3;
   const long long nh = (long long)n * kH + h;
   stage_rows(sK, a.k + (long long)n * a.Lk * a.ldk, a.ldk, a.Lk, tid, 1.f);
   stage_rows(sV, a.v + (long long)n * a.Lk * a.ldv, a.ldv, a.Lk, tid, 1.f);
   stage_rows(sQ, a.q + (long long)n * a.Lq * a.ldq, a.ldq, a.Lq, tid, kMScale * kLog2e);
-  stage_bias(a, n, sB, tid);
+  stage_bias<ML>(a, n, sB, tid);
   float g[8], lse2 = INFINITY, delta = 0.f;
 #pragma unroll
   for (int c = 0; c < 8; ++c) g[c] = 0.f;
@@ -194,15 +202,31 @@ __global__ void __launch_bounds__(256) attn_mid_bwd_kernel(AttnArgs a) {
 
 bool attn_mid_eligible(const AttnArgs& a) {
   static const bool off = [] { const char* e = getenv("VAESNE_NO_MID_ATTN"); return e && e[0] && e[0] != '0'; }();
-  return !off && a.Lk > 8 && a.Lk <= ML && a.Lq <= ML && a.Lq >= 1;
+  return !off && a.Lk > 8 && a.Lk < kMidMax && a.Lq < kMidMax && a.Lq >= 1;
 }
-int attn_mid_fwd(const AttnArgs& a, cudaStream_t st) {
-  VLAUNCH(attn_mid_fwd_kernel, dim3(a.N), dim3(256), 0, st, a);
+template <int ML>
+static int mid_fwd(const AttnArgs& a, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (2 * ML * 32 + ML);
+  auto k = attn_mid_fwd_kernel<ML>;
+  VSET_SMEM(k, smem);
+  VLAUNCH(k, dim3(a.N), dim3(ML * 4), smem, st, a);
   return check_launch("attn_mid_fwd");
 }
-int attn_mid_bwd(const AttnArgs& a, cudaStream_t st) {
-  VLAUNCH(attn_mid_bwd_kernel, dim3(a.N), dim3(256), 0, st, a);
+template <int ML>
+static int mid_bwd(const AttnArgs& a, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (4 * ML * 32 + 2 * kH * ML + ML);
+  auto k = attn_mid_bwd_kernel<ML>;
+  VSET_SMEM(k, smem);
+  VLAUNCH(k, dim3(a.N), dim3(ML * 4), smem, st, a);
   return check_launch("attn_mid_bwd");
+}
+int attn_mid_fwd(const AttnArgs& a, cudaStream_t st) {
+  const int L = a.Lq > a.Lk ? a.Lq : a.Lk;
+  return L <= 64 ? mid_fwd<64>(a, st) : (L <= 128 ? mid_fwd<128>(a, st) : mid_fwd<256>(a, st));
+}
+int attn_mid_bwd(const AttnArgs& a, cudaStream_t st) {
+  const int L = a.Lq > a.Lk ? a.Lq : a.Lk;
+  return L <= 64 ? mid_bwd<64>(a, st) : (L <= 128 ? mid_bwd<128>(a, st) : mid_bwd<256>(a, st));
 }
 
 }  // namespace vaesne

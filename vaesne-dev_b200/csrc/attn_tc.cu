@@ -1314,8 +1314,11 @@ static bool env_flag(const char* name) { const char* e = getenv(name); return e 
 bool attn_tc_eligible(const AttnArgs& a) {
   static const bool off = env_flag("VAESNE_NO_TC");
   if (off) return false;
-  // long attention only: the tile machinery needs >= 2 row tiles to be worth a CTA
-  return a.Lq >= 256 && a.Lk >= 256 && a.Lk <= MAXL && a.Lq <= MAXL && a.N <= 65535;
+  // from 96 tokens on either side: measured per score element (forward + backward, B200) the tensor-core kernels pass the
+  // one-CTA-per-row CUDA-core kernels (attn_mid.cu) between 64 and 96 tokens — 10.7 vs 8.8 ps at 64, 6.2 vs 8.7 at 96, 4.0 vs
+  // 9.1 at 128, 2.1 at 256 — so there is no cliff between the windows (tests/edge_cases.py run_window_timing)
+  static const int lmin = [] { const char* e = getenv("VAESNE_TC_MIN"); const int v = e ? atoi(e) : 0; return v >= 16 ? v : 96; }();
+  return a.Lq >= lmin && a.Lk >= lmin && a.Lk <= MAXL && a.Lq <= MAXL && a.N <= 65535;
 }
 bool attn_tc_has_bwd() { return true; }
 

@@ -427,16 +427,19 @@ def main():
         key, top = max(summ.items(), key=lambda kv: kv[1]["total_ms"])
         pk = peaks()
         name = key[0]
-        # measured DRAM traffic per batch row (ncu --set full of the SAME build: the table carries the library's hash and a
+        # measured DRAM traffic per batch row (ncu --set full of the SAME build: the table carries the hash of the kernel sources and a
         # mismatched table is refused, so the figure cannot go stale silently; profiles/make_traffic.py regenerates it)
         traffic_tab, traffic_note = {}, None
         try:
             tab = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
-            sha = hashlib.sha256(open(_native.LIB_PATH, "rb").read()).hexdigest()
-            if tab.get("lib_sha256") == sha:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("vaesne_b200_build", os.path.join(PKG, "build.py"))
+            bmod = importlib.util.module_from_spec(spec); spec.loader.exec_module(bmod)
+            sha = bmod.source_hash()
+            if tab.get("src_sha256") == sha:
                 traffic_tab = tab
             else:
-                traffic_note = f"profiles/r2_traffic.json was measured on build {str(tab.get('lib_sha256'))[:12]}, this is {sha[:12]}: refused"
+                traffic_note = f"profiles/r2_traffic.json was measured on kernel sources {str(tab.get('src_sha256'))[:12]}, these are {sha[:12]}: refused"
         except Exception as e:      # noqa: BLE001
             traffic_note = f"no traffic table: {e!r}"
         if name.startswith("attn"):

@@ -4,8 +4,9 @@ captures of the CURRENT build (run on the CPU box after the GPU session brought 
     python profiles/make_traffic.py gpurun_out/r2_attn_fwd.ncu-rep gpurun_out/r2_attn_bwd.ncu-rep --rows 1024 --lq 982 --lk 982
 
 traffic = dram__bytes_read.sum + dram__bytes_write.sum of one launch; the kernels stream each (row, head) once, so it is stored
-per batch row and bench.py scales it by N.  The table carries the sha256 of lib/libvaesne_b200.so the captures were taken with
-(tests/probe/gpu_ncu_r2.sh writes it next to the reports); bench.py refuses a table whose hash is not the loaded library's."""
+per batch row and bench.py scales it by N.  The table carries the sha256 of the kernel sources the captured library was built
+from (tests/probe/gpu_ncu_r2.sh writes it next to the reports; the .so itself is not bit-reproducible across links); bench.py
+refuses a table whose hash is not that of the sources in the tree."""
 import argparse
 import csv
 import io
@@ -35,12 +36,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("fwd"); ap.add_argument("bwd")
     ap.add_argument("--rows", type=int, default=1024); ap.add_argument("--lq", type=int, default=982); ap.add_argument("--lk", type=int, default=982)
-    ap.add_argument("--sha", default=os.path.join(ROOT, "gpurun_out", "r2_ncu_lib.sha256"))
+    ap.add_argument("--sha", default=os.path.join(ROOT, "gpurun_out", "r2_ncu_src.sha256"))
     a = ap.parse_args()
     sha = open(a.sha).read().split()[0]
     tab = {"_source": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none on tests/probe/attn_tc_check.py "
                       f"(N={a.rows} rows x 4 heads, Lq={a.lq}, Lk={a.lk}, p_drop 0.1); per batch row, scaled by N in bench.py",
-           "lib_sha256": sha, "per_row": {}, "kernels": {}}
+           "src_sha256": sha, "per_row": {}, "kernels": {}}
     for name, rep in (("attn_fwd", a.fwd), ("attn_bwd", a.bwd)):
         kname, tot, dur = dram_bytes(rep)[0]
         tab["per_row"][f"{name}|{a.lq}|{a.lk}"] = tot / a.rows

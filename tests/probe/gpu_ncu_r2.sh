@@ -2,7 +2,7 @@
 # round-2 evidence session: plain bench (exit 0) -> ncu launch list of the same command -> ncu --set full of the top kernels
 cd "$GRAFT_REPO_ROOT" || exit 1
 mkdir -p gpurun_out
-sha256sum vaesne-dev_b200/lib/libvaesne_b200.so > gpurun_out/r2_ncu_lib.sha256
+python vaesne-dev_b200/build.py --source-hash > gpurun_out/r2_ncu_src.sha256
 timeout 300 python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > gpurun_out/r2_plain_bench.json 2> gpurun_out/r2_plain_bench.err || exit 1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 700 --csv --log-file gpurun_out/r2_launches.csv \
   python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline --no-profile > gpurun_out/r2_ncu_bench.log 2>&1

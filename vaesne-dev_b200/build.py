@@ -23,6 +23,16 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def source_hash():
+    """sha256 over the kernel sources (sorted csrc/*.cu, *.cuh and the C-ABI header): identifies a build independently of
+    link-time noise in the .so; profiles/r2_traffic.json is tied to it."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))) + [os.path.join(ROOT, "include", "vaesne_b200.h")]:
+        h.update(os.path.basename(f).encode()); h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
 def up_to_date():
     if not os.path.exists(OUT):
         return False
@@ -52,4 +62,6 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
+    if "--source-hash" in sys.argv:
+        print(source_hash()); sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

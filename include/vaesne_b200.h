@@ -84,6 +84,25 @@ int vaesne_attn_bwd(const float* q, long long ldq, const float* k, long long ldk
                     float* delta_ws /* [N,4,Lq] scratch */, float* dq, long long lddq, float* dk, long long lddk,
                     float* dv, long long lddv, void* stream);
 
+/* Key-block form (sequences beyond the 1024 tokens the tcgen05 kernels stage at once).  `flags` bit 0 marks a call as ONE
+ * KEY BLOCK of a longer attention: a (row, head) whose keys are all masked inside the block then yields O = 0, LSE = -inf and
+ * zero gradients instead of NaN.  Forward: call per key block, then vaesne_attn_combine (O = sum_b exp(LSE_b - LSE) O_b,
+ * LSE = logsumexp_b LSE_b; O_parts / LSE_parts are HOST arrays of nparts <= 8 device pointers to contiguous [N, Lb, 32] /
+ * [N, 4, Lb] blocks; the result goes to rows q0 .. q0 + Lb of O / LSE).  Backward: call per key block with the COMBINED O and
+ * LSE; dk / dv of the block are exact, the dq of the blocks add up.  Served by the tcgen05 kernels only (96 <= Lq, Lk <= 1024). */
+int vaesne_attn_fwd_ex(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
+                       int N, int Lq, int Lk, const unsigned char* mask, int mask_rows, int mask_len,
+                       float p_drop, const uint64_t* seed, uint32_t stream_id,
+                       float* O, long long ldo, float* LSE, int flags, void* stream);
+int vaesne_attn_bwd_ex(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
+                       int N, int Lq, int Lk, const unsigned char* mask, int mask_rows, int mask_len,
+                       float p_drop, const uint64_t* seed, uint32_t stream_id,
+                       const float* O, long long ldo, const float* LSE, const float* dO, long long lddo,
+                       float* delta_ws, float* dq, long long lddq, float* dk, long long lddk,
+                       float* dv, long long lddv, int flags, void* stream);
+int vaesne_attn_combine(const float* const* O_parts /* host */, const float* const* LSE_parts /* host */, int nparts, long long N, int Lb,
+                        int Lq, int q0, float* O, long long ldo, float* LSE, void* stream);
+
 /* ---- embeddings and data movement -----------------------------------------------------------
  * sincos_feat: out[t, 0:nf] = sin(x[t]*div), out[t, nf:2nf] = cos(x[t]*div)   util_layers.py:125-129,142-146
  * gather/scatter_rows: nn.Embedding(num_bands, 32) forward / weight gradient   PhotometricLayers.py:61,129

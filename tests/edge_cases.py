@@ -76,8 +76,11 @@ BOUNDARY_GPU = [
     dict(id="cross_300x90", N=2, Lq=300, Lk=90, mask=True, packed="q+kv"),     # too few keys for tcgen05, too many queries for one CTA per row: general
     dict(id="self_256", N=2, Lq=256, Lk=256, mask=True, packed="qkv"),
     dict(id="self_1024", N=1, Lq=1024, Lk=1024, mask=True, packed="qkv"),      # largest tcgen05 shape
-    dict(id="self_1025", N=1, Lq=1025, Lk=1025, mask=True, packed="qkv"),      # past it: general kernels
-    dict(id="cross_300x1030", N=1, Lq=300, Lk=1030, mask=True, packed="q+kv"),
+    dict(id="self_1025", N=1, Lq=1025, Lk=1025, mask=True, packed="qkv"),      # past it: 2 x 2 blocks of 513 / 512 tokens
+    dict(id="cross_300x1030", N=2, Lq=300, Lk=1030, mask=True, packed="q+kv"), # two key blocks, combined through their LSEs
+    dict(id="cross_1500x400_rowmod", N=4, Lq=1500, Lk=400, mask=True, mask_rows=2, packed="q+kv"),   # two query blocks
+    dict(id="self_2100_masklen", N=1, Lq=2100, Lk=2100, mask=True, mask_len=1500, packed="qkv"),      # 3 x 3 blocks; the last key block has no mask
+    dict(id="cross_50x1100", N=2, Lq=50, Lk=1100, mask=True, packed="q+kv"),   # too few queries for a tensor-core block: general kernels
 ]
 
 
@@ -118,7 +121,30 @@ def run_window_timing(device="cuda"):
         b.record(); torch.cuda.synchronize()
         return a.elapsed_time(b) / 5 / (N * 4.0 * L * L) * 1e6          # ns per score element, fwd + bwd
 
-    t = {L: per_element(L, max(256, int(4096 * (60.0 / L) ** 2))) for L in (60, 95, 96, 128, 200, 256)}
+    t = {L: per_element(L, max(256, int(4096 * (60.0 / L) ** 2))) for L in (60, 95, 96, 128, 200, 256, 1024, 1100, 2100)}
     assert t[95] < 2 * t[60] and t[96] < 2 * t[95] and t[95] < 2 * t[96], t
     assert t[128] < 1.2 * t[96] and t[200] < 1.2 * t[128] and t[256] < 1.2 * t[200], t
+    assert t[1100] < 2.5 * t[1024] and t[2100] < 2.5 * t[1024], t                 # beyond one block: tensor-core blocks (the general kernels are 8x)
     return t
+
+
+def run_blocked_dropout(device="cuda"):
+    """Sequences beyond one tensor-core block with dropout: every (query block, key block) draws its own mask stream; the
+    combined output stays an unbiased estimate (V = 1 -> O ~ 1), the same call is deterministic, and the backward regenerates
+    the forward's masks (dV = P_dropped^T dO: with dO = 1 the column sums of the dropped probabilities add up to Lq)."""
+    from VAESNe import _ops as P
+    g = torch.Generator().manual_seed(1)
+    Nb, L = 3, 1500
+    qk = (torch.randn(Nb, L, 64, generator=g) * 0.5).to(device)
+    v1 = torch.ones(Nb, L, 32, device=device)
+    seed = torch.tensor([424242], dtype=torch.int64, device=device)
+    drop = P.Drop(0.1, seed, 5)
+    O, LSE = P.attn_fwd(qk[..., :32], qk[..., 32:], v1, None, drop)
+    O2, _ = P.attn_fwd(qk[..., :32], qk[..., 32:], v1, None, drop)
+    assert torch.equal(O, O2)
+    assert abs(O.mean().item() - 1.0) < 5e-3 and O.std().item() > 1e-3, (O.mean().item(), O.std().item())
+    dq = torch.empty(Nb, L, 32, device=device); dk = torch.empty_like(dq); dv = torch.empty_like(dq)
+    P.attn_bwd(qk[..., :32], qk[..., 32:], v1, None, O, LSE, torch.ones_like(O), dq, dk, dv, drop)
+    assert torch.isfinite(dq).all() and torch.isfinite(dk).all() and torch.isfinite(dv).all()
+    # sum over keys of dV[:, key, c] = sum over (query, key) of dropped P = sum over queries of O (V = 1)
+    assert abs(dv[..., 0].sum().item() - O[..., 0].sum().item()) < 2e-3 * O[..., 0].sum().item()

@@ -21,6 +21,11 @@ def is_tc_shape(Lq, Lk, device):
     if not str(device).startswith("cuda") or os.environ.get("VAESNE_NO_TC"):
         return False
     lmin = int(os.environ.get("VAESNE_TC_MIN", "96"))
+    if Lq > 1024 or Lk > 1024:          # blocks of <= 1024 tokens (VAESNe/_ops.py): tensor-core blocks if every block is long enough
+        def blocks(L):
+            nb = -(-L // 1024); sz = -(-L // nb)
+            return [min(L, a + sz) - a for a in range(0, L, sz)]
+        return min(blocks(Lq) + blocks(Lk)) >= 96
     return lmin <= Lq <= 1024 and lmin <= Lk <= 1024
 
 

@@ -61,3 +61,8 @@ def test_no_cliff_between_the_attention_windows():
     import edge_cases
     t = edge_cases.run_window_timing("cuda")
     print("ns per score element (fwd + bwd):", {k: round(v, 4) for k, v in t.items()})
+
+
+def test_long_attention_blocks_with_dropout():
+    import edge_cases
+    edge_cases.run_blocked_dropout("cuda")

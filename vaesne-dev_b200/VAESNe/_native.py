@@ -28,6 +28,10 @@ _SIGS = {
     "vaesne_attn_fwd": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _i, _i, _f, _vp, _u32, _vp, _ll, _vp, _vp],
     "vaesne_attn_bwd": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _i, _i, _f, _vp, _u32, _vp, _ll, _vp, _vp, _ll,
                         _vp, _vp, _ll, _vp, _ll, _vp, _ll, _vp],
+    "vaesne_attn_fwd_ex": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _i, _i, _f, _vp, _u32, _vp, _ll, _vp, _i, _vp],
+    "vaesne_attn_bwd_ex": [_vp, _ll, _vp, _ll, _vp, _ll, _i, _i, _i, _vp, _i, _i, _f, _vp, _u32, _vp, _ll, _vp, _vp, _ll,
+                           _vp, _vp, _ll, _vp, _ll, _vp, _ll, _i, _vp],
+    "vaesne_attn_combine": [_vp, _vp, _i, _ll, _i, _i, _i, _vp, _ll, _vp, _vp],
     "vaesne_sincos_feat": [_vp, _ll, _vp, _i, _vp, _ll, _vp],
     "vaesne_gather_rows": [_vp, _ll, _vp, _i, _vp, _ll, _i, _vp],
     "vaesne_scatter_rows": [_vp, _ll, _vp, _ll, _vp, _i, _vp],

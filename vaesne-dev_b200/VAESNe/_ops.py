@@ -163,6 +163,102 @@ def _row_chunks(Nb: int, mask):
     return [(a, min(Nb, a + step)) for a in range(0, Nb, step)]
 
 
+# ---- sequences beyond the 1024 tokens the tcgen05 kernels stage at once: blocks of <= 1024 queries x <= 1024 keys -------------
+_TC_MAX, _TC_MIN = 1024, 96
+
+
+def _blocks(L: int):
+    nb = -(-L // _TC_MAX)
+    sz = -(-L // nb)
+    return [(a, min(L, a + sz)) for a in range(0, L, sz)]
+
+
+def _blocked(Lq: int, Lk: int, q) -> bool:
+    """Long attention runs as tensor-core blocks when it is longer than one block on either side (on a CUDA device, unless the
+    tcgen05 path is switched off); the key blocks of a query block are combined through their log-sum-exps."""
+    import os
+    if not q.is_cuda or N.is_emulated() or os.environ.get("VAESNE_NO_TC", "0") not in ("", "0"):
+        return False
+    return (Lq > _TC_MAX or Lk > _TC_MAX) and min(b - a for a, b in _blocks(Lq) + _blocks(Lk)) >= _TC_MIN
+
+
+def _slab(t, a, b):
+    """Contiguous copy of tokens a..b of a [N, L, C] view with unit inner stride (one strided block copy)."""
+    Nb, L, Cc = t.shape
+    out = torch.empty(Nb, b - a, Cc, device=t.device, dtype=torch.float32)
+    ld = t.stride(1)
+    N.check(N.lib().vaesne_copy3d(t.data_ptr() + 4 * a * ld, L * ld, ld, out.data_ptr(), (b - a) * Cc, Cc, Nb, b - a, Cc, 0, N.stream_of(t)))
+    return out
+
+
+def _unslab(src, dst, a, accumulate):
+    """dst[:, a:a+Lb, :] (+)= src for a [N, L, C] view dst with unit inner stride."""
+    Nb, Lb, Cc = src.shape
+    ld = dst.stride(1)
+    N.check(N.lib().vaesne_copy3d(src.data_ptr(), Lb * Cc, Cc, dst.data_ptr() + 4 * a * ld, dst.shape[1] * ld, ld, Nb, Lb, Cc, int(accumulate),
+                                  N.stream_of(src)))
+
+
+def _mask_block(mask, a, b):
+    if mask is None or a >= mask.shape[1]:
+        return None                                        # keys beyond mask_len are never masked
+    return mask[:, a:min(b, mask.shape[1])].contiguous()
+
+
+def _block_drop(drop: Drop, qi: int, ki: int) -> Drop:
+    return Drop(drop.p, drop.seed, drop.sid + 104729 * (qi * 8 + ki + 1)) if drop.seed is not None else drop
+
+
+def _attn_fwd_blocked(q, k, v, mask, drop):
+    Nb, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+    O = torch.empty(Nb, Lq, 32, device=q.device, dtype=torch.float32)
+    LSE = torch.empty(Nb, 4, Lq, device=q.device, dtype=torch.float32)
+    kb = _blocks(Lk)
+    if len(kb) > 8:
+        raise ValueError(f"attention over {Lk} keys: at most 8 blocks of {_TC_MAX}")
+    ks = [(_slab(k, a, b), _slab(v, a, b), _mask_block(mask, a, b)) for a, b in kb]
+    for qi, (q0, q1) in enumerate(_blocks(Lq)):
+        qs = _slab(q, q0, q1)
+        parts = []
+        for ki, (kc, vc, mc) in enumerate(ks):
+            Ob = torch.empty(Nb, q1 - q0, 32, device=q.device, dtype=torch.float32)
+            Lb = torch.empty(Nb, 4, q1 - q0, device=q.device, dtype=torch.float32)
+            mp, mrows, mlen = _mask_args(mc)
+            d = _block_drop(drop, qi, ki)
+            with _span("attn_fwd", Nb, q1 - q0, kc.shape[1]):
+                N.check(N.lib().vaesne_attn_fwd_ex(qs.data_ptr(), 32, kc.data_ptr(), 32, vc.data_ptr(), 32, Nb, q1 - q0, kc.shape[1], mp, mrows, mlen,
+                                                   d.p, N.ptr(d.seed), d.sid, Ob.data_ptr(), 32, Lb.data_ptr(), 1, N.stream_of(q)))
+            parts.append((Ob, Lb))
+        N.check(N.lib().vaesne_attn_combine(N.ptr_table([p[0] for p in parts]), N.ptr_table([p[1] for p in parts]), len(parts), Nb, q1 - q0, Lq, q0,
+                                            O.data_ptr(), 32, LSE.data_ptr(), N.stream_of(q)))
+    return O, LSE
+
+
+def _attn_bwd_blocked(q, k, v, mask, O, LSE, dO, dq, dk, dv, drop):
+    Nb, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
+    kb = _blocks(Lk)
+    ks = [(_slab(k, a, b), _slab(v, a, b), _mask_block(mask, a, b)) for a, b in kb]
+    for qi, (q0, q1) in enumerate(_blocks(Lq)):
+        Lb = q1 - q0
+        qs, Os, dOs = _slab(q, q0, q1), _slab(O, q0, q1), _slab(dO, q0, q1)
+        Ls = torch.empty(Nb, 4, Lb, device=q.device, dtype=torch.float32)          # LSE[:, :, q0:q1]
+        N.check(N.lib().vaesne_copy3d(LSE.data_ptr() + 4 * q0, Lq, Lq, Ls.data_ptr(), Lb, Lb, Nb * 4, 1, Lb, 0, N.stream_of(q)))
+        ws = torch.empty(Nb, 4, Lb, device=q.device, dtype=torch.float32)
+        for ki, ((k0, k1), (kc, vc, mc)) in enumerate(zip(kb, ks)):
+            dqb = torch.empty(Nb, Lb, 32, device=q.device, dtype=torch.float32)
+            dkb = torch.empty(Nb, k1 - k0, 32, device=q.device, dtype=torch.float32)
+            dvb = torch.empty(Nb, k1 - k0, 32, device=q.device, dtype=torch.float32)
+            mp, mrows, mlen = _mask_args(mc)
+            d = _block_drop(drop, qi, ki)
+            with _span("attn_bwd", Nb, Lb, k1 - k0):
+                N.check(N.lib().vaesne_attn_bwd_ex(qs.data_ptr(), 32, kc.data_ptr(), 32, vc.data_ptr(), 32, Nb, Lb, k1 - k0, mp, mrows, mlen,
+                                                   d.p, N.ptr(d.seed), d.sid, Os.data_ptr(), 32, Ls.data_ptr(), dOs.data_ptr(), 32, ws.data_ptr(),
+                                                   dqb.data_ptr(), 32, dkb.data_ptr(), 32, dvb.data_ptr(), 32, 1, N.stream_of(q)))
+            _unslab(dqb, dq, q0, accumulate=ki > 0)
+            _unslab(dkb, dk, k0, accumulate=qi > 0)
+            _unslab(dvb, dv, k0, accumulate=qi > 0)
+
+
 def attn_fwd(q, k, v, mask, drop: Drop = NO_DROP):
     """q [N,Lq,32] view, k/v [N,Lk,32] views -> O [N,Lq,32], LSE [N,4,Lq]."""
     Nb, Lq, Lk = q.shape[0], q.shape[1], k.shape[1]
@@ -171,10 +267,12 @@ def attn_fwd(q, k, v, mask, drop: Drop = NO_DROP):
         outs = [attn_fwd(q[a:b], k[a:b], v[a:b], mask, Drop(drop.p, drop.seed, drop.sid + 7919 * (i + 1)) if drop.seed is not None else drop)
                 for i, (a, b) in enumerate(chunks)]
         return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
-    O = torch.empty(Nb, Lq, 32, device=q.device, dtype=torch.float32)
-    LSE = torch.empty(Nb, 4, Lq, device=q.device, dtype=torch.float32)
     qp, ldq = _attn_operand(q, "q"); kp, ldk = _attn_operand(k, "k"); vp, ldv = _attn_operand(v, "v")
     mp, mrows, mlen = _mask_args(mask)
+    if _blocked(Lq, Lk, q):
+        return _attn_fwd_blocked(q, k, v, mask, drop)
+    O = torch.empty(Nb, Lq, 32, device=q.device, dtype=torch.float32)
+    LSE = torch.empty(Nb, 4, Lq, device=q.device, dtype=torch.float32)
     with _span("attn_fwd", Nb, Lq, Lk):
         N.check(N.lib().vaesne_attn_fwd(qp, ldq, kp, ldk, vp, ldv, Nb, Lq, Lk, mp, mrows, mlen, drop.p, N.ptr(drop.seed), drop.sid,
                                         O.data_ptr(), 32, LSE.data_ptr(), N.stream_of(q)))
@@ -194,6 +292,9 @@ def attn_bwd(q, k, v, mask, O, LSE, dO, dq, dk, dv, drop: Drop = NO_DROP):
     dqp, lddq = _attn_operand(dq, "dq"); dkp, lddk = _attn_operand(dk, "dk"); dvp, lddv = _attn_operand(dv, "dv")
     dop, lddo = _attn_operand(dO, "dO")
     mp, mrows, mlen = _mask_args(mask)
+    if _blocked(Lq, Lk, q):
+        _attn_operand(O, "O")
+        return _attn_bwd_blocked(q, k, v, mask, O, LSE, dO, dq, dk, dv, drop)
     ws = torch.empty(Nb, 4, Lq, device=q.device, dtype=torch.float32)
     with _span("attn_bwd", Nb, Lq, Lk):
         N.check(N.lib().vaesne_attn_bwd(qp, ldq, kp, ldk, vp, ldv, Nb, Lq, Lk, mp, mrows, mlen, drop.p, N.ptr(drop.seed), drop.sid,

@@ -289,16 +289,21 @@ static int check_common(const AttnArgs& a, const char* what) {
 
 using namespace vaesne;
 
-extern "C" int vaesne_attn_fwd(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
+extern "C" int vaesne_attn_fwd_ex(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
                                int N, int Lq, int Lk, const unsigned char* mask, int mask_rows, int mask_len,
                                float p_drop, const uint64_t* seed, uint32_t stream_id,
-                               float* O, long long ldo, float* LSE, void* stream) {
+                               float* O, long long ldo, float* LSE, int flags, void* stream) {
   AttnArgs a{};
   a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.N = N; a.Lq = Lq; a.Lk = Lk;
   a.mask = mask; a.mask_rows = mask_rows; a.mask_len = mask_len; a.p_drop = p_drop; a.seed = seed; a.stream_id = stream_id;
-  a.O = O; a.ldo = ldo; a.LSE = LSE;
+  a.O = O; a.ldo = ldo; a.LSE = LSE; a.flags = flags;
   if (N == 0) return V_OK;                  // an empty batch has no buffers: torch hands out null pointers for it
   int rc = check_common(a, "attn_fwd"); if (rc) return rc;
+#ifndef VAESNE_EMU
+  V_REQUIRE(flags == 0 || attn_tc_eligible(a), V_EUNSUPPORTED, "attn_fwd: key-block calls (flags) are served by the tcgen05 kernels only (96 <= Lq, Lk <= 1024)");
+#else
+  V_REQUIRE(flags == 0, V_EUNSUPPORTED, "attn_fwd: key-block calls (flags) are served by the tcgen05 kernels only");
+#endif
   V_REQUIRE(O && LSE, V_ENULL, "attn_fwd: null O/LSE");
   cudaStream_t st = (cudaStream_t)stream;
 #ifndef VAESNE_EMU
@@ -313,19 +318,31 @@ extern "C" int vaesne_attn_fwd(const float* q, long long ldq, const float* k, lo
   return check_launch("attn_fwd");
 }
 
-extern "C" int vaesne_attn_bwd(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
+extern "C" int vaesne_attn_fwd(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
+                               int N, int Lq, int Lk, const unsigned char* mask, int mask_rows, int mask_len,
+                               float p_drop, const uint64_t* seed, uint32_t stream_id,
+                               float* O, long long ldo, float* LSE, void* stream) {
+  return vaesne_attn_fwd_ex(q, ldq, k, ldk, v, ldv, N, Lq, Lk, mask, mask_rows, mask_len, p_drop, seed, stream_id, O, ldo, LSE, 0, stream);
+}
+
+extern "C" int vaesne_attn_bwd_ex(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
                                int N, int Lq, int Lk, const unsigned char* mask, int mask_rows, int mask_len,
                                float p_drop, const uint64_t* seed, uint32_t stream_id,
                                const float* O, long long ldo, const float* LSE, const float* dO, long long lddo,
                                float* delta_ws, float* dq, long long lddq, float* dk, long long lddk, float* dv, long long lddv,
-                               void* stream) {
+                               int flags, void* stream) {
   AttnArgs a{};
   a.q = q; a.ldq = ldq; a.k = k; a.ldk = ldk; a.v = v; a.ldv = ldv; a.N = N; a.Lq = Lq; a.Lk = Lk;
   a.mask = mask; a.mask_rows = mask_rows; a.mask_len = mask_len; a.p_drop = p_drop; a.seed = seed; a.stream_id = stream_id;
   a.O = const_cast<float*>(O); a.ldo = ldo; a.LSE = const_cast<float*>(LSE); a.dO = dO; a.lddo = lddo; a.delta = delta_ws;
-  a.dq = dq; a.lddq = lddq; a.dk = dk; a.lddk = lddk; a.dv = dv; a.lddv = lddv;
+  a.dq = dq; a.lddq = lddq; a.dk = dk; a.lddk = lddk; a.dv = dv; a.lddv = lddv; a.flags = flags;
   if (N == 0) return V_OK;
   int rc = check_common(a, "attn_bwd"); if (rc) return rc;
+#ifndef VAESNE_EMU
+  V_REQUIRE(flags == 0 || attn_tc_eligible(a), V_EUNSUPPORTED, "attn_bwd: key-block calls (flags) are served by the tcgen05 kernels only (96 <= Lq, Lk <= 1024)");
+#else
+  V_REQUIRE(flags == 0, V_EUNSUPPORTED, "attn_bwd: key-block calls (flags) are served by the tcgen05 kernels only");
+#endif
   V_REQUIRE(O && LSE && dO && delta_ws && dq && dk && dv, V_ENULL, "attn_bwd: null argument");
   cudaStream_t st = (cudaStream_t)stream;
 #ifndef VAESNE_EMU
@@ -340,4 +357,14 @@ extern "C" int vaesne_attn_bwd(const float* q, long long ldq, const float* k, lo
   if (Lk <= 32) { dim3 grid((Lk + 3) / 4, kH, N); auto kf = attn_bwd_dkv_kernel<32>; VLAUNCH(kf, grid, block, 0, st, a); }
   else { dim3 grid((Lk + AT - 1) / AT, kH, N); auto kf = attn_bwd_dkv_kernel<1>; VLAUNCH(kf, grid, block, 0, st, a); }
   return check_launch("attn_bwd_dkv");
+}
+
+extern "C" int vaesne_attn_bwd(const float* q, long long ldq, const float* k, long long ldk, const float* v, long long ldv,
+                               int N, int Lq, int Lk, const unsigned char* mask, int mask_rows, int mask_len,
+                               float p_drop, const uint64_t* seed, uint32_t stream_id,
+                               const float* O, long long ldo, const float* LSE, const float* dO, long long lddo,
+                               float* delta_ws, float* dq, long long lddq, float* dk, long long lddk, float* dv, long long lddv,
+                               void* stream) {
+  return vaesne_attn_bwd_ex(q, ldq, k, ldk, v, ldv, N, Lq, Lk, mask, mask_rows, mask_len, p_drop, seed, stream_id, O, ldo, LSE, dO, lddo,
+                            delta_ws, dq, lddq, dk, lddk, dv, lddv, 0, stream);
 }

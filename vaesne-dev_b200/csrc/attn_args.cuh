@@ -19,7 +19,10 @@ struct AttnArgs {
   float* dq; long long lddq;
   float* dk; long long lddk;
   float* dv; long long lddv;
+  int flags;                  // bit 0: this call is one KEY BLOCK of a longer attention — a (row, head) whose keys are all
+                              // masked inside the block contributes nothing (O = 0, LSE = -inf, zero gradients) instead of NaN
 };
+constexpr int kAttnPartial = 1;
 
 #ifndef VAESNE_EMU
 // tcgen05 path (attn_tc.cu): returns V_OK after enqueueing, or a negative code. `eligible` says whether the

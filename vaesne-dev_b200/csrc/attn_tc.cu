@@ -489,7 +489,7 @@ __global__ void __launch_bounds__(NWG * 128 + 128, NWG == 4 ? 1 : 2) attn_tc_fwd
       if (T == 0) {       // every key masked: softmax of an empty set (the reference yields NaN)
         if (valid) {
           float* op = a.O + ((long long)n * a.Lq + i) * a.ldo + h * 8;
-          for (int c = 0; c < 8; ++c) op[c] = __int_as_float(0x7fc00000);
+          for (int c = 0; c < 8; ++c) op[c] = (a.flags & kAttnPartial) ? 0.f : __int_as_float(0x7fc00000);
           a.LSE[(long long)nh * a.Lq + i] = -INFINITY;
         }
         continue;
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
     float delta[RPT];
     float gm = 0.f;
     uint32_t qmb = 0u;
-    const float init = LkC > 0 ? 0.f : __int_as_float(0x7fc00000);
+    const float init = (LkC > 0 || (a.flags & kAttnPartial)) ? 0.f : __int_as_float(0x7fc00000);
 #pragma unroll
     for (int u = 0; u < RPT; ++u) {
       const int i = tid + u * NTHREADS;
@@ -1103,7 +1103,7 @@ __global__ void __launch_bounds__(B1_THREADS, 2) attn_tc_bwd1_kernel(AttnArgs a)
   __syncthreads();
   // maxima and delta = rowsum(dO * O) from the staged rows; per-query tables (delta is rescaled once the normalisers are known)
   {
-    const float init = LkC > 0 ? 0.f : __int_as_float(0x7fc00000);
+    const float init = (LkC > 0 || (a.flags & kAttnPartial)) ? 0.f : __int_as_float(0x7fc00000);
 #pragma unroll
     for (int u = 0; u < B1_RPT; ++u) {
       const int i = tid + u * B1_THREADS;

@@ -162,8 +162,49 @@ __global__ void augment_kernel(const float* x, const unsigned char* mask, long l
   }
 }
 
+// ---- long attention as key blocks: O = sum_b exp(LSE_b - LSE) O_b, LSE = logsumexp_b LSE_b ---------------------------------
+struct CombineParts { const float* O[8]; const float* L[8]; };
+__global__ void attn_combine_kernel(CombineParts p, int nparts, long long N, int Lb, int Lq, int q0, float* O, long long ldo, float* LSE) {
+  const long long total = N * Lb * 4;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int h = (int)(t & 3);
+    const long long ni = t >> 2;
+    const long long n = ni / Lb; const int i = (int)(ni - n * Lb);
+    float l[8], m = -INFINITY;
+    for (int b = 0; b < nparts; ++b) { l[b] = p.L[b][(n * 4 + h) * Lb + i]; m = fmaxf(m, l[b]); }
+    float sum = 0.f, acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+    for (int b = 0; b < nparts; ++b) {
+      if (l[b] == -INFINITY) continue;                       // a block with every key masked contributes nothing
+      const float w = expf(l[b] - m);
+      sum += w;
+      const float* o = p.O[b] + (n * Lb + i) * 32 + h * 8;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) acc[c] = fmaf(w, o[c], acc[c]);
+    }
+    float* dst = O + (n * Lq + q0 + i) * ldo + h * 8;
+    const float inv = 1.f / sum;                              // every block empty: 0 / 0 = NaN, as the unblocked kernels give
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dst[c] = acc[c] * inv;
+    LSE[(n * 4 + h) * Lq + q0 + i] = m + logf(sum);
+  }
+}
+
 }  // namespace vaesne
 using namespace vaesne;
+
+extern "C" int vaesne_attn_combine(const float* const* O_parts, const float* const* LSE_parts, int nparts, long long N, int Lb, int Lq, int q0,
+                                   float* O, long long ldo, float* LSE, void* stream) {
+  V_REQUIRE(O_parts && LSE_parts && O && LSE, V_ENULL, "attn_combine: null argument");
+  V_REQUIRE(nparts >= 1 && nparts <= 8, V_EUNSUPPORTED, "attn_combine: 1..8 key blocks (got %d)", nparts);
+  if (N * Lb == 0) return V_OK;
+  CombineParts p{};
+  for (int b = 0; b < nparts; ++b) { p.O[b] = O_parts[b]; p.L[b] = LSE_parts[b]; }
+  auto k = attn_combine_kernel;
+  VLAUNCH(k, dim3(ew_grid2(N * Lb * 4, 256)), dim3(256), 0, (cudaStream_t)stream, p, nparts, N, Lb, Lq, q0, O, ldo, LSE);
+  return check_launch("attn_combine");
+}
 
 extern "C" int vaesne_l2norm_fwd(const float* x, int B, int P, float eps, float* y, float* inv_norm, void* stream) {
   V_REQUIRE(x && y && inv_norm, V_ENULL, "l2norm_fwd: null argument");

@@ -94,3 +94,14 @@ def test_mixed_prior_posterior_families_use_the_generic_objective(emu):
     torch.manual_seed(5); a = elbo(m2, x, K=2)
     torch.manual_seed(5); b = elbo(m2, x, K=2, debug=True)
     assert abs(a.item() - b.item()) < 1e-4 * abs(b.item())
+
+
+def test_first_decoder_block_with_shared_projection_only(emu):
+    """Under dropout a decoder's first block shares only the q|k|v projection across the K*M replicas (the attention masks are
+    per replica); that form is forced here at dropout 0 and must reproduce the live-reference golden like the fully shared one."""
+    from VAESNe import _stacks
+    _stacks._INPROJ_ONLY = True
+    try:
+        MC.run_mm_case("mm_normal", "cpu")
+    finally:
+        _stacks._INPROJ_ONLY = False

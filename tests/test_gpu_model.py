@@ -57,3 +57,12 @@ def test_reference_checkpoint_loads():
     """torch.load of a whole-module pickle written by the reference (cannon/test_photospectra.py:153)."""
     import pickle_case
     pickle_case.run("cuda")
+
+
+def test_first_decoder_block_with_shared_projection_only():
+    from VAESNe import _stacks
+    _stacks._INPROJ_ONLY = True
+    try:
+        MC.run_mm_case("mm_goldstein", "cuda")
+    finally:
+        _stacks._INPROJ_ONLY = False

@@ -267,6 +267,7 @@ def head(tape: Tape, pv: PView, prefix: str, X, Xadd):
 # TransformerBlock (util_layers.py:285-309)
 # ------------------------------------------------------------------------------------------------
 _NO_SHARED = os.environ.get("VAESNE_NO_SHARED_LAYER0", "0") not in ("", "0")      # A/B switch for the measurement in bench.py
+_INPROJ_ONLY = False      # tests: take the "shared projection, per-replica attention" form of a decoder's first block at dropout 0 too
 
 
 def block_forward(tape: Tape, pv: PView, pre: str, x, ctx, mask, ctx_mask, Nb: int, Lq: int, Lc: int, shared=None):
@@ -280,7 +281,7 @@ def block_forward(tape: Tape, pv: PView, pre: str, x, ctx, mask, ctx_mask, Nb: i
     reference draws an independent dropout mask per replica)."""
     sa, ca = _j(pre, "self_attn"), _j(pre, "cross_attn")
     pre = pre + "." if pre else ""
-    if shared is not None and tape.drop_p == 0.0 and shared[1] > 1 and not _NO_SHARED:
+    if shared is not None and tape.drop_p == 0.0 and shared[1] > 1 and not _NO_SHARED and not _INPROJ_ONLY:
         xs, copies = shared
         Ns = Nb // copies
         qkv = t_lin(tape, pv, xs, sa + ".in_proj_weight", sa + ".in_proj_bias")
@@ -289,7 +290,16 @@ def block_forward(tape: Tape, pv: PView, pre: str, x, ctx, mask, ctx_mask, Nb: i
         x1s = t_lin(tape, pv, a.view(Ns * Lq, 32), sa + ".out_proj.weight", sa + ".out_proj.bias", R=xs, ln=pre + "layernorm1", dropout=True)
         x1 = t_expand(tape, x1s.view(Ns, Lq * 32), copies).view(Nb * Lq, 32)
     else:
-        qkv = t_lin(tape, pv, x, sa + ".in_proj_weight", sa + ".in_proj_bias")
+        if shared is not None and shared[1] > 1 and not _NO_SHARED:
+            # a decoder's first block under dropout: the replicas draw independent masks, but the block INPUT is still `copies`
+            # replicas of xs, so q|k|v are projected once per object and replicated (same values bit for bit) — and in the
+            # backward the replicas' d(q|k|v) are summed first, so the projection's weight / input gradients run on 1/copies
+            # of the tokens (the packed 32 -> 96 backward is the most expensive linear call of the step)
+            xs, copies = shared
+            qkv_s = t_lin(tape, pv, xs, sa + ".in_proj_weight", sa + ".in_proj_bias")
+            qkv = t_expand(tape, qkv_s.view(Nb // copies, Lq * 96), copies).view(Nb * Lq, 96)
+        else:
+            qkv = t_lin(tape, pv, x, sa + ".in_proj_weight", sa + ".in_proj_bias")
         q3 = qkv.view(Nb, Lq, 96)
         a = t_attn(tape, q3, q3[..., 0:32], q3, q3[..., 32:64], q3[..., 64:96], mask)
         x1 = t_lin(tape, pv, a.view(Nb * Lq, 32), sa + ".out_proj.weight", sa + ".out_proj.bias", R=x, ln=pre + "layernorm1", dropout=True)

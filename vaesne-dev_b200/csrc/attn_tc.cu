@@ -1004,7 +1004,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) attn_tc_bwd_kernel(AttnArgs a) {
 // =================================================================================================
 constexpr int B1_THREADS = 160;
 constexpr int B1_RPT = (MAXL + B1_THREADS - 1) / B1_THREADS;      // 7 rows per thread and pass
-constexpr size_t BWD1_SMEM = (size_t)2 * TILE_F * 4 + DS_BYTES + KB_BYTES + 2 * MAXL * 4 + MAXL * 2 + MAXL * 2 + 32 * 4 + 36 * 4 + 8 * 8 + 16 + 8 * 4;
+// TMEM columns of this kernel: IN 0..127 (S^T | T^T), OUT 128..191 (P^T | dS^T fp16 pairs), dK 192..207, dV 208..223, dQ 224..239
+// (each hi | lo: every second product takes its shared-memory operand as fp16 [hi | lo]), X 240..255 (K and V rows [hi | lo]).
+// X needs no "[hi | 0]" copies: the low-order first-product MMA multiplies [Khi | Klo] by [Qlo | Qlo], whose extra Klo*Qlo
+// term is the genuine fourth term of the exact product.
+constexpr int E_DK = 192, E_DV = 208, E_DQ = 224, E_X = 240;
+constexpr size_t BWD1_SMEM = (size_t)2 * TILE_F * 4 + DS_BYTES + 2 * KB_BYTES + 2 * MAXL * 4 + MAXL * 2 + MAXL * 2 + 32 * 4 + 36 * 4 + 8 * 8 + 16 + 8 * 4;
 static_assert(2 * (BWD1_SMEM + 1024) <= 233472, "two one-warpgroup backward CTAs must fit one SM");
 
 __global__ void __launch_bounds__(B1_THREADS, 2) attn_tc_bwd1_kernel(AttnArgs a) {
@@ -1014,10 +1019,10 @@ __global__ void __launch_bounds__(B1_THREADS, 2) attn_tc_bwd1_kernel(AttnArgs a)
   __half* Q2h = reinterpret_cast<__half*>(fb);                       // Q  hi | lo  ([d][query] fp16, 16 KB each)
   __half* G2h = reinterpret_cast<__half*>(fb + TILE_F);              // dO hi | lo
   unsigned char* const dsb = tc_smem_raw + (size_t)2 * TILE_F * 4;   // dS^T of a tile pair (A of the dQ product)
-  unsigned char* const kbb = dsb + DS_BYTES;                         // K rows (B of the dQ product)
+  unsigned char* const kbb = dsb + DS_BYTES;                         // K rows, fp16 hi then lo (B of the dQ product)
   uint16_t* w16;                                                     // [MAXL] per-query dropout halves a_i
   {
-    float* f = reinterpret_cast<float*>(kbb + KB_BYTES);
+    float* f = reinterpret_cast<float*>(kbb + 2 * KB_BYTES);
     for (int i = 0; i < 6; ++i) s.arr[i] = nullptr;
     s.pad = nullptr; s.w0 = nullptr;
     s.f0 = f; f += MAXL; s.f1 = f; f += MAXL;
@@ -1159,21 +1164,20 @@ __global__ void __launch_bounds__(B1_THREADS, 2) attn_tc_bwd1_kernel(AttnArgs a)
   const uint32_t tb = *s.tmem;
   uint64_t* const bars = s.bars;
   uint64_t* const bdq = s.bars + 6;
-  // TMEM: IN = S^T (64) | T^T (64) ; OUT = P^T (32) | dS^T (32) fp16 pairs ; ACC = dK hi|lo (16) | dV (8) | dQ tile (8) ; X = Khi | Klo | Vhi | Vlo
 
   if (warp == 4) {
-    const uint32_t idK = idesc_f16(128, 16), idV = idesc_f16(128, 8), idQ = idesc_f16_mn(128, 8, true, true);
+    const uint32_t idK = idesc_f16(128, 16), idQ = idesc_f16_mn(128, 16, true, true);
     const uint32_t aQ2 = smem_u32(Q2h), aG2 = smem_u32(G2h);
     const uint32_t aDS = smem_u32(dsb), aKB = smem_u32(kbb);
     const uint32_t tw = tb;
     const uint32_t idF = idesc_f16_mn(128, BK, false, true);
     auto issue_st = [&](int j) {
-      const uint32_t d = tw + C_IN, x = tw + C_X;
+      const uint32_t d = tw + C_IN, x = tw + E_X;
       const uint32_t off = (uint32_t)j * (BK / 8) * 128;
       mma_ts_f16(d, x, smem_desc(aQ2 + off, 0, 128), idF, 0);                          // [Khi | Klo] x [Qhi | Qhi]
-      mma_ts_f16(d, x + 8, smem_desc(aQ2 + HALF_ARR * 2 + off, 0, 128), idF, 1);       // [Khi | 0  ] x [Qlo | Qlo]
-      mma_ts_f16(d + 64, x + 16, smem_desc(aG2 + off, 0, 128), idF, 0);                // [Vhi | Vlo] x [Ghi | Ghi]
-      mma_ts_f16(d + 64, x + 24, smem_desc(aG2 + HALF_ARR * 2 + off, 0, 128), idF, 1); // [Vhi | 0  ] x [Glo | Glo]
+      mma_ts_f16(d, x, smem_desc(aQ2 + HALF_ARR * 2 + off, 0, 128), idF, 1);           // [Khi | Klo] x [Qlo | Qlo]
+      mma_ts_f16(d + 64, x + 8, smem_desc(aG2 + off, 0, 128), idF, 0);                 // [Vhi | Vlo] x [Ghi | Ghi]
+      mma_ts_f16(d + 64, x + 8, smem_desc(aG2 + HALF_ARR * 2 + off, 0, 128), idF, 1);  // [Vhi | Vlo] x [Glo | Glo]
     };
     uint32_t cF = 0, cP = 0;
     for (int kt = 0; kt < nKT; ++kt) {
@@ -1194,17 +1198,17 @@ __global__ void __launch_bounds__(B1_THREADS, 2) attn_tc_bwd1_kernel(AttnArgs a)
         fence_after();
         if (elect_one()) {
           const int nsteps = (min(BK, a.Lq - j * BK) + 15) >> 4;
-          const uint32_t dK = tw + C_ACC, dV = dK + 16;
+          const uint32_t dK = tw + E_DK, dV = tw + E_DV;
           for (int t = 0; t < nsteps; ++t) {
             const uint32_t off = (uint32_t)(j * (BK / 16) + t) * 256;
             const uint32_t acc = (j > 0 || t > 0) ? 1u : 0u;
-            mma_ts_f16(dV, tw + C_OUT + (uint32_t)t * 8, smem_desc(aG2 + off, 128, 256), idV, acc);                   // P^T dO
+            mma_ts_f16(dV, tw + C_OUT + (uint32_t)t * 8, smem_desc(aG2 + off, 128, HALF_ARR * 2), idK, acc);          // P^T [dOhi | dOlo]
             mma_ts_f16(dK, tw + C_OUT + 32 + (uint32_t)t * 8, smem_desc(aQ2 + off, 128, HALF_ARR * 2), idK, acc);     // dS^T [Qhi | Qlo]
           }
           if (!last) commit(&bars[B_OF]);
           if ((j & 1) || last) {                    // dS K -> dQ of the tile pair (M = 128: two 64-query tiles)
             for (int t = 0; t < ksteps; ++t)
-              mma_ss_f16(tw + C_DQ, smem_desc(aDS + t * 256, 128, 2048), smem_desc(aKB + t * 256, 128, 2048), idQ, t > 0 ? 1u : 0u);
+              mma_ss_f16(tw + E_DQ, smem_desc(aDS + t * 256, 128, 2048), smem_desc(aKB + t * 256, 128, 2048), idQ, t > 0 ? 1u : 0u);   // dS [Khi | Klo]
             commit(last ? &bars[B_O] : bdq);
           }
         }
@@ -1214,7 +1218,7 @@ __global__ void __launch_bounds__(B1_THREADS, 2) attn_tc_bwd1_kernel(AttnArgs a)
   } else {
     const int r = tid;
     const uint32_t tw = tb + ((uint32_t)(warp * 32) << 16);
-    const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tA = tw + C_ACC, tX = tw + C_X;
+    const uint32_t tIN = tw + C_IN, tOUT = tw + C_OUT, tX = tw + E_X;
     unsigned char* const ds_row = dsb + (r & 7) * 16 + (r >> 3) * 128;      // this key's 16-byte slot in each query group
     unsigned char* const kb_row = kbb + (r & 7) * 16 + (r >> 3) * 128;
     const float ds_inv = 1.f / (cs_scale * v_norm);     // undoes the scale dS^T (and what is contracted with it) carries
@@ -1223,13 +1227,13 @@ __global__ void __launch_bounds__(B1_THREADS, 2) attn_tc_bwd1_kernel(AttnArgs a)
     uint32_t cdq = 0;
     // dQ contribution of the tile pair starting at query tile jq: accumulator row m (query jq*64 + m) sits in lane m
     auto drain_dq = [&](int jq, int nrows) {
-      uint32_t v[8];
-      tmem_ld8(tw + C_DQ, v); tmem_wait_ld();
+      uint32_t v[16];
+      tmem_ld16(tw + E_DQ, v); tmem_wait_ld();
       const int i = jq * BK + r;
       if (r < nrows && i < a.Lq) {
         float o[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) o[c] = __uint_as_float(v[c]) * dq_scale;
+        for (int c = 0; c < 8; ++c) o[c] = (__uint_as_float(v[c]) + __uint_as_float(v[8 + c])) * dq_scale;
         red_add8(a.dq + ((long long)n * a.Lq + i) * a.lddq + h * 8, o);
       }
     };
@@ -1258,9 +1262,9 @@ __global__ void __launch_bounds__(B1_THREADS, 2) attn_tc_bwd1_kernel(AttnArgs a)
       const float inv_qk = 1.f / (q_norm * k_norm);
       const f32x2 iqk2 = pk2(inv_qk, inv_qk);
       dq_scale = kScale * ds_inv / k_norm;
-      *reinterpret_cast<uint4*>(kb_row) = make_uint4(pack_h2(k[0], k[1]), pack_h2(k[2], k[3]), pack_h2(k[4], k[5]), pack_h2(k[6], k[7]));
-      {                // A operands: columns 0-3 = hi pairs, 4-7 = lo pairs (K index 0-7 hi, 8-15 lo); second operand: [hi | 0]
-        uint32_t xa[8], xb[8];
+      {                // A operands: columns 0-3 = hi pairs, 4-7 = lo pairs (K index 0-7 hi, 8-15 lo); the K rows also go to
+                       // shared memory as the [hi | lo] B operand of the dQ product
+        uint32_t xa[8];
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
           const float* src = pass ? v : k;
@@ -1270,9 +1274,12 @@ __global__ void __launch_bounds__(B1_THREADS, 2) attn_tc_bwd1_kernel(AttnArgs a)
             const float2 hf = __half22float2(h2);
             xa[c] = *reinterpret_cast<const uint32_t*>(&h2);
             xa[4 + c] = pack_h2(src[2 * c] - hf.x, src[2 * c + 1] - hf.y);
-            xb[c] = xa[c]; xb[4 + c] = 0u;
           }
-          tmem_st8(tX + pass * 16, xa); tmem_st8(tX + pass * 16 + 8, xb);
+          tmem_st8(tX + pass * 8, xa);
+          if (pass == 0) {
+            *reinterpret_cast<uint4*>(kb_row) = make_uint4(xa[0], xa[1], xa[2], xa[3]);
+            *reinterpret_cast<uint4*>(kb_row + KB_BYTES) = make_uint4(xa[4], xa[5], xa[6], xa[7]);
+          }
         }
       }
       fence_async_smem();
@@ -1342,8 +1349,8 @@ __global__ void __launch_bounds__(B1_THREADS, 2) attn_tc_bwd1_kernel(AttnArgs a)
       mbar_wait(&bars[B_O], kt & 1);
       fence_after();
       if (NQ & 1) drain_dq(NQ - 1, BK); else drain_dq(NQ - 2, 2 * BK);     // an odd last tile sits alone in rows 0..63
-      uint32_t o[24];
-      tmem_ld16(tA, o); tmem_ld8(tA + 16, o + 16); tmem_wait_ld();
+      uint32_t o[32];
+      tmem_ld32(tw + E_DK, o); tmem_wait_ld();                 // dK hi | lo | dV hi | lo
       if (valid) {
         float dk[8], dv[8];
         const float ck = kLn2 * ds_inv / q_norm;               // hi + lo parts; Q carried log2(e) and its normaliser
@@ -1351,7 +1358,7 @@ __global__ void __launch_bounds__(B1_THREADS, 2) attn_tc_bwd1_kernel(AttnArgs a)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           dk[c] = (__uint_as_float(o[c]) + __uint_as_float(o[8 + c])) * ck;
-          dv[c] = __uint_as_float(o[16 + c]) * cv;
+          dv[c] = (__uint_as_float(o[16 + c]) + __uint_as_float(o[24 + c])) * cv;
         }
         st8g(a.dk + ((long long)n * a.Lk + jk) * a.lddk + h * 8, dk);
         st8g(a.dv + ((long long)n * a.Lk + jk) * a.lddv + h * 8, dv);

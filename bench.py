@@ -276,21 +276,27 @@ def run_batch_sweep(dev, headline):
     return out
 
 
-def run_dp_small_batch(model, opt, loss_fn, dev, rank, world, timed, B=16, steps=20):
-    """samples/s at per-GPU batch 16 (cannon/ZTF_photospect.py:77), eager and graph-replayed; max over ranks like the headline."""
+def run_dp_small_batch(model, opt, loss_fn, dev, rank, world, timed):
+    """SURVEY 8d's per-GPU batch sweep under data parallelism: 16 (cannon/ZTF_photospect.py:77, launch-bound; eager and replayed
+    as one CUDA graph with the NCCL bucket all-reduces captured inside), 256 and 1024; max over ranks like the headline."""
     from VAESNe.training_util import training_step
-    batches = [_to_dev(synth_batch(B, 7000 + 10 * rank + i), dev, True) for i in range(2)]
-    out = {"per_gpu_batch": B}
-    for tag, graph in (("samples_per_s", False), ("samples_per_s_cuda_graph", True)):
-        def run(n, graph=graph):
-            training_step(model, opt, [batches[i % 2] for i in range(n)], loss_fn, multimodal=True, cuda_graph=graph)
-        try:
-            run(4)
-            ms = timed(run, steps)
-            out[tag] = world * B * steps / (ms * 1e-3)
-        except Exception as e:      # noqa: BLE001
-            out[tag] = None
-            out[tag + "_error"] = repr(e)[:200]
+    out = []
+    for B, steps in ((16, 20), (256, 5), (1024, 3)):
+        batches = [_to_dev(synth_batch(B, 7000 + 10 * rank + i), dev, True) for i in range(2)]
+        rec = {"per_gpu_batch": B, "global_batch": B * world}
+        for tag, graph in (("samples_per_s", False),) + ((("samples_per_s_cuda_graph", True),) if B == 16 else ()):
+            def run(n, graph=graph):
+                training_step(model, opt, [batches[i % 2] for i in range(n)], loss_fn, multimodal=True, cuda_graph=graph)
+            try:
+                run(4 if B == 16 else 2)
+                ms = timed(run, steps)
+                rec[tag] = world * B * steps / (ms * 1e-3)
+            except Exception as e:      # noqa: BLE001
+                rec[tag] = None
+                rec[tag + "_error"] = repr(e)[:200]
+        out.append(rec)
+        del batches
+        torch.cuda.empty_cache()
     return out
 
 

@@ -26,6 +26,7 @@
 #include "tc_common.cuh"
 #include <stdlib.h>
 #include <stdio.h>
+#include <cuda_bf16.h>
 #include <cuda.h>          // CUtensorMap (the encoder itself is fetched through the runtime: no libcuda link)
 
 namespace vaesne {
@@ -613,6 +614,290 @@ __global__ void __launch_bounds__(BT, 2) lin_tc_bwd_kernel(LinBwd a) {
   if (warp == 0) { fence_after(); tmem_dealloc<COLS>(tb); }
 }
 
+// =================================================================================================
+// backward, pipelined variant (N = K = 32): one persistent CTA per SM, warp-specialised
+// =================================================================================================
+// warps 0-3 = row group 0, warps 4-7 = row group 1 (one thread per token row, a whole 128-token tile per group, the two
+// groups half a tile out of phase), warp 8 = TMA producer, warp 9 = MMA issuer.  Everything that crosses HBM moves through
+// the TMA unit: per group one input stage {dY | S or activation input | X} filled while the group still works on its
+// previous tile, and one output staging tile drained by bulk tensor stores (or bulk tensor reduce-adds when the
+// destination accumulates).  dW comes from MN-major bf16 operands - each token writes 16-byte pieces of its own row, no
+// transposition - split hi + lo (16 mantissa bits): A = [dZ_hi ; dZ_lo] stacked along M (64), B = [X_hi | X_lo] along
+// N (64), one kind::f16 MMA per 16 tokens, all tiles of the CTA accumulating into one TMEM region.  dX keeps the
+// fp32-level tf32 hi/lo product with the A operand in TMEM.  Column sums (db, dgamma, dbeta) are warp transposes-by-
+// shuffle once per tile, one register per lane.
+constexpr int B2T = 320;
+constexpr int B2_STAGE = 3 * TSW;                    // floats per input stage
+constexpr int B2_OP = 64 * LT * 2;                   // bytes per bf16 operand tile [64 mn][128 tokens]
+constexpr size_t B2_SMEM = sizeof(float) * (2 * B2_STAGE + 2 * TSW + 2 * 1024 + 32 * 4) + 4 * (size_t)B2_OP + 8 * 8 + 16;
+
+__device__ __forceinline__ void group_bar(int g) {
+  if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_tile(const CUtensorMap* tm, int row0, const float* src, bool add) {
+  if (add)
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 :: "l"(tm), "r"(0), "r"(row0), "r"(smem_u32(src)) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 :: "l"(tm), "r"(0), "r"(row0), "r"(smem_u32(src)) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_drained() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_done() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// bf16 hi / lo of two neighbouring values, packed (low half = first value)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h); lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// one token row (32 values) -> MN-major bf16 operand tile: rows 0-31 hi, rows 32-63 lo; element (mn, tok) at
+// (mn & 7) * 2 + (mn >> 3) * 2048 + (tok & 7) * 16 + (tok >> 3) * 128 bytes   (LBO 128, SBO 2048)
+__device__ __forceinline__ void sts_row_bf16mn(unsigned char* op, int r, const float* v) {
+  unsigned char* base = op + (r & 7) * 16 + (r >> 3) * 128;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) split_bf16x2(v[8 * q + 2 * e], v[8 * q + 2 * e + 1], h[e], l[e]);
+    *reinterpret_cast<uint4*>(base + q * 2048) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(base + (4 + q) * 2048) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+__device__ __forceinline__ constexpr uint32_t idesc_bf16_mn(int M, int N) {
+  return idesc_f16_mn(M, N, true, true) | (1u << 7) | (1u << 10);
+}
+
+template <bool LN>
+__global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmAUX,
+                                                             const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDR,
+                                                             const __grid_constant__ CUtensorMap tmDX) {
+  constexpr int COLS = 256;            // per group: A hi|lo 64 + dX 32 (columns g*96 ..); dW at 192..255
+  extern __shared__ __align__(1024) unsigned char lin_tc_raw[];
+  float* ST = reinterpret_cast<float*>(lin_tc_raw);          // 2 input stages (plain pointer arithmetic keeps LDS / STS)
+  float* OUT = ST + 2 * B2_STAGE;                            // 2 staging tiles
+  unsigned char* OPA = reinterpret_cast<unsigned char*>(OUT + 2 * TSW);      // 2 x dZ operand
+  unsigned char* OPB = OPA + 2 * B2_OP;                                      // 2 x X operand
+  float* WThi = reinterpret_cast<float*>(OPB + 2 * B2_OP);
+  float* WTlo = WThi + 1024;
+  float* sG = WTlo + 1024;            // [32]
+  float* sDb = sG + 32; float* sDg = sDb + 32; float* sDbe = sDg + 32;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sDbe + 32);   // [2] TMA bytes landed
+  uint64_t* empty = full + 2;                                // [2] stage rows are in registers
+  uint64_t* ready = empty + 2;                               // [2] operands written
+  uint64_t* done = ready + 2;                                // [2] MMAs complete
+  uint32_t* tmem_s = reinterpret_cast<uint32_t*>(done + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool has_aux = LN || a.act != 0;
+
+  for (int i = tid; i < 1024; i += B2T) {
+    const int n = i >> 5, k = i & 31;
+    float hi, lo;
+    split_tf32(a.W[i], hi, lo);
+    const int o = (k >> 3) * 256 + (n >> 2) * 32 + (k & 7) * 4 + (n & 3);
+    WThi[o] = hi; WTlo[o] = lo;
+  }
+  if (tid < 32) { sG[tid] = LN ? a.gamma[tid] : 0.f; sDb[tid] = 0.f; sDg[tid] = 0.f; sDbe[tid] = 0.f; }
+  if (tid == 0) {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) { mbar_init(&full[g], 1); mbar_init(&empty[g], 128); mbar_init(&ready[g], 128); mbar_init(&done[g], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tmem_alloc<COLS>(tmem_s);
+  fence_async_smem();
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tb = *tmem_s;
+  const int ntiles = (a.T + LT - 1) / LT;
+
+  if (warp == 8) {
+    // ---- TMA producer ----
+    if (lane == 0) {
+      for (int i = 0;; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        if (tile >= ntiles) break;
+        const int g = i & 1, k = i >> 1;
+        if (k > 0) mbar_wait(&empty[g], (uint32_t)((k - 1) & 1));
+        float* st = ST + g * B2_STAGE;
+        mbar_expect_tx(&full[g], (has_aux ? 3u : 2u) * LT * 128u);
+        tma_load_tile(st, &tmDY, tile * LT, &full[g]);
+        if (has_aux) tma_load_tile(st + TSW, &tmAUX, tile * LT, &full[g]);
+        tma_load_tile(st + 2 * TSW, &tmX, tile * LT, &full[g]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ---- MMA issuer ----
+    if (lane == 0) {
+      const uint32_t idX = idesc_tf32(128, 32), idW = idesc_bf16_mn(64, 64);
+      const uint32_t aWThi = smem_u32(WThi), aWTlo = smem_u32(WTlo);
+      for (int i = 0;; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        if (tile >= ntiles) break;
+        const int g = i & 1, k = i >> 1;
+        mbar_wait(&ready[g], (uint32_t)(k & 1));
+        fence_after();
+        const uint32_t tA = tb + g * 96, tD = tA + 64;
+#pragma unroll
+        for (int s2 = 0; s2 < 4; ++s2) {
+          const uint32_t off = (uint32_t)(2 * s2) * 128;
+          const uint64_t bhi = smem_desc(aWThi + off, 128, 1024), blo = smem_desc(aWTlo + off, 128, 1024);
+          mma_ts(tD, tA + s2 * 8, bhi, idX, s2 > 0 ? 1u : 0u);
+          mma_ts(tD, tA + 32 + s2 * 8, bhi, idX, 1u);
+          mma_ts(tD, tA + s2 * 8, blo, idX, 1u);
+        }
+        const uint32_t aA = smem_u32(OPA + g * B2_OP), aB = smem_u32(OPB + g * B2_OP);
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          mma_ss_f16(tb + 192, smem_desc(aA + t * 256, 128, 2048), smem_desc(aB + t * 256, 128, 2048), idW, (i > 0 || t > 0) ? 1u : 0u);
+        commit(&done[g]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ---- row groups ----
+    const int g = warp >> 2, r = tid & 127;
+    const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16) + g * 96;
+    const DropCfg dc = make_drop(LN ? a.p_drop : 0.f, a.seed, a.stream_id);
+    float* st = ST + g * B2_STAGE;
+    float* out = OUT + g * TSW;
+    unsigned char* opA = OPA + g * B2_OP;
+    unsigned char* opB = OPB + g * B2_OP;
+    float acc_db = 0.f, acc_dg = 0.f, acc_dbe = 0.f;       // lane l: column l, this warp's rows, all tiles
+    int prev_row0 = -1;                                    // tile whose MMAs are in flight (dX not yet read back)
+    // dX of the previous tile: read back, staged and stored while this tile is already in progress.  The staging tile
+    // is free: thread r == 0 waits for its earlier bulk stores to drain before every `ready` arrive, and done[g]
+    // (waited for here) follows that arrive.
+    auto collect_dx = [&](int k_prev) {
+      mbar_wait(&done[g], (uint32_t)(k_prev & 1));
+      fence_after();
+      uint32_t d[32];
+      tmem_ld32(tl + 64, d); tmem_wait_ld();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(d[j]);
+      sts_row_sw(out, r, v);
+      fence_async_smem();
+      fence_before();
+      group_bar(g);
+      if (r == 0) tma_store_tile(&tmDX, prev_row0, out, a.dX_acc != 0);
+    };
+    int k = 0;
+    for (;; ++k) {
+      const int tile = blockIdx.x + (2 * k + g) * gridDim.x;
+      if (tile >= ntiles) break;
+      const int row0 = tile * LT;
+      const long long t = (long long)row0 + r;
+      mbar_wait(&full[g], (uint32_t)(k & 1));
+      float dz[32];
+      lds_row_sw(dz, st, r);
+      const bool store_dr = LN && a.dR != nullptr;
+      if (LN) {
+        float sv[32];
+        lds_row_sw(sv, st + TSW, r);
+        float mean = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mean += sv[j];
+        mean *= (1.f / 32);
+        float var = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { sv[j] -= mean; var = fmaf(sv[j], sv[j], var); }
+        const float rstd = 1.f / sqrtf(var * (1.f / 32) + a.eps);
+        float m1 = 0.f, m2 = 0.f;
+        float gq[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { gq[j] = dz[j] * sG[j]; m1 += gq[j]; m2 = fmaf(gq[j], sv[j], m2); }
+        m1 *= (1.f / 32); m2 *= (1.f / 32) * rstd;
+        {
+          float tg[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tg[j] = dz[j] * rstd * sv[j];
+          acc_dg += warp_colsum32(tg, lane);
+          acc_dbe += warp_colsum32(dz, lane);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dz[j] = rstd * (gq[j] - m1 - sv[j] * rstd * m2);      // dS = dR
+        if (store_dr) {          // staged over this thread's own (already consumed) dY row of the input stage
+          sts_row_sw(st, r, dz);
+          fence_async_smem();
+          group_bar(g);
+          if (r == 0) tma_store_tile(&tmDR, row0, st, a.dR_acc != 0);
+        }
+      } else if (a.act != 0) {
+        float av[32];
+        lds_row_sw(av, st + TSW, r);
+        if (a.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dz[j] = av[j] > 0.f ? dz[j] : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dz[j] *= gelu_erf_grad(av[j]);
+        }
+      }
+      if (prev_row0 >= 0) collect_dx(k - 1);     // from here on the operand tiles and the TMEM A region are free
+      {
+        float x[32];
+        lds_row_sw(x, st + 2 * TSW, r);
+        sts_row_bf16mn(opB, r, x);
+      }
+      if (!(store_dr && r == 0)) mbar_arrive(&empty[g]);       // this thread is done with the input stage
+      if (LN && dc.on) {
+        const uint32_t rh = drop_row_hash(dc, (uint64_t)t);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dz[j] *= drop_mult_row(dc, rh, j);
+      }
+      {
+        float hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) split_tf32(dz[j], hi[j], lo[j]);
+        tmem_put32(tl, hi); tmem_put32(tl + 32, lo);
+      }
+      sts_row_bf16mn(opA, r, dz);
+      tmem_wait_st();
+      fence_async_smem();
+      fence_before();
+      if (r == 0) {
+        tma_store_drained();                     // dX of the previous tile and dR of this one have left shared memory
+        if (store_dr) mbar_arrive(&empty[g]);
+      }
+      mbar_arrive(&ready[g]);
+      acc_db += warp_colsum32(dz, lane);         // dz is dead after this
+      prev_row0 = row0;
+    }
+    if (prev_row0 >= 0) collect_dx(k - 1);
+    if (r == 0) tma_store_done();
+    atomicAdd(&sDb[lane], acc_db);
+    if (LN) { atomicAdd(&sDg[lane], acc_dg); atomicAdd(&sDbe[lane], acc_dbe); }
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  if ((int)blockIdx.x < ntiles) {
+    // D_dW (M = 64): row m in TMEM lane (m & 15) + 32 * (m >> 4); rows 0-31 = dZ_hi x [X_hi | X_lo], rows 32-63 = dZ_lo x [X_hi | ..]
+    if (warp < 4) {
+      uint32_t d[32], e[32];
+      const uint32_t tq = tb + ((uint32_t)(warp * 32) << 16) + 192;
+      tmem_ld32(tq, d); tmem_ld32(tq + 32, e); tmem_wait_ld();
+      if (lane < 16) {
+        const int n = (warp & 1) * 16 + lane;
+#pragma unroll
+        for (int k = 0; k < 32; ++k)
+          atomicAdd(&a.dW[n * 32 + k], __uint_as_float(d[k]) + (warp < 2 ? __uint_as_float(e[k]) : 0.f));
+      }
+    }
+    if (tid < 32) {
+      atomicAdd(&a.db[tid], sDb[tid]);
+      if (LN && a.dgamma) atomicAdd(&a.dgamma[tid], sDg[tid]);
+      if (LN && a.dbeta) atomicAdd(&a.dbeta[tid], sDbe[tid]);
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 0) { fence_after(); tmem_dealloc<COLS>(tb); }
+}
+
 // ------------------------------------------------------------------------------------------------
 static bool al16(const void* p, long long ld) { return p == nullptr || ((((uintptr_t)p) & 15) == 0 && (ld & 3) == 0); }
 static bool tc_off() { static const bool off = [] { const char* e = getenv("VAESNE_NO_TC_LIN"); return e && e[0] && e[0] != '0'; }(); return off; }
@@ -726,7 +1011,37 @@ int lin_tc_fwd(const LinFwd& a, cudaStream_t st) {
   if (a.N == 64) return lin_tc_fwd_launch(lin_tc_fwd_kernel<2, false>, lin_tc_fwd_smem<2>(), g, st, "lin_tc_fwd", a);
   return lin_tc_fwd_launch(lin_tc_fwd_kernel<3, false>, lin_tc_fwd_smem<3>(), g, st, "lin_tc_fwd", a);
 }
+// pipelined variant: the big N = K = 32 calls of a training step (out_proj / ffn.2 with LayerNorm, q / ffn.0 plain)
+static int bwd2_mode() {     // VAESNE_LIN_BWD2: 0 = never, 1 = when eligible (default), 2 = also for small T (tests)
+  static const int m = [] { const char* e = getenv("VAESNE_LIN_BWD2"); return e && e[0] ? atoi(e) : 1; }();
+  return m;
+}
+static bool lin_tc_bwd2_eligible(const LinBwd& a) {
+  if (bwd2_mode() == 0 || a.N != 32 || a.K != 32) return false;
+  if (!a.dX || !a.dW || !a.db || a.Xadd) return false;
+  if (a.S && a.lddr != 0 && a.dR && (a.lddr & 3)) return false;
+  return bwd2_mode() >= 2 || a.T >= 148 * LT * 4;
+}
+template <typename K>
+static int lin_tc_bwd2_launch(K k, cudaStream_t st, const char* what, const LinBwd& a) {
+  TcKernelInfo ki;
+  int rc = tc_prepare(k, B2_SMEM, what, ki, B2T); if (rc) return rc;
+  CUtensorMap tmDY, tmAUX, tmX, tmDR, tmDX;
+  rc = make_tile_map(&tmDY, a.dY, a.lddy, a.T, what); if (rc) return rc;
+  tmAUX = tmDY; tmDR = tmDY;
+  if (a.S) { rc = make_tile_map(&tmAUX, a.S, 32, a.T, what); if (rc) return rc; }
+  else if (a.act != 0) { rc = make_tile_map(&tmAUX, a.A, a.lda, a.T, what); if (rc) return rc; }
+  rc = make_tile_map(&tmX, a.X, a.ldx, a.T, what); if (rc) return rc;
+  if (a.S && a.dR) { rc = make_tile_map(&tmDR, a.dR, a.lddr, a.T, what); if (rc) return rc; }
+  rc = make_tile_map(&tmDX, a.dX, a.lddx, a.T, what); if (rc) return rc;
+  const int ntiles = (a.T + LT - 1) / LT;
+  k<<<ntiles < ki.sms ? ntiles : ki.sms, B2T, B2_SMEM, st>>>(a, tmDY, tmAUX, tmX, tmDR, tmDX);
+  return check_launch(what);
+}
 static int lin_tc_bwd_one(const LinBwd& a, cudaStream_t st) {
+  if (lin_tc_bwd2_eligible(a))
+    return a.S ? lin_tc_bwd2_launch(lin_tc_bwd2_kernel<true>, st, "lin_tc_bwd2_ln", a)
+               : lin_tc_bwd2_launch(lin_tc_bwd2_kernel<false>, st, "lin_tc_bwd2", a);
   const int g = 2;                                   // TMEM: 256 columns per CTA
   if (a.S) return tc_launch(lin_tc_bwd_kernel<1, true>, lin_tc_bwd_smem<1>(), g, st, "lin_tc_bwd_ln", a, BT);
   if (a.N == 32) return tc_launch(lin_tc_bwd_kernel<1, false>, lin_tc_bwd_smem<1>(), g, st, "lin_tc_bwd", a, BT);

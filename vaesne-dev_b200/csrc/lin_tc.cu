@@ -578,18 +578,33 @@ __global__ void __launch_bounds__(BT, 2) lin_tc_bwd_kernel(LinBwd a) {
   }
   if (pending) { mbar_wait(bar, ph); ph ^= 1u; pending = false; }
   fence_after();
-  if (wgrad && !first_tile && warp < 2) {
-    // D_dW region c (64 columns): lanes 0-31 hold [hi*hi | hi*lo] of row n = lane, lanes 32-63 hold [lo*hi | lo*lo]
+  if (wgrad && !first_tile) {
+    // D_dW region c (64 columns): lanes 0-31 hold [hi*hi | hi*lo] of row n = lane, lanes 32-63 hold [lo*hi | lo*lo].
+    // The three parts are summed in shared memory first, so that the CTA sends one coalesced atomic per 128-byte line of
+    // dW: every CTA of the grid flushes at about the same time, and one atomic per element per part serialises in L2
+    // (measured: ~19 us per launch, against ~1 us for this form).
+    float* part = dZT;                 // [N][33]; every operand tile is dead by now
+    __syncthreads();
+    if (warp < 2) {
 #pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-      uint32_t d[32], e[32];
-      tmem_ld32(tl + 96 + c * 64, d);
-      tmem_ld32(tl + 96 + c * 64 + 32, e);
-      tmem_wait_ld();
+      for (int c = 0; c < NCH; ++c) {
+        uint32_t d[32], e[32];
+        tmem_ld32(tl + 96 + c * 64, d);
+        tmem_ld32(tl + 96 + c * 64 + 32, e);
+        tmem_wait_ld();
+        if (warp == 0) {
 #pragma unroll
-      for (int k = 0; k < 32; ++k)
-        atomicAdd(&a.dW[(c * 32 + lane) * 32 + k], __uint_as_float(d[k]) + (warp == 0 ? __uint_as_float(e[k]) : 0.f));
+          for (int k = 0; k < 32; ++k) part[(c * 32 + lane) * 33 + k] = __uint_as_float(d[k]) + __uint_as_float(e[k]);
+        }
+        __syncwarp();
+        if (warp == 1) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) part[(N + c * 32 + lane) * 33 + k] = __uint_as_float(d[k]);
+        }
+      }
     }
+    __syncthreads();
+    for (int i = tid; i < N * 32; i += BT) atomicAdd(&a.dW[i], part[(i >> 5) * 33 + (i & 31)] + part[(N + (i >> 5)) * 33 + (i & 31)]);
   }
   // column sums of this thread's rows -> shared accumulators (lane l < 16 holds column c0 + l)
   if (wgrad && a.db) {
@@ -627,9 +642,9 @@ __global__ void __launch_bounds__(BT, 2) lin_tc_bwd_kernel(LinBwd a) {
 // fp32-level tf32 hi/lo product with the A operand in TMEM.  Column sums (db, dgamma, dbeta) are warp transposes-by-
 // shuffle once per tile, one register per lane.
 constexpr int B2T = 320;
-constexpr int B2_STAGE = 3 * TSW;                    // floats per input stage
+constexpr int B2_RING = 9 * TSW;                     // floats of the input ring: 3 stages of 3 tiles or 4 stages of 2 tiles
 constexpr int B2_OP = 64 * LT * 2;                   // bytes per bf16 operand tile [64 mn][128 tokens]
-constexpr size_t B2_SMEM = sizeof(float) * (2 * B2_STAGE + 2 * TSW + 2 * 1024 + 32 * 4) + 4 * (size_t)B2_OP + 8 * 8 + 16;
+constexpr size_t B2_SMEM = sizeof(float) * (B2_RING + 2 * 1024 + 32 * 4) + 4 * (size_t)B2_OP + 12 * 8 + 16;
 
 __device__ __forceinline__ void group_bar(int g) {
   if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -642,6 +657,9 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap* tm, int row0, 
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
                  :: "l"(tm), "r"(0), "r"(row0), "r"(smem_u32(src)) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_tile(const CUtensorMap* tm, int row0) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(tm), "r"(0), "r"(row0) : "memory");
 }
 __device__ __forceinline__ void tma_store_drained() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_done() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -675,21 +693,27 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
                                                              const __grid_constant__ CUtensorMap tmDX) {
   constexpr int COLS = 256;            // per group: A hi|lo 64 + dX 32 (columns g*96 ..); dW at 192..255
   extern __shared__ __align__(1024) unsigned char lin_tc_raw[];
-  float* ST = reinterpret_cast<float*>(lin_tc_raw);          // 2 input stages (plain pointer arithmetic keeps LDS / STS)
-  float* OUT = ST + 2 * B2_STAGE;                            // 2 staging tiles
-  unsigned char* OPA = reinterpret_cast<unsigned char*>(OUT + 2 * TSW);      // 2 x dZ operand
+  float* ST = reinterpret_cast<float*>(lin_tc_raw);          // input ring (plain pointer arithmetic keeps LDS / STS)
+  unsigned char* OPA = reinterpret_cast<unsigned char*>(ST + B2_RING);       // 2 x dZ operand
   unsigned char* OPB = OPA + 2 * B2_OP;                                      // 2 x X operand
   float* WThi = reinterpret_cast<float*>(OPB + 2 * B2_OP);
   float* WTlo = WThi + 1024;
   float* sG = WTlo + 1024;            // [32]
   float* sDb = sG + 32; float* sDg = sDb + 32; float* sDbe = sDg + 32;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sDbe + 32);   // [2] TMA bytes landed
-  uint64_t* empty = full + 2;                                // [2] stage rows are in registers
-  uint64_t* ready = empty + 2;                               // [2] operands written
-  uint64_t* done = ready + 2;                                // [2] MMAs complete
+  uint64_t* full = reinterpret_cast<uint64_t*>(sDbe + 32);   // [4] TMA bytes landed in stage s
+  uint64_t* empty = full + 4;                                // [4] stage s may be refilled
+  uint64_t* ready = empty + 4;                               // [2] operands of group g written
+  uint64_t* done = ready + 2;                                // [2] MMAs of group g complete
   uint32_t* tmem_s = reinterpret_cast<uint32_t*>(done + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef VAESNE_B2_PROF
+  unsigned long long tp0, tp1 = 0, tp2 = 0, tp3 = 0;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tp0));
+#endif
   const bool has_aux = LN || a.act != 0;
+  const int nst = (a.smem_acc >> 16) ? (a.smem_acc >> 16) : (has_aux ? 3 : 4);      // stages in the ring
+  const int stage_floats = (has_aux ? 3 : 2) * TSW;          // {dY | S or activation input | X}  /  {dY | X}
+  const int x_off = (has_aux ? 2 : 1) * TSW;
 
   for (int i = tid; i < 1024; i += B2T) {
     const int n = i >> 5, k = i & 31;
@@ -701,7 +725,9 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
   if (tid < 32) { sG[tid] = LN ? a.gamma[tid] : 0.f; sDb[tid] = 0.f; sDg[tid] = 0.f; sDbe[tid] = 0.f; }
   if (tid == 0) {
 #pragma unroll
-    for (int g = 0; g < 2; ++g) { mbar_init(&full[g], 1); mbar_init(&empty[g], 128); mbar_init(&ready[g], 128); mbar_init(&done[g], 1); }
+    for (int q = 0; q < 4; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], 128); }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) { mbar_init(&ready[g], 128); mbar_init(&done[g], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) tmem_alloc<COLS>(tmem_s);
@@ -711,20 +737,31 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
   fence_after();
   const uint32_t tb = *tmem_s;
   const int ntiles = (a.T + LT - 1) / LT;
+#ifdef VAESNE_B2_PROF
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tp1));
+#endif
 
   if (warp == 8) {
-    // ---- TMA producer ----
+    // ---- TMA producer: tile i of this CTA goes to stage i % nst ----
     if (lane == 0) {
+      const int pf = a.smem_acc & 255;   // (probe) L2 prefetch distance in CTA tiles
+      int s = 0, u = 0;                  // stage, use count of that stage
       for (int i = 0;; ++i) {
         const int tile = blockIdx.x + i * gridDim.x;
         if (tile >= ntiles) break;
-        const int g = i & 1, k = i >> 1;
-        if (k > 0) mbar_wait(&empty[g], (uint32_t)((k - 1) & 1));
-        float* st = ST + g * B2_STAGE;
-        mbar_expect_tx(&full[g], (has_aux ? 3u : 2u) * LT * 128u);
-        tma_load_tile(st, &tmDY, tile * LT, &full[g]);
-        if (has_aux) tma_load_tile(st + TSW, &tmAUX, tile * LT, &full[g]);
-        tma_load_tile(st + 2 * TSW, &tmX, tile * LT, &full[g]);
+        if (u > 0) mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));
+        float* st = ST + s * stage_floats;
+        mbar_expect_tx(&full[s], (has_aux ? 3u : 2u) * LT * 128u);
+        tma_load_tile(st, &tmDY, tile * LT, &full[s]);
+        if (has_aux) tma_load_tile(st + TSW, &tmAUX, tile * LT, &full[s]);
+        tma_load_tile(st + x_off, &tmX, tile * LT, &full[s]);
+        const int ahead = tile + pf * (int)gridDim.x;      // the ring holds too few bytes in flight for HBM latency:
+        if (pf > 0 && ahead < ntiles) {                    // tiles further ahead are pulled into L2 meanwhile
+          tma_prefetch_tile(&tmDY, ahead * LT);
+          if (has_aux) tma_prefetch_tile(&tmAUX, ahead * LT);
+          tma_prefetch_tile(&tmX, ahead * LT);
+        }
+        if (++s == nst) { s = 0; ++u; }
       }
     }
     __syncwarp();
@@ -740,6 +777,7 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
         mbar_wait(&ready[g], (uint32_t)(k & 1));
         fence_after();
         const uint32_t tA = tb + g * 96, tD = tA + 64;
+        if (a.smem_acc & 1024) { commit(&done[g]); continue; }
 #pragma unroll
         for (int s2 = 0; s2 < 4; ++s2) {
           const uint32_t off = (uint32_t)(2 * s2) * 128;
@@ -757,43 +795,28 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
     }
     __syncwarp();
   } else {
-    // ---- row groups ----
+    // ---- row groups: group g takes the CTA's tiles i = g, g + 2, ... ----
     const int g = warp >> 2, r = tid & 127;
     const uint32_t tl = tb + ((uint32_t)((warp & 3) * 32) << 16) + g * 96;
     const DropCfg dc = make_drop(LN ? a.p_drop : 0.f, a.seed, a.stream_id);
-    float* st = ST + g * B2_STAGE;
-    float* out = OUT + g * TSW;
     unsigned char* opA = OPA + g * B2_OP;
     unsigned char* opB = OPB + g * B2_OP;
+    const bool store_dr = LN && a.dR != nullptr;
     float acc_db = 0.f, acc_dg = 0.f, acc_dbe = 0.f;       // lane l: column l, this warp's rows, all tiles
     int prev_row0 = -1;                                    // tile whose MMAs are in flight (dX not yet read back)
-    // dX of the previous tile: read back, staged and stored while this tile is already in progress.  The staging tile
-    // is free: thread r == 0 waits for its earlier bulk stores to drain before every `ready` arrive, and done[g]
-    // (waited for here) follows that arrive.
-    auto collect_dx = [&](int k_prev) {
-      mbar_wait(&done[g], (uint32_t)(k_prev & 1));
-      fence_after();
-      uint32_t d[32];
-      tmem_ld32(tl + 64, d); tmem_wait_ld();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(d[j]);
-      sts_row_sw(out, r, v);
-      fence_async_smem();
-      fence_before();
-      group_bar(g);
-      if (r == 0) tma_store_tile(&tmDX, prev_row0, out, a.dX_acc != 0);
-    };
+    float* st = ST;
     int k = 0;
     for (;; ++k) {
-      const int tile = blockIdx.x + (2 * k + g) * gridDim.x;
+      const int i = 2 * k + g;
+      const int tile = blockIdx.x + i * gridDim.x;
       if (tile >= ntiles) break;
+      const int s = i % nst, u = i / nst;
+      st = ST + s * stage_floats;
       const int row0 = tile * LT;
       const long long t = (long long)row0 + r;
-      mbar_wait(&full[g], (uint32_t)(k & 1));
+      mbar_wait(&full[s], (uint32_t)(u & 1));
       float dz[32];
       lds_row_sw(dz, st, r);
-      const bool store_dr = LN && a.dR != nullptr;
       if (LN) {
         float sv[32];
         lds_row_sw(sv, st + TSW, r);
@@ -814,17 +837,14 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
           float tg[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) tg[j] = dz[j] * rstd * sv[j];
+          if (!(a.smem_acc & 2048)) {
           acc_dg += warp_colsum32(tg, lane);
           acc_dbe += warp_colsum32(dz, lane);
+          }
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) dz[j] = rstd * (gq[j] - m1 - sv[j] * rstd * m2);      // dS = dR
-        if (store_dr) {          // staged over this thread's own (already consumed) dY row of the input stage
-          sts_row_sw(st, r, dz);
-          fence_async_smem();
-          group_bar(g);
-          if (r == 0) tma_store_tile(&tmDR, row0, st, a.dR_acc != 0);
-        }
+        if (store_dr) sts_row_sw(st, r, dz);     // staged over this thread's own (already consumed) dY row of the stage
       } else if (a.act != 0) {
         float av[32];
         lds_row_sw(av, st + TSW, r);
@@ -836,13 +856,35 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
           for (int j = 0; j < 32; ++j) dz[j] *= gelu_erf_grad(av[j]);
         }
       }
-      if (prev_row0 >= 0) collect_dx(k - 1);     // from here on the operand tiles and the TMEM A region are free
+      // dX of the group's previous tile is collected only now, behind this tile's row arithmetic; from here on the
+      // operand tiles and the TMEM A region are free again.  It is staged over this thread's own X row of the stage.
       {
+        uint32_t d[32];
+        if (prev_row0 >= 0) {
+          mbar_wait(&done[g], (uint32_t)((k - 1) & 1));
+          fence_after();
+          tmem_ld32(tl + 64, d); tmem_wait_ld();
+          fence_before();
+        }
         float x[32];
-        lds_row_sw(x, st + 2 * TSW, r);
+        lds_row_sw(x, st + x_off, r);
         sts_row_bf16mn(opB, r, x);
+        if (prev_row0 >= 0) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(d[j]);
+          sts_row_sw(st + x_off, r, v);
+        }
       }
-      if (!(store_dr && r == 0)) mbar_arrive(&empty[g]);       // this thread is done with the input stage
+      if (store_dr || prev_row0 >= 0) {
+        fence_async_smem();
+        group_bar(g);
+        if (r == 0) {
+          if (store_dr && !(a.smem_acc & 512)) tma_store_tile(&tmDR, row0, st, a.dR_acc != 0);
+          if (prev_row0 >= 0 && !(a.smem_acc & 256)) tma_store_tile(&tmDX, prev_row0, st + x_off, a.dX_acc != 0);
+        }
+      }
+      if (r != 0) mbar_arrive(&empty[s]);        // this thread is done with the stage (thread 0: once its stores have drained)
       if (LN && dc.on) {
         const uint32_t rh = drop_row_hash(dc, (uint64_t)t);
 #pragma unroll
@@ -858,15 +900,26 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
       tmem_wait_st();
       fence_async_smem();
       fence_before();
-      if (r == 0) {
-        tma_store_drained();                     // dX of the previous tile and dR of this one have left shared memory
-        if (store_dr) mbar_arrive(&empty[g]);
-      }
+      if (r == 0) { tma_store_drained(); mbar_arrive(&empty[s]); }
       mbar_arrive(&ready[g]);
-      acc_db += warp_colsum32(dz, lane);         // dz is dead after this
+      if (!(a.smem_acc & 2048)) acc_db += warp_colsum32(dz, lane);         // dz is dead after this
       prev_row0 = row0;
     }
-    if (prev_row0 >= 0) collect_dx(k - 1);
+    if (prev_row0 >= 0) {
+      // last tile of the group: its stage is not refilled any more (thread 0 drained its stores before releasing it)
+      mbar_wait(&done[g], (uint32_t)((k - 1) & 1));
+      fence_after();
+      uint32_t d[32];
+      tmem_ld32(tl + 64, d); tmem_wait_ld();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(d[j]);
+      sts_row_sw(st + x_off, r, v);
+      fence_async_smem();
+      fence_before();
+      group_bar(g);
+      if (r == 0) tma_store_tile(&tmDX, prev_row0, st + x_off, a.dX_acc != 0);
+    }
     if (r == 0) tma_store_done();
     atomicAdd(&sDb[lane], acc_db);
     if (LN) { atomicAdd(&sDg[lane], acc_dg); atomicAdd(&sDbe[lane], acc_dbe); }
@@ -874,19 +927,25 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
   fence_before();
   __syncthreads();
   fence_after();
+#ifdef VAESNE_B2_PROF
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tp2));
+#endif
   if ((int)blockIdx.x < ntiles) {
     // D_dW (M = 64): row m in TMEM lane (m & 15) + 32 * (m >> 4); rows 0-31 = dZ_hi x [X_hi | X_lo], rows 32-63 = dZ_lo x [X_hi | ..]
+    // the parts are summed in shared memory (the input ring is idle now) and leave as one coalesced atomic per line
+    float* part = ST;                  // [64][33]: rows 0-31 hi parts, 32-63 lo parts
     if (warp < 4) {
       uint32_t d[32], e[32];
       const uint32_t tq = tb + ((uint32_t)(warp * 32) << 16) + 192;
       tmem_ld32(tq, d); tmem_ld32(tq + 32, e); tmem_wait_ld();
       if (lane < 16) {
-        const int n = (warp & 1) * 16 + lane;
+        const int m = warp * 16 + lane;
 #pragma unroll
-        for (int k = 0; k < 32; ++k)
-          atomicAdd(&a.dW[n * 32 + k], __uint_as_float(d[k]) + (warp < 2 ? __uint_as_float(e[k]) : 0.f));
+        for (int k = 0; k < 32; ++k) part[m * 33 + k] = __uint_as_float(d[k]) + (warp < 2 ? __uint_as_float(e[k]) : 0.f);
       }
     }
+    __syncthreads();
+    for (int i = tid; i < 1024; i += B2T) atomicAdd(&a.dW[i], part[(i >> 5) * 33 + (i & 31)] + part[(32 + (i >> 5)) * 33 + (i & 31)]);
     if (tid < 32) {
       atomicAdd(&a.db[tid], sDb[tid]);
       if (LN && a.dgamma) atomicAdd(&a.dgamma[tid], sDg[tid]);
@@ -895,6 +954,11 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
   }
   fence_before();
   __syncthreads();
+#ifdef VAESNE_B2_PROF
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tp3));
+  if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == 147))
+    printf("[b2prof] cta %d LN %d tiles %d: start %llu prologue %llu loop %llu flush %llu ns\n", (int)blockIdx.x, (int)LN, ntiles, tp0 % 100000000ull, tp1 - tp0, tp2 - tp1, tp3 - tp2);
+#endif
   if (warp == 0) { fence_after(); tmem_dealloc<COLS>(tb); }
 }
 
@@ -1035,7 +1099,10 @@ static int lin_tc_bwd2_launch(K k, cudaStream_t st, const char* what, const LinB
   if (a.S && a.dR) { rc = make_tile_map(&tmDR, a.dR, a.lddr, a.T, what); if (rc) return rc; }
   rc = make_tile_map(&tmDX, a.dX, a.lddx, a.T, what); if (rc) return rc;
   const int ntiles = (a.T + LT - 1) / LT;
-  k<<<ntiles < ki.sms ? ntiles : ki.sms, B2T, B2_SMEM, st>>>(a, tmDY, tmAUX, tmX, tmDR, tmDX);
+  static const int pf = [] { const char* e = getenv("VAESNE_BWD2_PF"); return e && e[0] ? atoi(e) : 4; }();
+  LinBwd b = a;
+  b.smem_acc = pf;                     // (field reused) L2 prefetch distance, in tiles of one CTA
+  k<<<ntiles < ki.sms ? ntiles : ki.sms, B2T, B2_SMEM, st>>>(b, tmDY, tmAUX, tmX, tmDR, tmDX);
   return check_launch(what);
 }
 static int lin_tc_bwd_one(const LinBwd& a, cudaStream_t st) {

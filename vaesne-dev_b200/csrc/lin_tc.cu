@@ -658,9 +658,6 @@ __device__ __forceinline__ void tma_store_tile(const CUtensorMap* tm, int row0, 
                  :: "l"(tm), "r"(0), "r"(row0), "r"(smem_u32(src)) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void tma_prefetch_tile(const CUtensorMap* tm, int row0) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" :: "l"(tm), "r"(0), "r"(row0) : "memory");
-}
 __device__ __forceinline__ void tma_store_drained() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_done() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // bf16 hi / lo of two neighbouring values, packed (low half = first value)
@@ -711,7 +708,7 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tp0));
 #endif
   const bool has_aux = LN || a.act != 0;
-  const int nst = (a.smem_acc >> 16) ? (a.smem_acc >> 16) : (has_aux ? 3 : 4);      // stages in the ring
+  const int nst = has_aux ? 3 : 4;                           // stages in the ring
   const int stage_floats = (has_aux ? 3 : 2) * TSW;          // {dY | S or activation input | X}  /  {dY | X}
   const int x_off = (has_aux ? 2 : 1) * TSW;
 
@@ -744,7 +741,6 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
   if (warp == 8) {
     // ---- TMA producer: tile i of this CTA goes to stage i % nst ----
     if (lane == 0) {
-      const int pf = a.smem_acc & 255;   // (probe) L2 prefetch distance in CTA tiles
       int s = 0, u = 0;                  // stage, use count of that stage
       for (int i = 0;; ++i) {
         const int tile = blockIdx.x + i * gridDim.x;
@@ -755,12 +751,6 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
         tma_load_tile(st, &tmDY, tile * LT, &full[s]);
         if (has_aux) tma_load_tile(st + TSW, &tmAUX, tile * LT, &full[s]);
         tma_load_tile(st + x_off, &tmX, tile * LT, &full[s]);
-        const int ahead = tile + pf * (int)gridDim.x;      // the ring holds too few bytes in flight for HBM latency:
-        if (pf > 0 && ahead < ntiles) {                    // tiles further ahead are pulled into L2 meanwhile
-          tma_prefetch_tile(&tmDY, ahead * LT);
-          if (has_aux) tma_prefetch_tile(&tmAUX, ahead * LT);
-          tma_prefetch_tile(&tmX, ahead * LT);
-        }
         if (++s == nst) { s = 0; ++u; }
       }
     }
@@ -777,7 +767,6 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
         mbar_wait(&ready[g], (uint32_t)(k & 1));
         fence_after();
         const uint32_t tA = tb + g * 96, tD = tA + 64;
-        if (a.smem_acc & 1024) { commit(&done[g]); continue; }
 #pragma unroll
         for (int s2 = 0; s2 < 4; ++s2) {
           const uint32_t off = (uint32_t)(2 * s2) * 128;
@@ -837,10 +826,8 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
           float tg[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) tg[j] = dz[j] * rstd * sv[j];
-          if (!(a.smem_acc & 2048)) {
           acc_dg += warp_colsum32(tg, lane);
           acc_dbe += warp_colsum32(dz, lane);
-          }
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) dz[j] = rstd * (gq[j] - m1 - sv[j] * rstd * m2);      // dS = dR
@@ -880,8 +867,8 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
         fence_async_smem();
         group_bar(g);
         if (r == 0) {
-          if (store_dr && !(a.smem_acc & 512)) tma_store_tile(&tmDR, row0, st, a.dR_acc != 0);
-          if (prev_row0 >= 0 && !(a.smem_acc & 256)) tma_store_tile(&tmDX, prev_row0, st + x_off, a.dX_acc != 0);
+          if (store_dr) tma_store_tile(&tmDR, row0, st, a.dR_acc != 0);
+          if (prev_row0 >= 0) tma_store_tile(&tmDX, prev_row0, st + x_off, a.dX_acc != 0);
         }
       }
       if (r != 0) mbar_arrive(&empty[s]);        // this thread is done with the stage (thread 0: once its stores have drained)
@@ -902,7 +889,7 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
       fence_before();
       if (r == 0) { tma_store_drained(); mbar_arrive(&empty[s]); }
       mbar_arrive(&ready[g]);
-      if (!(a.smem_acc & 2048)) acc_db += warp_colsum32(dz, lane);         // dz is dead after this
+      acc_db += warp_colsum32(dz, lane);         // dz is dead after this
       prev_row0 = row0;
     }
     if (prev_row0 >= 0) {
@@ -1099,10 +1086,7 @@ static int lin_tc_bwd2_launch(K k, cudaStream_t st, const char* what, const LinB
   if (a.S && a.dR) { rc = make_tile_map(&tmDR, a.dR, a.lddr, a.T, what); if (rc) return rc; }
   rc = make_tile_map(&tmDX, a.dX, a.lddx, a.T, what); if (rc) return rc;
   const int ntiles = (a.T + LT - 1) / LT;
-  static const int pf = [] { const char* e = getenv("VAESNE_BWD2_PF"); return e && e[0] ? atoi(e) : 4; }();
-  LinBwd b = a;
-  b.smem_acc = pf;                     // (field reused) L2 prefetch distance, in tiles of one CTA
-  k<<<ntiles < ki.sms ? ntiles : ki.sms, B2T, B2_SMEM, st>>>(b, tmDY, tmAUX, tmX, tmDR, tmDX);
+  k<<<ntiles < ki.sms ? ntiles : ki.sms, B2T, B2_SMEM, st>>>(a, tmDY, tmAUX, tmX, tmDR, tmDX);
   return check_launch(what);
 }
 static int lin_tc_bwd_one(const LinBwd& a, cudaStream_t st) {

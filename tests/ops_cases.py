@@ -153,6 +153,55 @@ def run_lin_case(c, device):
     assert rel_err(dX2.cpu(), refs["dX"]) < TOL
 
 
+def run_lin_accumulate_case(kind, T, device):
+    """Accumulating destinations (dX_acc / dR_acc) of the linear backward at a token count that keeps many tiles per
+    persistent CTA in flight: every combination must equal the overwrite-mode result plus the previous contents, and the
+    overwrite-mode result must match an fp64 torch reference.  (Round 2: bulk tensor reduce-adds raced with the loads of
+    the pipelined kernel at this scale while every small case passed.)"""
+    from VAESNe import _ops as P
+    g = _g(T + len(kind))
+    N = 96 if kind == "wide" else 32
+    X, dY = torch.randn(T, 32, generator=g), torch.randn(T, N, generator=g)
+    W, b = torch.randn(N, 32, generator=g) / 6, torch.randn(N, generator=g)
+    ln = kind == "ln"
+    act = 2 if kind == "gelu" else 0
+    Xd, Wd, bd = X.double().requires_grad_(), W.double().requires_grad_(), b.double().requires_grad_()
+    lin = Xd @ Wd.T + bd
+    out = F.gelu(lin) if act == 2 else lin
+    kw, refs = {}, {}
+    Xc, dYc, Wc = X.to(device), dY.to(device), W.to(device)
+    H = torch.empty(T, N, device=device) if act == 2 else None
+    if ln:
+        R, gamma, beta = torch.randn(T, 32, generator=g), torch.randn(32, generator=g), torch.randn(32, generator=g)
+        Rd, gd, bed = R.double().requires_grad_(), gamma.double().requires_grad_(), beta.double().requires_grad_()
+        out = F.layer_norm(Rd + out, (32,), gd, bed, 1e-5)
+        Sbuf = torch.empty(T, 32, device=device)
+        P.lin_fwd(Xc, Wc, b.to(device), R=R.to(device), gamma=gamma.to(device), beta=beta.to(device), S=Sbuf)
+        kw = dict(S=Sbuf, gamma=gamma.to(device))
+    else:
+        P.lin_fwd(Xc, Wc, b.to(device), act=act, H=H)
+    out.backward(dY.double())
+    refs = dict(dX=Xd.grad, dW=Wd.grad, db=bd.grad)
+    if ln:
+        refs.update(dR=Rd.grad, dgamma=gd.grad, dbeta=bed.grad)
+    for racc, xacc in [(False, False), (True, False), (False, True), (True, True)] if ln else [(False, False), (False, True)]:
+        dW = torch.zeros(N, 32, device=device); db = torch.zeros(N, device=device)
+        dX = torch.full((T, 32), 0.5 if xacc else -3.0, device=device)
+        k2 = dict(kw)
+        if ln:
+            k2.update(dgamma=torch.zeros(32, device=device), dbeta=torch.zeros(32, device=device),
+                      dR=torch.full((T, 32), 0.25 if racc else 7.0, device=device), dR_acc=racc)
+        P.lin_bwd(dYc, Xc, Wc, act=act, A=H, dW=dW, db=db, dX=dX, dX_acc=xacc, **k2)
+        tag = (kind, T, racc, xacc)
+        assert rel_err(dX.cpu() - (0.5 if xacc else 0.0), refs["dX"]) < TOL, (tag, "dX")
+        assert rel_err(dW.cpu(), refs["dW"]) < TOL, (tag, "dW")
+        assert rel_err(db.cpu(), refs["db"]) < TOL, (tag, "db")
+        if ln:
+            assert rel_err(k2["dR"].cpu() - (0.25 if racc else 0.0), refs["dR"]) < TOL, (tag, "dR")
+            assert rel_err(k2["dgamma"].cpu(), refs["dgamma"]) < TOL, (tag, "dgamma")
+            assert rel_err(k2["dbeta"].cpu(), refs["dbeta"]) < TOL, (tag, "dbeta")
+
+
 # ------------------------------------------------------------------------------------------------
 ATTN_CASES_SMALL = [
     dict(id="self_8x8", N=3, Lq=8, Lk=8, mask=False, packed="qkv"),

@@ -1,9 +1,6 @@
 #!/bin/bash
-# Dev probe: A/B of two versions of lin_tc.cu on the same box (tests/probe/tmp/lin_tc_prev.cu.txt = version A).
+# Dev probe: accumulate-mode soak of the pipelined linear backward with the in-kernel stage check.
 cd "$GRAFT_REPO_ROOT" || exit 1
-echo "--- B (current)"; timeout 300 python tests/probe/lin_bench.py 2>&1 | grep "bwd_ln\|bwd 32   \|bwd gelu\|bwd 96"
-cp vaesne-dev_b200/csrc/lin_tc.cu /tmp/cur.cu; cp tests/probe/tmp/lin_tc_prev.cu.txt vaesne-dev_b200/csrc/lin_tc.cu
-python vaesne-dev_b200/build.py --force > /dev/null 2>&1
-echo "--- A (previous)"; timeout 300 python tests/probe/lin_bench.py 2>&1 | grep "bwd_ln\|bwd 32   \|bwd gelu\|bwd 96"
-cp /tmp/cur.cu vaesne-dev_b200/csrc/lin_tc.cu; python vaesne-dev_b200/build.py --force > /dev/null 2>&1
-echo "--- B again"; timeout 300 python tests/probe/lin_bench.py 2>&1 | grep "bwd_ln\|bwd 32   \|bwd gelu\|bwd 96"
+B2_CHECK=1 python vaesne-dev_b200/build.py --force > /dev/null 2>&1
+for i in 1 2 3 4 5 6; do MARK=1 TS=1005568,8044544 VAESNE_LIN_BWD2=2 timeout 300 python tests/probe/bwd2_acc_probe.py 2>&1 | grep "b2check\|^T=\|Error" | grep -v "e-07\|0.00e+00\|e-08" | cut -c1-200 | head -14; done
+echo soak done

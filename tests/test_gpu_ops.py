@@ -18,6 +18,13 @@ def test_attn(case):
     OC.run_attn_case(case, "cuda", tol=1e-3 if OC.is_tc_shape(case["Lq"], case["Lk"], "cuda") else OC.TOL)
 
 
+@pytest.mark.parametrize("kind", ["ln", "plain", "gelu", "wide"])
+def test_lin_accumulating_destinations_at_pipeline_scale(kind):
+    # 27 tiles per persistent CTA (the pipelined kernel's steady state), ragged tail; repeated: the round-2 race was intermittent
+    for rep in range(2):
+        OC.run_lin_accumulate_case(kind, 128 * 148 * 27 + 77 + rep, "cuda")
+
+
 def test_misc():
     OC.run_misc_cases("cuda")
 

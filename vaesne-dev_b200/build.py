@@ -17,6 +17,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 if os.environ.get("VAESNE_TC_PROFILE"):      # probe build: per-phase clocks in attn_tc_dkv_kernel (tests/probe/attn_tc_check.py TC_PROF=1)
     FLAGS.append("-DVAESNE_TC_PROFILE")
+if os.environ.get("B2_CHECK"):
+    FLAGS.append("-DB2_CHECK")
 if os.environ.get("VAESNE_B2_PROF"):         # probe build: per-phase timers printed by lin_tc_bwd2_kernel
     FLAGS.append("-DVAESNE_B2_PROF")
 

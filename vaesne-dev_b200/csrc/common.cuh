@@ -87,6 +87,21 @@ __device__ __forceinline__ float drop_mult_row(const DropCfg& d, uint32_t rh, in
 }
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// Same derivative with erf from Abramowitz & Stegun 7.1.26 (|error| < 1.5e-7), sharing its exponential with the
+// density term: two MUFU operations and ~12 FMA-pipe instructions per element instead of erff + expf (~45).  Used where
+// the derivative is the bulk of a kernel's arithmetic (the pipelined linear backward).
+__device__ __forceinline__ float gelu_erf_grad_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  const float e = __expf(-0.5f * x * x);
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erf_abs = fmaf(-p * t, e, 1.f);
+  const float cdf = fmaf(0.5f, copysignf(erf_abs, x), 0.5f);
+  return fmaf(x * 0.3989422804014327f, e, cdf);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
   float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
   float pdf = 0.3989422804014327f * expf(-0.5f * x * x);

@@ -691,6 +691,20 @@ __device__ __forceinline__ void sts_row_bf16mn(unsigned char* op, int r, const f
     *reinterpret_cast<uint4*>(base + (4 + q) * 2048) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
+// lane l <- sum over rows [row0, row0 + 32) of column l of a 128-byte-swizzled [128][32] tile (conflict-free: the 32
+// lanes read the 32 words of one row).  Replaces a 31-shuffle register transpose and needs no register array.
+__device__ __forceinline__ float colsum_tile(const float* tile, int row0, int lane) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const int q = lane >> 2, w = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    a0 += tile[(row0 + i) * 32 + ((q ^ ((row0 + i) & 7)) << 2) + w];
+    a1 += tile[(row0 + i + 1) * 32 + ((q ^ ((row0 + i + 1) & 7)) << 2) + w];
+    a2 += tile[(row0 + i + 2) * 32 + ((q ^ ((row0 + i + 2) & 7)) << 2) + w];
+    a3 += tile[(row0 + i + 3) * 32 + ((q ^ ((row0 + i + 3) & 7)) << 2) + w];
+  }
+  return (a0 + a1) + (a2 + a3);
+}
 __device__ __forceinline__ constexpr uint32_t idesc_bf16_mn(int M, int N) {
   return idesc_f16_mn(M, N, true, true) | (1u << 7) | (1u << 10);
 }
@@ -768,6 +782,10 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
         if (tile < 0) continue;
         if (u > 0) mbar_wait(&empty[s], (uint32_t)((u - 1) & 1));
         float* st = ST + s * stage_floats;
+#ifdef B2_CHECK
+        if (s < 3) reinterpret_cast<volatile int*>(tmem_s + 1)[s] = u;      // use index of stage s, published before the barrier is armed
+        __threadfence_block();
+#endif
         const bool with_x = c == 0;
         mbar_expect_tx(&full[s], ((has_aux ? 2u : 1u) + (with_x ? 1u : 0u)) * LT * 128u);
         tma_load_tile_at(st, &tmDY, c * 32, tile * LT, &full[s]);
@@ -834,12 +852,28 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
       float* st = ST + s_cur * stage_floats;
       const int row0 = tile * LT;
       const long long t = (long long)row0 + r;
+      // With three stages the uses of a stage alternate between the two groups, and a group can get here while the other
+      // group's load into this stage - the previous phase of full[s] - is still in flight: a parity wait for phase u is
+      // then satisfied at once by the completed phase u - 2 and the rows of the tile before last are read (seen on the
+      // GPU once slow accumulating stores starved the ring).  The stage's previous release, empty[s] phase u - 1, orders
+      // it: that barrier can only be in phase u - 1 or u here (u - 2 was this group's own release, u needs this group's
+      // arrivals), so its parity is unambiguous, and behind it full[s] is in phase u or u + 1.
+      if (u_cur > 0) mbar_wait(&empty[s_cur], (uint32_t)((u_cur - 1) & 1));
       mbar_wait(&full[s_cur], (uint32_t)(u_cur & 1));
+      const int wrow = (warp & 3) * 32;          // first row of this warp inside the tile
       float dz[32];
       lds_row_sw(dz, st, r);
+      // Column sums (db, dgamma, dbeta) are taken from shared memory: a row lands in (or already is in) a tile slot of
+      // the stage that this thread owns, and lane l adds up column l over the warp's 32 rows.
       if (LN) {
         float sv[32];
         lds_row_sw(sv, st + TSW, r);
+        acc_dbe += colsum_tile(st, wrow, lane);                // dY tile as the TMA unit wrote it
+#ifdef B2_CHECK
+        if (t < a.T && sv[0] != (float)t && lane == 0)      // probe build: tests/probe/bwd2_acc_probe.py MARK=1 writes the row index into S[:, 0]
+          printf("[b2check] cta %d warp %d tile %d (k %d, stage %d use %d, producer armed use %d): S[row][0] = %.0f, expected %lld (tile %d)\n", (int)blockIdx.x, warp, tile, k,
+                 s_cur, u_cur, s_cur < 3 ? reinterpret_cast<volatile int*>(tmem_s + 1)[s_cur] : -1, sv[0], t, (int)(sv[0] / 128));
+#endif
         float mean = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) mean += sv[j];
@@ -848,21 +882,31 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
 #pragma unroll
         for (int j = 0; j < 32; ++j) { sv[j] -= mean; var = fmaf(sv[j], sv[j], var); }
         const float rstd = 1.f / sqrtf(var * (1.f / 32) + a.eps);
-        float m1 = 0.f, m2 = 0.f;
-        float gq[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { gq[j] = dz[j] * sG[j]; m1 += gq[j]; m2 = fmaf(gq[j], sv[j], m2); }
-        m1 *= (1.f / 32); m2 *= (1.f / 32) * rstd;
         {
           float tg[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) tg[j] = dz[j] * rstd * sv[j];
-          acc_dg += warp_colsum32(tg, lane);
-          acc_dbe += warp_colsum32(dz, lane);
+          sts_row_sw(st + TSW, r, tg);                         // own S row: consumed
         }
+        float m1 = 0.f, m2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dz[j] = rstd * (gq[j] - m1 - sv[j] * rstd * m2);      // dS = dR
+        for (int j = 0; j < 32; ++j) { dz[j] *= sG[j]; m1 += dz[j]; m2 = fmaf(dz[j], sv[j], m2); }
+        m1 *= (1.f / 32); m2 *= (1.f / 32) * rstd;
+        __syncwarp();                                          // every lane: dY rows read (dbeta), dy * xhat rows written
+        acc_dg += colsum_tile(st + TSW, wrow, lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dz[j] = rstd * (dz[j] - m1 - sv[j] * rstd * m2);      // dS = dR
         if (store_dr) sts_row_sw(st, r, dz);     // staged over this thread's own (already consumed) dY row of the stage
+        if (dc.on) {
+          const uint32_t rh = drop_row_hash(dc, (uint64_t)t);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dz[j] *= drop_mult_row(dc, rh, j);
+        }
+        __syncwarp();                                          // every lane: dgamma column reads done
+        const float* dbsrc = st;                               // without dropout dZ = dR, which is staged already
+        if (dc.on || !store_dr) { sts_row_sw(st + TSW, r, dz); dbsrc = st + TSW; }
+        __syncwarp();
+        acc_db[0] += colsum_tile(dbsrc, wrow, lane);
       } else if (NCH == 1 && a.act != 0) {
         float av[32];
         lds_row_sw(av, st + TSW, r);
@@ -871,8 +915,15 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
           for (int j = 0; j < 32; ++j) dz[j] = av[j] > 0.f ? dz[j] : 0.f;
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dz[j] *= gelu_erf_grad(av[j]);
+          for (int j = 0; j < 32; ++j) dz[j] *= gelu_erf_grad_fast(av[j]);
         }
+        sts_row_sw(st + TSW, r, dz);                           // own row of the activation-input tile: consumed
+        __syncwarp();
+        acc_db[0] += colsum_tile(st + TSW, wrow, lane);
+      } else {
+        const float cs = colsum_tile(st, wrow, lane);          // dZ = dY: straight from the TMA-written tile
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) if (q == c) acc_db[q] += cs;
       }
       // The group's previous entry must have left the tensor core before its operand tiles and TMEM A region are rewritten.
       // When that entry closed a token tile, its dX is collected here, behind this entry's row arithmetic, and staged
@@ -906,11 +957,6 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
         }
       }
       if (r != 0) mbar_arrive(&empty[s_cur]);    // this thread is done with the stage (thread 0: once its stores have drained)
-      if (LN && dc.on) {
-        const uint32_t rh = drop_row_hash(dc, (uint64_t)t);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) dz[j] *= drop_mult_row(dc, rh, j);
-      }
       {
         float hi[32], lo[32];
 #pragma unroll
@@ -923,11 +969,6 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
       fence_before();
       if (r == 0) { tma_store_drained(); mbar_arrive(&empty[s_cur]); }
       mbar_arrive(&ready[g]);
-      {
-        const float cs = warp_colsum32(dz, lane);          // dz is dead after this
-#pragma unroll
-        for (int q = 0; q < NCH; ++q) if (q == c) acc_db[q] += cs;
-      }
       prev_row0 = row0;
       ++k;
       // next own entry
@@ -1135,6 +1176,12 @@ static int lin_tc_bwd2_launch(K k, size_t smem, cudaStream_t st, const char* wha
   rc = make_tile_map(&tmDX, a.dX, a.lddx, a.T, what); if (rc) return rc;
   const int ntiles = (a.T + LT - 1) / LT;
   k<<<ntiles < ki.sms ? ntiles : ki.sms, B2T, smem, st>>>(a, tmDY, tmAUX, tmX, tmDR, tmDX);
+  if (getenv("VAESNE_BWD2_SYNC")) {
+    const cudaError_t e = cudaStreamSynchronize(st);
+    fprintf(stderr, "[bwd2] %s T=%d N=%d act=%d dY=%p/%lld S=%p A=%p/%lld X=%p/%lld dR=%p/%lld acc=%d dX=%p/%lld acc=%d dW=%p db=%p dg=%p p=%g -> %s\n", what, a.T, a.N,
+            a.act, (const void*)a.dY, a.lddy, (const void*)a.S, (const void*)a.A, a.lda, (const void*)a.X, a.ldx, (void*)a.dR, a.lddr, a.dR_acc,
+            (void*)a.dX, a.lddx, a.dX_acc, (void*)a.dW, (void*)a.db, (void*)a.dgamma, (double)a.p_drop, cudaGetErrorString(e));
+  }
   return check_launch(what);
 }
 static int lin_tc_bwd_one(const LinBwd& a, cudaStream_t st) {

@@ -486,6 +486,7 @@ def main():
             gbs = T * 128.0 * tensors / (lv["avg_ms"] * 1e-3) / 1e9
             roof["hbm_kernel"] = {"kernel": f"{lk[0]}[T={T},K={Kd},N={Nd}] (lin_tc_* kernels)", "bound": "hbm", "achieved": gbs, "peak": pk["hbm"],
                                   "unit": "GB/s", "frac": gbs / pk["hbm"], "bytes_per_token": 128.0 * tensors,
+                                  "traffic": (lambda t: None if t is None else int(t * T))(traffic_tab.get("per_token", {}).get(lk[0])),
                                   "share_of_step": lv["total_ms"] / tot, "avg_ms": lv["avg_ms"],
                                   "note": "inputs partly L2-resident inside the step; tests/probe/lin_bench.py times the same kernels cold"}
         if rank == 0:

@@ -37,6 +37,9 @@ def main():
     ap.add_argument("fwd"); ap.add_argument("bwd")
     ap.add_argument("--rows", type=int, default=1024); ap.add_argument("--lq", type=int, default=982); ap.add_argument("--lk", type=int, default=982)
     ap.add_argument("--sha", default=os.path.join(ROOT, "gpurun_out", "r2_ncu_src.sha256"))
+    ap.add_argument("--lin-bwd-ln", default=None, help="ncu --set full report of lin_tc_bwd2_kernel<LayerNorm> from tests/probe/lin_bench.py")
+    ap.add_argument("--lin-fwd-ln", default=None, help="same for lin_tc_fwd_kernel<LayerNorm>")
+    ap.add_argument("--tokens", type=int, default=1005568, help="token count of tests/probe/lin_bench.py")
     a = ap.parse_args()
     sha = open(a.sha).read().split()[0]
     tab = {"_source": f"dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full --clock-control none on tests/probe/attn_tc_check.py "
@@ -46,6 +49,12 @@ def main():
         kname, tot, dur = dram_bytes(rep)[0]
         tab["per_row"][f"{name}|{a.lq}|{a.lk}"] = tot / a.rows
         tab["kernels"][name] = {"kernel": kname, "dram_bytes": tot, "ncu_duration": dur, "report": os.path.basename(rep)}
+    tab["per_token"] = {}
+    for name, rep in (("lin_bwd_ln", a.lin_bwd_ln), ("lin_fwd_ln", a.lin_fwd_ln)):
+        if rep:
+            kname, tot, dur = dram_bytes(rep)[0]
+            tab["per_token"][name] = tot / a.tokens
+            tab["kernels"][name] = {"kernel": kname, "dram_bytes": tot, "ncu_duration": dur, "tokens": a.tokens, "report": os.path.basename(rep)}
     path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     json.dump(tab, open(path, "w"), indent=1)
     print(open(path).read())

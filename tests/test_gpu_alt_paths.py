@@ -57,3 +57,16 @@ def test_bright_spectra_with_the_fp32_attention_meets_the_contract_on_every_tens
            "import model_cases as MC\nl, w = MC.run_bright_case('bright_spec_elbo', 'cuda')\nassert w[0] < 1e-4, w\nprint('ok', w)\n"
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, VAESNE_NO_TC="1"), capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("mode", ["0", "2"])
+def test_linear_backward_kernels_in_both_dispatch_modes(mode):
+    """VAESNE_LIN_BWD2=2 sends every eligible linear backward (any token count) through the pipelined warp-specialised kernel,
+    =0 through the tile-serial one; the default picks by token count, so the small cases only see one of them otherwise."""
+    code = f"import sys, os\nROOT = {ROOT!r}\nsys.path[:0] = [os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'vaesne-dev_b200'), ROOT]\n" \
+           "import ops_cases as OC\n" \
+           "for c in OC.LIN_CASES:\n    OC.run_lin_case(c, 'cuda')\n" \
+           "for kind in ('ln', 'plain', 'gelu', 'wide'):\n    OC.run_lin_accumulate_case(kind, 128 * 148 * 9 + 5, 'cuda')\n" \
+           "print('ok')\n"
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, VAESNE_LIN_BWD2=mode), capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

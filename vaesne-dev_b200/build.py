@@ -17,10 +17,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 if os.environ.get("VAESNE_TC_PROFILE"):      # probe build: per-phase clocks in attn_tc_dkv_kernel (tests/probe/attn_tc_check.py TC_PROF=1)
     FLAGS.append("-DVAESNE_TC_PROFILE")
-if os.environ.get("B2_CHECK"):
-    FLAGS.append("-DB2_CHECK")
-if os.environ.get("VAESNE_B2_PROF"):         # probe build: per-phase timers printed by lin_tc_bwd2_kernel
-    FLAGS.append("-DVAESNE_B2_PROF")
+if os.environ.get("B2_CHECK"):               # probe build: lin_tc_bwd2_kernel checks that a ring stage holds the expected tile
+    FLAGS.append("-DB2_CHECK")                # (tests/probe/bwd2_acc_probe.py MARK=1)
 
 
 def sources():

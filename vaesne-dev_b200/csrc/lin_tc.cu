@@ -1031,9 +1031,6 @@ __global__ void __launch_bounds__(B2T, 1) lin_tc_bwd2_kernel(LinBwd a, const __g
   }
   fence_before();
   __syncthreads();
-#ifdef VAESNE_B2_PROF
-  if (tid == 0 && blockIdx.x == 0) printf("[b2prof] LN %d NCH %d tiles %d\n", (int)LN, NCH, ntiles);
-#endif
   if (warp == 0) { fence_after(); tmem_dealloc<COLS>(tb); }
 }
 
@@ -1176,7 +1173,7 @@ static int lin_tc_bwd2_launch(K k, size_t smem, cudaStream_t st, const char* wha
   rc = make_tile_map(&tmDX, a.dX, a.lddx, a.T, what); if (rc) return rc;
   const int ntiles = (a.T + LT - 1) / LT;
   k<<<ntiles < ki.sms ? ntiles : ki.sms, B2T, smem, st>>>(a, tmDY, tmAUX, tmX, tmDR, tmDX);
-  if (getenv("VAESNE_BWD2_SYNC")) {
+  if (getenv("VAESNE_BWD2_SYNC")) {          // diagnosis: synchronise and print the arguments of every launch with its outcome
     const cudaError_t e = cudaStreamSynchronize(st);
     fprintf(stderr, "[bwd2] %s T=%d N=%d act=%d dY=%p/%lld S=%p A=%p/%lld X=%p/%lld dR=%p/%lld acc=%d dX=%p/%lld acc=%d dW=%p db=%p dg=%p p=%g -> %s\n", what, a.T, a.N,
             a.act, (const void*)a.dY, a.lddy, (const void*)a.S, (const void*)a.A, a.lda, (const void*)a.X, a.ldx, (void*)a.dR, a.lddr, a.dR_acc,

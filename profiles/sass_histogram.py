@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "vaesne-dev_b200", "lib", "libvaesne_b200.so")
-WATCH = ["UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "MUFU.EX2", "MUFU.RCP", "MUFU.LG2",
+WATCH = ["UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTCBAR", "SYNCS", "MUFU.EX2", "MUFU.RCP", "MUFU.LG2",
          "FFMA2", "FADD2", "FMUL2", "F2FP", "RED", "ATOM", "LDS", "STS", "LDG", "STG", "LDL", "STL", "BAR.SYNC", "ELECT"]
 
 

@@ -5,21 +5,24 @@
 // Same arithmetic as lin.cu (its docstring cites the reference lines); restructured for sm_100a because these
 // kernels move 384..640 B per token and must run at HBM speed:
 //
-//   * every global access is coalesced: 128-token tiles travel global -> shared with 16-byte cp.async into
-//     rows padded to 144 B, and results leave through the same padded tiles with 16-byte coalesced stores.
-//     A thread then reads / writes ITS row with conflict-free 16-byte shared accesses (stride 36 words).
+//   * every global access is coalesced and moved in 128-token tiles: the forward and the pipelined backward use the TMA
+//     unit (cp.async.bulk.tensor, 128-byte swizzle: a thread reads / writes ITS row with conflict-free 16-byte shared
+//     accesses), the round-1 backward 16-byte cp.async into rows padded to 144 B.
 //   * thread r owns token r of the tile = TMEM lane r: the LayerNorm / activation / dropout epilogues are
-//     plain per-thread register code, no shuffles.
+//     plain per-thread register code.
 //   * the 32-wide contractions run on the tensor core: the row is split into tf32 hi + lo parts and stored
 //     to TMEM as the A operand (tcgen05.st), W (hi + lo, K-major canonical layout) is staged once per CTA,
 //     3 MMAs per 8-wide K step restore fp32-level products (kind::tf32 truncates its inputs), fp32
 //     accumulation in TMEM, one elected lane issues, tcgen05.commit -> mbarrier.
-//   * dW is a contraction over the 128 tokens of the tile: dZ^T and X^T are written (conflict-free, 144-byte
-//     chunk stride) as K-major operands, 16 MMAs per tile accumulate into TMEM across ALL tiles of the
-//     persistent CTA, and are flushed with one atomicAdd per element per CTA at the end.  Operands are
-//     rounded to nearest tf32 (unbiased; the sum runs over every token of the batch).
-//   * db / dgamma / dbeta: fp32 butterfly transpose-reductions (31 shuffles per 32 columns), shared-memory
-//     accumulators, one atomicAdd per element per CTA.
+//   * dW is a contraction over the 128 tokens of the tile, accumulated in TMEM across ALL tiles of the persistent CTA:
+//     MN-major bf16 hi + lo operand tiles and kind::f16 MMAs in the pipelined backward (lin_tc_bwd2_kernel), transposed
+//     tf32 operands in the round-1 backward (lin_tc_bwd_kernel); the parts are summed in shared memory and flushed with
+//     one coalesced atomicAdd per 128-byte line per CTA.
+//   * db / dgamma / dbeta: column sums read column-wise from the swizzled shared-memory tiles (pipelined backward) or
+//     fp32 butterfly transpose-reductions (round-1 backward), shared-memory accumulators, one atomicAdd per element per CTA.
+// Kernels: lin_tc_fwd_kernel (3 CTAs per SM), lin_tc_bwd2_kernel (one warp-specialised CTA per SM: TMA producer warp, MMA
+// issuer warp, two row groups; the big calls of a training step), lin_tc_bwd_kernel (two CTAs per SM; small token counts,
+// dX-only / dW-only calls, the Xadd heads).
 #include "common.cuh"
 #include "vaesne_b200.h"
 #include "lin_args.cuh"
